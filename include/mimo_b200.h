@@ -1,0 +1,191 @@
+/* mimo_b200.h -- C ABI of libmimo_b200.so (hand-written sm_100a CUDA kernels for the MIMO U-Net hot path).
+ *
+ * Drop-in boundary: the reference (antonbaumann/MIMO-Unet) has no FFI of its own; its hot path is
+ * the torch.nn call sites listed next to each entry point below (paths relative to the reference checkout). A
+ * binding replaces those call sites by passing raw device pointers and the current CUDA stream.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, POD structs; no torch / C++ types cross the boundary.
+ *   - every entry point returns 0 (MIMO_OK) or a negative mimo_status; the message is available from
+ *     mimo_last_error() (thread-local). No exceptions, no exit(), no CPU fallback.
+ *   - the library never allocates or frees device memory and never synchronises: all buffers (inputs,
+ *     outputs, workspaces) are owned by the caller; every call only enqueues work on `stream`
+ *     (a cudaStream_t passed as void*), so calls are safe inside CUDA-graph capture.
+ *   - activations are NHWC bf16, optionally with a 1-pixel reflect halo and as a channel slice of a wider
+ *     buffer: see mimo_act_t.
+ */
+#ifndef MIMO_B200_H
+#define MIMO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MIMO_B200_VERSION 100
+
+typedef enum {
+  MIMO_OK = 0,
+  MIMO_ERR_ARG = -1,     /* bad shape / argument */
+  MIMO_ERR_ALIGN = -2,   /* pointer or pitch alignment */
+  MIMO_ERR_CUDA = -3,    /* CUDA runtime / driver error (launch, tensor-map encode, ...) */
+  MIMO_ERR_ARCH = -4,    /* device is not sm_100 */
+  MIMO_ERR_STATE = -5    /* plan not bound / call order */
+} mimo_status;
+
+/* NHWC bf16 activation view.
+ * element (n,h,w,c) at ptr[((n*(h_+2*pad) + h+pad)*(w_+2*pad) + w+pad)*cpitch + c_off + c]   (bf16 elements) */
+typedef struct {
+  void* ptr;   /* base of the whole buffer (16-byte aligned) */
+  int n, h, w; /* logical (un-haloed) extent */
+  int pad;     /* 0, or 1 = one-pixel reflect halo stored around every image */
+  int cpitch;  /* channels per pixel in memory, multiple of 8 */
+  int c_off;   /* first channel of the view */
+  int c;       /* channels of the view */
+} mimo_act_t;
+
+int mimo_version(void);
+const char* mimo_last_error(void);
+/* 0 if the current device is sm_100 (B200), MIMO_ERR_ARCH otherwise */
+int mimo_check_device(void);
+
+/* ------------------------------------------------------------------ layout ------------------------------- */
+/* fp32 NCHW image (element (b,c,h,w) at x[b*sb + c*sc + h*W + w]) -> bf16 NHWC view with reflect halo.
+ * gather (device int64[n], may be NULL) remaps the batch index: folds apply_input_transform's
+ * index_select+stack (mimo/models/utils.py:38-41) into the load. */
+int mimo_pack_input(const float* x, long long sb, long long sc, const long long* gather, mimo_act_t out, void* stream);
+/* OIHW fp32 conv weight -> bf16 [9][cout][cin_pitch] (fprop) and flipped/transposed [9][cin][cout_pitch] (dgrad,
+ * may be NULL). Pitches are multiples of 8. */
+int mimo_weight_pack(const float* w_oihw, int cout, int cin, void* w_fprop, int cin_pitch, void* w_dgrad, int cout_pitch,
+                     void* stream);
+
+/* ------------------------------------------------------------------ convolution -------------------------- */
+/* nn.Conv2d(k=3, padding=1, padding_mode="reflect") forward, bias-free (components.py:23,26) -- tcgen05/TMA
+ * implicit GEMM. mode 0: `in` is a pad==1 view, output domain h x w. mode 1 (input gradient): `in` is the
+ * pad==0 output gradient, w_packed the dgrad pack, output domain (h+2) x (w+2) (padded-domain gradient whose
+ * halo is folded back by mimo_grad_gather). out: bf16 [n][oh][ow][out_cpitch].
+ * stat_sum/stat_sq (may be NULL): fp32 [mimo_conv3x3_m_tiles()][out_cpitch] per-tile partial sums of the stored
+ * outputs and their squares (training-mode BatchNorm statistics). bias (may be NULL) / relu: fused epilogue. */
+int mimo_conv3x3_m_tiles(int n, int out_h, int out_w);
+int mimo_conv3x3(mimo_act_t in, int mode, const void* w_packed, int cout, int cin_pitch, void* out, int out_cpitch,
+                 float* stat_sum, float* stat_sq, const float* bias, int relu, void* stream);
+/* weight gradient (cuDNN wgrad in the reference's autograd): dy pad==0 view, x pad==1 view of the conv input.
+ * dw_packed: fp32 [9][cout][cin_pitch] scratch (zeroed inside); grad_oihw receives (or accumulates) the OIHW grad. */
+int mimo_conv3x3_wgrad(mimo_act_t dy, mimo_act_t x, float* dw_packed, int cin_pitch, float* grad_oihw, int accumulate,
+                       void* stream);
+
+/* ------------------------------------------------------------------ BatchNorm / ReLU / pool / upsample ---- */
+/* nn.BatchNorm2d training statistics (components.py:24,27): reduces the conv partials, writes scale/shift
+ * (z = scale*y + shift), the saved mean / invstd, updates running_mean/var (momentum 0.1, unbiased var;
+ * conv_bias is added to the running mean because the stored conv output is bias-free) and num_batches_tracked. */
+int mimo_bn_finalize(const float* stat_sum, const float* stat_sq, int tiles, int cpitch, int c, double count,
+                     const float* gamma, const float* beta, const float* conv_bias, float* running_mean,
+                     float* running_var, long long* num_batches_tracked, float momentum, float eps, float* scale,
+                     float* shift, float* save_mean, float* save_invstd, void* stream);
+/* eval-mode affine from the running statistics */
+int mimo_bn_eval_affine(int c, const float* gamma, const float* beta, const float* conv_bias, const float* running_mean,
+                        const float* running_var, float eps, float* scale, float* shift, float* save_mean,
+                        float* save_invstd, void* stream);
+/* BN apply + ReLU (+ Dropout2d keep-scale [n][c], may be NULL) (+ MaxPool2d(2) into `pool`, may be NULL), writing
+ * the reflect halo of every output (components.py:24-29,48). y: raw conv output [n][h][w][y_cpitch]. */
+int mimo_bn_relu_apply(const void* y, int y_cpitch, const float* scale, const float* shift, const float* drop,
+                       mimo_act_t out, const mimo_act_t* pool, void* stream);
+/* nn.MaxPool2d(2[, return_indices]) (components.py:48); idx_nchw (may be NULL): int64 [n][c][h/2][w/2], h*W+w */
+int mimo_maxpool2x2(mimo_act_t in, mimo_act_t out, long long* idx_nchw, void* stream);
+/* nn.Upsample(x2, bilinear, align_corners=True) + F.pad to the skip size (components.py:78,112-115) into `out` */
+int mimo_upsample_bilinear2x(mimo_act_t in, mimo_act_t out, void* stream);
+int mimo_upsample_bilinear2x_bwd(mimo_act_t g_out, mimo_act_t g_in, int accumulate, void* stream);
+/* G = fold_reflect(dpad) [+ maxpool backward of gpool through act]; any of dpad / (gpool, act) may be NULL */
+int mimo_grad_gather(const mimo_act_t* dpad, const mimo_act_t* gpool, const mimo_act_t* act, mimo_act_t g_out,
+                     int accumulate, void* stream);
+/* BN + ReLU (+dropout) backward: dy, dgamma, dbeta (dbias_conv == 0 in training). part: fp32 scratch of
+ * mimo_bn_bwd_scratch_floats(c) floats; s1s2: fp32 [2][c]. */
+size_t mimo_bn_bwd_scratch_floats(int c);
+int mimo_bn_relu_bwd(mimo_act_t g, const void* y, int y_cpitch, const float* scale, const float* shift,
+                     const float* save_mean, const float* save_invstd, const float* drop, int training, float* part,
+                     float* s1s2, float* dgamma, float* dbeta, float* dbias, int accumulate, void* dy, int dy_cpitch,
+                     void* stream);
+
+/* ------------------------------------------------------------------ heads / loss / aggregation ------------ */
+/* OutConv 1x1 (components.py:123-129): out fp32 planes, element (n,k,h,w) at out[n*out_bstride + k*h*w + ...] */
+int mimo_head1x1(mimo_act_t feat, const float* w, const float* bias, int k, float* out, long long out_bstride, void* stream);
+size_t mimo_head1x1_bwd_scratch_floats(int k, int c);
+int mimo_head1x1_bwd(mimo_act_t feat, const float* w, int k, const float* dout, long long out_bstride,
+                     const float* grad_scale, mimo_act_t g_feat, float* part, float* dw, float* db, int accumulate,
+                     void* stream);
+
+/* LaplaceNLL.forward (mimo/losses.py:132-164) over [rows][cols] fp32 with per-tensor row strides.
+ * out_elem (may be NULL): elementwise loss [rows*cols]; out_mean (may be NULL): scalar mean, needs `part`
+ * (mimo_laplace_scratch_floats() floats). */
+size_t mimo_laplace_scratch_floats(void);
+int mimo_laplace_nll_fwd(const float* mu, long long mu_rs, const float* log_s, long long ls_rs, const float* y,
+                         long long y_rs, const float* mask, long long m_rs, long long rows, long long cols, float eps_min,
+                         float eps_max, float* out_elem, float* part, float* out_mean, void* stream);
+/* gradients w.r.t. mu / log_s (contiguous outputs); upstream is elementwise [rows*cols] or a device scalar */
+int mimo_laplace_nll_bwd(const float* mu, long long mu_rs, const float* log_s, long long ls_rs, const float* y,
+                         long long y_rs, const float* mask, long long m_rs, long long rows, long long cols, float eps_min,
+                         float eps_max, const float* upstream, int upstream_is_scalar, float upstream_scale, float* g_mu,
+                         float* g_log_s, void* stream);
+
+/* LossBuffer (mimo/models/mimo_components/loss_buffer.py:18-74) kept on the device */
+size_t mimo_lossbuffer_bytes(int subnetworks, int buffer_size);
+int mimo_lossbuffer_init(void* state, int subnetworks, int buffer_size, float temperature, void* stream);
+int mimo_lossbuffer_get_weights(const void* state, float* weights, void* stream);
+int mimo_lossbuffer_add(void* state, const float* loss, void* stream);
+
+/* _calculate_train_loss + loss.backward seed (mimo/models/mimo_unet.py:223-247,138) in one pass:
+ * out fp32 [B][S][2C][H][W]; y element (b,s,j) at y[src_b*y_bs + s*y_ss + j], src_b = gather[s*B+b] if gather;
+ * weights come from lb_state (read before the new loss is added), from fixed_w, or are 1.
+ * Writes loss[S], weights[S], weighted[1] = mean_s(w_s*loss_s) and (if dout) d weighted / d out. */
+size_t mimo_laplace_train_scratch_floats(int batch, int subnetworks, int c, long long hw);
+int mimo_laplace_nll_train(const float* out, const float* y, long long y_bs, long long y_ss, const float* mask,
+                           long long m_bs, long long m_ss, const long long* gather, int batch, int subnetworks, int c,
+                           long long hw, float eps_min, float eps_max, void* lb_state, const float* fixed_w,
+                           int update_buffer, float* dout, float* part, float* loss, float* weights, float* weighted,
+                           void* stream);
+int mimo_scale_by_scalar(float* x, long long n, const float* scalar, void* stream);
+
+/* compute_uncertainties (mimo/models/utils.py:76-101): element (b,s,j) at p[b*bs + s*ss + j], j < inner */
+int mimo_ensemble_aggregate(const float* p1, long long p1_bs, long long p1_ss, const float* p2, long long p2_bs,
+                            long long p2_ss, int batch, int members, long long inner, float* mean, float* aleatoric_var,
+                            float* epistemic_var, void* stream);
+
+/* ------------------------------------------------------------------ whole-network executor ---------------- */
+/* MimoUNet.forward / autograd backward (mimo/models/mimo_components/model.py:94-117), bilinear path. */
+typedef struct {
+  int in_channels, out_channels, num_subnetworks, filter_base_count;
+  int batch, height, width;
+} mimo_unet_config_t;
+typedef struct mimo_unet_plan mimo_unet_plan_t;
+
+int mimo_unet_plan_create(const mimo_unet_config_t* cfg, mimo_unet_plan_t** plan);
+void mimo_unet_plan_destroy(mimo_unet_plan_t* plan);
+size_t mimo_unet_workspace_bytes(const mimo_unet_plan_t* plan);
+/* number of state_dict entries expected by mimo_unet_bind, in MimoUNet.state_dict() order */
+int mimo_unet_num_state(const mimo_unet_plan_t* plan);
+int mimo_unet_num_double_convs(const mimo_unet_plan_t* plan);
+/* channels of the Dropout2d mask of double conv i (masks are [batch][channels] fp32 keep-scales) */
+int mimo_unet_dropout_channels(const mimo_unet_plan_t* plan, int i);
+/* state[i]: device pointer of state_dict entry i; grads[i]: fp32 gradient destination or NULL */
+int mimo_unet_bind(mimo_unet_plan_t* plan, void* workspace, size_t workspace_bytes, void* const* state, void* const* grads,
+                   int n);
+/* x fp32 [B][S][Cin][H][W]; gather: device int64 [S][B] or NULL; drop_masks[i]: device fp32 or NULL (may be NULL
+ * altogether); out fp32 [B][S][Cout][H][W]. training: batch statistics (+ running-stat update) vs running stats. */
+int mimo_unet_forward(mimo_unet_plan_t* plan, const float* x, const long long* gather, int training,
+                      const float* const* drop_masks, float* out, void* stream);
+/* dout fp32 like out; grad_scale: device scalar multiplier or NULL; dx: fp32 like x or NULL (input gradient,
+ * not supported together with gather). Parameter gradients are WRITTEN (accumulate==0) or ADDED to grads[]. */
+int mimo_unet_backward(mimo_unet_plan_t* plan, const float* dout, const float* grad_scale, float* dx, int accumulate,
+                       void* stream);
+/* test hook: geometry of a named intermediate ("<node>.<buf>", e.g. "core.down2.c1.y") inside the workspace.
+ * kind: 0 = bf16 activation view, 1 = fp32 vector of view->c floats. */
+int mimo_unet_debug_view(const mimo_unet_plan_t* plan, const char* name, mimo_act_t* view, int* kind);
+/* number of kernels the last forward / backward enqueued (bench.py's gpu_launches) */
+int mimo_unet_last_launches(const mimo_unet_plan_t* plan);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MIMO_B200_H */

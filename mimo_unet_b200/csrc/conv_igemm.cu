@@ -1,0 +1,364 @@
+// 3x3 convolution as an implicit GEMM on the 5th-generation tensor cores (tcgen05 + TMEM), fed by TMA.
+//
+// Replaces: nn.Conv2d(k=3, padding=1, padding_mode="reflect") forward (reference components.py:23,26)
+// and its input-gradient (cuDNN dgrad in the reference's autograd graph).
+//
+//   GEMM view   D[pixel, cout] = sum_{tap, cin} A[pixel + tap, cin] * Wp[tap][cout][cin]
+//   A operand   128 output pixels x 64 input channels per k-block, loaded by ONE 4-D TMA box
+//               (64 ch, tw, th, tn) straight out of the NHWC activation buffer. The tap shift is just a
+//               different box origin, so there is no im2col buffer. Reflect padding is materialised by the
+//               producer of the activation (1-pixel halo), so fprop is a "valid" conv over the padded
+//               buffer; dgrad runs the same kernel over the unpadded dY with origin offset -2 and relies on
+//               TMA's zero fill for out-of-bounds (negative) coordinates.
+//   B operand   BLOCK_N couts x 64 cins of the packed bf16 weights for that tap (3-D TMA box).
+//   Accumulator fp32 in TMEM, double buffered (2 x BLOCK_N columns) so the epilogue of tile i overlaps the
+//               MMAs of tile i+1. Persistent CTAs, static round-robin tile schedule.
+//   Epilogue    tcgen05.ld -> bf16 -> smem staging -> coalesced 16-byte global stores, plus (fprop, training)
+//               per-channel sum / sum-of-squares partials of the *stored* bf16 values for BatchNorm.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
+// warps 2..5 = epilogue (TMEM lane quarter = warp_idx % 4).
+#include "common.cuh"
+#include "ops.h"
+
+namespace mimo {
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;                      // bf16 elements = one 128-byte swizzle row
+constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KB
+constexpr int kThreads = 192;
+constexpr int kMaxStages = 8;
+
+struct ConvParams {
+  int n_img, out_h, out_w;    // output domain
+  int tw, th, tn;             // pixel tile (tw*th*tn == 128), powers of two
+  int tw_shift, th_shift;
+  int tiles_w, tiles_h, tiles_n, m_tiles, n_tiles;
+  int block_n;                // multiple of 16, <= 256
+  int cin_chunks;             // ceil(Cin / 64)
+  int origin;                 // 0 (fprop over padded input) or -2 (dgrad over unpadded dY)
+  int cout;                   // true number of output channels
+  int out_cpitch;             // channels per output pixel in memory (multiple of 8, >= cout)
+  int stages;
+  int b_stage_bytes;
+  int stage_pitch;            // epilogue staging row pitch in bytes
+  bf16* out;                  // [n_img][out_h][out_w][out_cpitch]
+  float* stat_sum;            // [m_tiles][out_cpitch] or nullptr
+  float* stat_sq;             // [m_tiles][out_cpitch] or nullptr
+  const float* bias;          // optional per-cout bias added before the store (eval path), or nullptr
+  int relu;                   // apply ReLU before the store (eval path with folded BN)
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_w,
+                     const ConvParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages x A][stages x B][staging][barriers]
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem_a + (size_t)p.stages * kABytes;
+  uint8_t* smem_stage = smem_b + (size_t)p.stages * p.b_stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stage + (size_t)kBlockM * p.stage_pitch);
+  uint64_t* full_bar = bars;                     // [stages]
+  uint64_t* empty_bar = bars + kMaxStages;       // [stages]
+  uint64_t* tmem_full = bars + 2 * kMaxStages;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;          // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint32_t* row_valid = tmem_ptr + 4;            // [128] validity of each tile row (epilogue scratch)
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int k_blocks = 9 * p.cin_chunks;
+  const uint32_t tmem_cols = (2 * p.block_n <= 32) ? 32 : (2 * p.block_n <= 64) ? 64 : (2 * p.block_n <= 128) ? 128
+                             : (2 * p.block_n <= 256) ? 256 : 512;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_in);
+    prefetch_tmap(&tmap_w);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < p.stages; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(&tmem_full[a], 1);
+        mbar_init(&tmem_empty[a], 4);  // one arrive per epilogue warp
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr, tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int mt = t / p.n_tiles, nt = t - mt * p.n_tiles;
+        const int twi = mt % p.tiles_w;
+        const int thi = (mt / p.tiles_w) % p.tiles_h;
+        const int tni = mt / (p.tiles_w * p.tiles_h);
+        const int w0 = twi * p.tw + p.origin, h0 = thi * p.th + p.origin, n0 = tni * p.tn;
+        const int co0 = nt * p.block_n;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          const int tap = kb / p.cin_chunks;
+          const int cc = kb - tap * p.cin_chunks;
+          const int kh = tap / 3, kw = tap - kh * 3;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], kABytes + p.b_stage_bytes);
+          tma_load_4d(&tmap_in, &full_bar[stage], smem_a + (size_t)stage * kABytes, cc * kBlockK, w0 + kw, h0 + kh, n0);
+          tma_load_3d(&tmap_w, &full_bar[stage], smem_b + (size_t)stage * p.b_stage_bytes, cc * kBlockK, co0, tap);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(kBlockM, p.block_n, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase[2] = {0, 0};
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase[acc] ^ 1);
+        tc_fence_after();
+        const uint32_t d_addr = tmem_base + (uint32_t)(acc * p.block_n);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + (size_t)stage * kABytes);
+          const uint32_t b_addr = smem_u32(smem_b + (size_t)stage * p.b_stage_bytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            const uint64_t ad = make_smem_desc(a_addr + k * 32, 16, 1024, kLayoutSW128);
+            const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, 1024, kLayoutSW128);
+            umma_bf16(d_addr, ad, bd, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);      // accumulator complete -> epilogue
+        acc_phase[acc] ^= 1;
+        acc ^= 1;
+      }
+    }
+  } else {
+    // ===================== epilogue (4 warps, 128 threads) =====================
+    const int q = warp & 3;                  // TMEM lane quarter owned by this warp
+    const int row = q * 32 + lane;           // accumulator row == pixel index inside the tile
+    const int et = threadIdx.x - 64;         // 0..127
+    int acc = 0;
+    uint32_t acc_phase[2] = {0, 0};
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int mt = t / p.n_tiles, nt = t - mt * p.n_tiles;
+      const int twi = mt % p.tiles_w;
+      const int thi = (mt / p.tiles_w) % p.tiles_h;
+      const int tni = mt / (p.tiles_w * p.tiles_h);
+      const int co0 = nt * p.block_n;
+      // my row's pixel
+      const int pw = twi * p.tw + (row & (p.tw - 1));
+      const int ph = thi * p.th + ((row >> p.tw_shift) & (p.th - 1));
+      const int pn = tni * p.tn + (row >> (p.tw_shift + p.th_shift));
+      const bool valid = (pw < p.out_w) && (ph < p.out_h) && (pn < p.n_img);
+      row_valid[row] = valid ? 1u : 0u;
+
+      mbar_wait(&tmem_full[acc], acc_phase[acc]);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.block_n);
+      uint8_t* my_row = smem_stage + (size_t)row * p.stage_pitch;
+      for (int c = 0; c < p.block_n; c += 16) {
+        float v[16];
+        tmem_ld16(t_addr + c, v);
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += (co0 + c + i < p.cout) ? __ldg(p.bias + co0 + c + i) : 0.f;
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
+        bf16x8 lo, hi;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          lo.v[i] = __float2bfloat16_rn(v[i]);
+          hi.v[i] = __float2bfloat16_rn(v[8 + i]);
+        }
+        *reinterpret_cast<bf16x8*>(my_row + c * 2) = lo;
+        *reinterpret_cast<bf16x8*>(my_row + c * 2 + 16) = hi;
+      }
+      // all TMEM reads of this warp are done -> hand the accumulator back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      acc_phase[acc] ^= 1;
+      acc ^= 1;
+
+      named_bar_sync(1, 128);  // staging tile complete
+
+      // ---- coalesced stores: 16-byte chunks, consecutive threads -> consecutive chunks of a pixel row ----
+      const int n_store = min(p.block_n, p.out_cpitch - co0);      // channels this tile owns in memory
+      const int chunks = n_store >> 3;                             // out_cpitch, co0 multiples of 8
+      for (int id = et; id < kBlockM * chunks; id += 128) {
+        const int r = id / chunks, ch = id - r * chunks;
+        if (!row_valid[r]) continue;
+        const int rw = twi * p.tw + (r & (p.tw - 1));
+        const int rh = thi * p.th + ((r >> p.tw_shift) & (p.th - 1));
+        const int rn = tni * p.tn + (r >> (p.tw_shift + p.th_shift));
+        const size_t pix = ((size_t)rn * p.out_h + rh) * p.out_w + rw;
+        const bf16x8 val = *reinterpret_cast<const bf16x8*>(smem_stage + (size_t)r * p.stage_pitch + ch * 16);
+        *reinterpret_cast<bf16x8*>(p.out + pix * p.out_cpitch + co0 + ch * 8) = val;
+      }
+      // ---- BatchNorm statistics of the stored values (per-tile partials, reduced deterministically later) ----
+      if (p.stat_sum != nullptr) {
+        for (int col = et; col < n_store; col += 128) {
+          float s = 0.f, sq = 0.f;
+          for (int r = 0; r < kBlockM; ++r) {
+            if (row_valid[r]) {
+              const float x = __bfloat162float(*reinterpret_cast<const bf16*>(smem_stage + (size_t)r * p.stage_pitch + col * 2));
+              s += x;
+              sq += x * x;
+            }
+          }
+          p.stat_sum[(size_t)mt * p.out_cpitch + co0 + col] = s;
+          p.stat_sq[(size_t)mt * p.out_cpitch + co0 + col] = sq;
+        }
+      }
+      named_bar_sync(1, 128);  // staging buffer free for the next tile
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+int pick_tile(int W, int H, int N, int* tw_o, int* th_o, int* tn_o) {
+  double best = 1e30;
+  for (int tw = 1; tw <= 128; tw <<= 1) {
+    for (int th = 1; tw * th <= 128; th <<= 1) {
+      const int tn = 128 / (tw * th);
+      const double tiles = (double)ceil_div(W, tw) * ceil_div(H, th) * ceil_div(N, tn);
+      const double cost = tiles * (1.0 + 0.5 / tw);
+      if (cost < best - 1e-9) {
+        best = cost;
+        *tw_o = tw; *th_o = th; *tn_o = tn;
+      }
+    }
+  }
+  return 0;
+}
+
+int ilog2(int v) { int s = 0; while ((1 << s) < v) ++s; return s; }
+
+}  // namespace
+
+int conv3x3_block_n(int cout) {
+  const int c16 = round_up(cout, 16);
+  if (c16 <= 256) return c16;
+  const int parts = ceil_div(c16, 256);
+  return round_up(ceil_div(c16, parts), 16);
+}
+
+int conv3x3_m_tiles(int n, int out_h, int out_w) {
+  int tw, th, tn;
+  pick_tile(out_w, out_h, n, &tw, &th, &tn);
+  return ceil_div(out_w, tw) * ceil_div(out_h, th) * ceil_div(n, tn);
+}
+
+// in      : activation view. mode 0 (fprop): pad == 1, output domain = in.H x in.W
+//                            mode 1 (dgrad): pad == 0, output domain = (in.H+2) x (in.W+2)
+// wpacked : bf16 [9][cout][cin_pitch] (cin contiguous), cin_pitch multiple of 8
+// out     : bf16 [N][out_h][out_w][out_cpitch]
+int conv3x3_launch(const ActView& in, int mode, const bf16* wpacked, int cout, int cin_pitch, bf16* out, int out_cpitch,
+                   float* stat_sum, float* stat_sq, const float* bias, int relu, cudaStream_t stream) {
+  MIMO_CHECK(mode == 0 || mode == 1, MIMO_ERR_ARG, "conv3x3: bad mode %d", mode);
+  MIMO_CHECK(in.pad == (mode == 0 ? 1 : 0), MIMO_ERR_ARG, "conv3x3: mode %d needs pad=%d input", mode, mode == 0 ? 1 : 0);
+  MIMO_CHECK(in.cpitch % 8 == 0 && in.c_off % 8 == 0, MIMO_ERR_ALIGN, "conv3x3: input cpitch/c_off must be multiples of 8 (got %d/%d)", in.cpitch, in.c_off);
+  MIMO_CHECK(cin_pitch % 8 == 0 && cin_pitch >= in.C, MIMO_ERR_ALIGN, "conv3x3: weight cin pitch %d invalid for C=%d", cin_pitch, in.C);
+  MIMO_CHECK(out_cpitch % 8 == 0 && out_cpitch >= cout, MIMO_ERR_ALIGN, "conv3x3: out_cpitch %d invalid for cout=%d", out_cpitch, cout);
+  MIMO_CHECK(((uintptr_t)in.base % 16) == 0 && ((uintptr_t)wpacked % 16) == 0 && ((uintptr_t)out % 16) == 0, MIMO_ERR_ALIGN,
+             "conv3x3: pointers must be 16-byte aligned");
+  MIMO_CHECK(in.H >= 2 && in.W >= 2, MIMO_ERR_ARG, "conv3x3: reflect padding needs H,W >= 2");
+
+  ConvParams p{};
+  p.n_img = in.N;
+  p.out_h = in.H + (mode == 1 ? 2 : 0);
+  p.out_w = in.W + (mode == 1 ? 2 : 0);
+  pick_tile(p.out_w, p.out_h, p.n_img, &p.tw, &p.th, &p.tn);
+  p.tw_shift = ilog2(p.tw);
+  p.th_shift = ilog2(p.th);
+  p.tiles_w = ceil_div(p.out_w, p.tw);
+  p.tiles_h = ceil_div(p.out_h, p.th);
+  p.tiles_n = ceil_div(p.n_img, p.tn);
+  p.m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  p.block_n = conv3x3_block_n(cout);
+  p.n_tiles = ceil_div(round_up(cout, 16), p.block_n);
+  p.cin_chunks = ceil_div(in.C, kBlockK);
+  p.origin = (mode == 1) ? -2 : 0;
+  p.cout = cout;
+  p.out_cpitch = out_cpitch;
+  p.b_stage_bytes = p.block_n * kBlockK * 2;
+  p.stage_pitch = p.block_n * 2 + 16;
+  p.out = out;
+  p.stat_sum = stat_sum;
+  p.stat_sq = stat_sq;
+  p.bias = bias;
+  p.relu = relu;
+  // the last n-tile may own fewer than block_n channels in memory; it must still be a multiple of 8
+  MIMO_CHECK((p.n_tiles - 1) * p.block_n < out_cpitch, MIMO_ERR_ARG, "conv3x3: n-tiling exceeds out_cpitch");
+
+  const int smem_budget = 227 * 1024 - 1024 /*align slack*/;
+  const int fixed = kBlockM * p.stage_pitch + (2 * kMaxStages + 4) * 8 + 16 + kBlockM * 4 + 64;
+  int stages = (smem_budget - fixed) / (kABytes + p.b_stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  MIMO_CHECK(stages >= 2, MIMO_ERR_ARG, "conv3x3: not enough shared memory for block_n=%d", p.block_n);
+  p.stages = stages;
+  const size_t smem_bytes = (size_t)stages * (kABytes + p.b_stage_bytes) + fixed + 1024;
+
+  // --- tensor maps ---
+  CUtensorMap tm_in, tm_w;
+  {
+    const int Hb = in.H + 2 * in.pad, Wb = in.W + 2 * in.pad;
+    uint64_t dims[4] = {(uint64_t)in.C, (uint64_t)Wb, (uint64_t)Hb, (uint64_t)in.N};
+    uint64_t strides[3] = {(uint64_t)in.cpitch * 2, (uint64_t)Wb * in.cpitch * 2, (uint64_t)Hb * Wb * in.cpitch * 2};
+    uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)p.tw, (uint32_t)p.th, (uint32_t)p.tn};
+    int rc = encode_tmap_bf16(&tm_in, in.base + in.c_off, 4, dims, strides, box, 1);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)cin_pitch, (uint64_t)cout, 9};
+    uint64_t strides[2] = {(uint64_t)cin_pitch * 2, (uint64_t)cout * cin_pitch * 2};
+    uint32_t box[3] = {(uint32_t)kBlockK, (uint32_t)p.block_n, 1};
+    int rc = encode_tmap_bf16(&tm_w, wpacked, 3, dims, strides, box, 1);
+    if (rc) return rc;
+  }
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    MIMO_CUDA(cudaFuncSetAttribute(conv3x3_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const int tiles = p.m_tiles * p.n_tiles;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  conv3x3_igemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(tm_in, tm_w, p);
+  MIMO_LAUNCH_CHECK();
+  return MIMO_OK;
+}
+
+}  // namespace mimo

@@ -1,0 +1,609 @@
+// Memory-bound NHWC bf16 kernels around the tensor-core convolutions: layout packing, BatchNorm
+// (training statistics finalize / apply / backward), ReLU, Dropout2d, 2x2 max-pool, bilinear x2
+// (align_corners=True) up-sampling, reflect-halo handling and their backward passes.
+//
+// Thread mapping everywhere: one thread = one pixel (or 2x2 pixel cell) x one group of 8 channels, channel
+// groups fastest, so a warp touches consecutive 16-byte chunks (coalesced, vectorised when aligned).
+#include "common.cuh"
+#include "ops.h"
+
+namespace mimo {
+namespace {
+
+constexpr int kBlock = 256;
+
+inline int grid_for(long long work) {
+  long long g = ceil_div_ll(work, kBlock);
+  const long long cap = (long long)num_sms() * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// Writes value vector to interior pixel (h,w) of a padded view and to every halo cell that mirrors it.
+__device__ __forceinline__ void store_with_halo(const ActView& o, int n, int h, int w, int c, int nvalid, const float v[8]) {
+  store8(o.base + o.pix(n, h, w) + c, nvalid, v);
+  if (o.pad == 0) return;
+  // reflect: halo row -1 mirrors row 1, halo row H mirrors row H-2 (same for columns)
+  const int hh = (h == 1) ? -1 : ((h == o.H - 2) ? o.H : -2);
+  const int ww = (w == 1) ? -1 : ((w == o.W - 2) ? o.W : -2);
+  const int hh2 = (o.H == 3 && h == 1) ? o.H : -2;  // H == 3: row 1 mirrors into both halos
+  const int ww2 = (o.W == 3 && w == 1) ? o.W : -2;
+  const int hs[3] = {h, hh, hh2};
+  const int ws[3] = {w, ww, ww2};
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    if (hs[a] == -2) continue;
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      if (ws[b] == -2 || (a == 0 && b == 0)) continue;
+      store8(o.base + o.pix(n, hs[a], ws[b]) + c, nvalid, v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// input packing: fp32 NCHW (strided) -> bf16 NHWC with reflect halo; optional batch gather
+// (folds models/utils.py:38-41 index_select+stack of apply_input_transform into the load)
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_input_kernel(const float* __restrict__ x, long long sb, long long sc, const long long* __restrict__ gather,
+                                  ActView o) {
+  const int Hp = o.H + 2 * o.pad, Wp = o.W + 2 * o.pad;
+  const long long total = (long long)o.N * Hp * Wp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int wp = (int)(i % Wp), hp = (int)((i / Wp) % Hp), n = (int)(i / ((long long)Wp * Hp));
+    const int h = reflect1(hp - o.pad, o.H), w = reflect1(wp - o.pad, o.W);
+    const long long b = gather ? gather[n] : n;
+    const float* src = x + b * sb + (long long)h * o.W + w;
+    bf16* dst = o.base + ((long long)(n * Hp + hp) * Wp + wp) * o.cpitch + o.c_off;
+    for (int c = 0; c < o.C; ++c) dst[c] = __float2bfloat16_rn(src[c * sc]);
+  }
+}
+
+// OIHW fp32 -> bf16 [9][cout][cin_pitch] (fprop) and flipped/transposed [9][cin][cout_pitch] (dgrad)
+__global__ void weight_pack_kernel(const float* __restrict__ w, int cout, int cin, bf16* __restrict__ wf, int cin_pitch,
+                                   bf16* __restrict__ wd, int cout_pitch) {
+  const int total_f = 9 * cout * cin_pitch;
+  const int total_d = wd ? 9 * cin * cout_pitch : 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total_f + total_d; i += gridDim.x * blockDim.x) {
+    if (i < total_f) {
+      const int ci = i % cin_pitch, co = (i / cin_pitch) % cout, tap = i / (cin_pitch * cout);
+      wf[i] = __float2bfloat16_rn(ci < cin ? w[((size_t)co * cin + ci) * 9 + tap] : 0.f);
+    } else {
+      const int j = i - total_f;
+      const int co = j % cout_pitch, ci = (j / cout_pitch) % cin, tap = j / (cout_pitch * cin);
+      // dgrad tap (a,b) uses W[kh=2-a][kw=2-b]  ->  flat tap index 8 - tap
+      wd[j] = __float2bfloat16_rn(co < cout ? w[((size_t)co * cin + ci) * 9 + (8 - tap)] : 0.f);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm statistics finalize (training): reduce per-tile partials, produce scale/shift, saved mean /
+// invstd for backward, and update the running estimates (momentum 0.1, unbiased running variance,
+// conv bias re-added to the running mean because the stored conv output is bias-free).
+// One block per channel.
+// ------------------------------------------------------------------------------------------------
+__global__ void bn_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ psq, int tiles, int cpitch, int C,
+                                   double count, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   const float* __restrict__ conv_bias, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, long long* __restrict__ nbt, float momentum, float eps, float* __restrict__ scale,
+                                   float* __restrict__ shift, float* __restrict__ save_mean, float* __restrict__ save_invstd) {
+  const int c = blockIdx.x;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int t = threadIdx.x; t < tiles; t += blockDim.x) {
+    s += (double)psum[(size_t)t * cpitch + c];
+    q += (double)psq[(size_t)t * cpitch + c];
+  }
+  __shared__ double sh_s[32], sh_q[32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { sh_s[warp] = s; sh_q[warp] = q; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double S = 0.0, Q = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { S += sh_s[i]; Q += sh_q[i]; }
+    const double mean = S / count;
+    double var = Q / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float g = gamma[c], b = beta[c];
+    scale[c] = g * invstd;
+    shift[c] = b - (float)mean * g * invstd;
+    save_mean[c] = (float)mean;
+    save_invstd[c] = invstd;
+    if (running_mean != nullptr) {
+      const float bias = conv_bias ? conv_bias[c] : 0.f;
+      const double unbiased = count > 1.0 ? var * (count / (count - 1.0)) : var;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * ((float)mean + bias);
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+      if (c == 0 && nbt != nullptr) *nbt += 1;
+    }
+  }
+}
+
+// eval-mode affine from the running statistics: z = scale*y + shift with the conv bias folded in
+__global__ void bn_eval_affine_kernel(int C, const float* gamma, const float* beta, const float* conv_bias, const float* rm,
+                                      const float* rv, float eps, float* scale, float* shift, float* save_mean,
+                                      float* save_invstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float invstd = rsqrtf(rv[c] + eps);
+  const float bias = conv_bias ? conv_bias[c] : 0.f;
+  scale[c] = gamma[c] * invstd;
+  shift[c] = beta[c] + (bias - rm[c]) * gamma[c] * invstd;
+  save_mean[c] = rm[c] - bias;  // so that x_hat = (y - save_mean) * invstd also holds in eval mode
+  save_invstd[c] = invstd;
+}
+
+// ------------------------------------------------------------------------------------------------
+// BN apply + ReLU (+ Dropout2d keep-scale) (+ 2x2 max-pool) with reflect-halo writes.
+// One thread = one 2x2 pixel cell x 8 channels.
+// ------------------------------------------------------------------------------------------------
+__global__ void bn_relu_apply_kernel(const bf16* __restrict__ y, int ycp, const float* __restrict__ scale,
+                                     const float* __restrict__ shift, const float* __restrict__ drop /*[N][C] or null*/,
+                                     ActView o, ActView pool, int do_pool) {
+  const int cells_h = (o.H + 1) >> 1, cells_w = (o.W + 1) >> 1;
+  const int groups = (o.C + 7) >> 3;
+  const long long total = (long long)o.N * cells_h * cells_w * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    long long r = i / groups;
+    const int cw = (int)(r % cells_w); r /= cells_w;
+    const int chh = (int)(r % cells_h);
+    const int n = (int)(r / cells_h);
+    const int c = g * 8, nv = min(8, o.C - c);
+    float sc[8], sh[8], dr[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      sc[k] = (k < nv) ? scale[c + k] : 0.f;
+      sh[k] = (k < nv) ? shift[c + k] : 0.f;
+      dr[k] = (drop && k < nv) ? drop[(size_t)n * o.C + c + k] : 1.f;
+    }
+    float mx[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) mx[k] = -INFINITY;
+    bool full = true;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int h = chh * 2 + dy, w = cw * 2 + dx;
+        if (h >= o.H || w >= o.W) { full = false; continue; }
+        float v[8];
+        load8(y + ((size_t)(n * o.H + h) * o.W + w) * ycp + c, nv, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          // the activation is STORED in bf16: pool over the stored value so indices/values agree with it
+          v[k] = __bfloat162float(__float2bfloat16_rn(fmaxf(fmaf(v[k], sc[k], sh[k]), 0.f) * dr[k]));
+          mx[k] = (v[k] > mx[k] || v[k] != v[k]) ? v[k] : mx[k];
+        }
+        store_with_halo(o, n, h, w, c, nv, v);
+      }
+    }
+    if (do_pool && full && chh < pool.H && cw < pool.W) store_with_halo(pool, n, chh, cw, c, nv, mx);
+  }
+}
+
+// stand-alone 2x2 max-pool (component-level API; optional int64 indices in PyTorch's h*W+w convention,
+// written for an NCHW [N][C][Hp][Wp] index tensor like nn.MaxPool2d(return_indices=True))
+__global__ void maxpool_kernel(ActView in, ActView o, long long* __restrict__ idx_nchw) {
+  const int groups = (o.C + 7) >> 3;
+  const long long total = (long long)o.N * o.H * o.W * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    long long r = i / groups;
+    const int w = (int)(r % o.W); r /= o.W;
+    const int h = (int)(r % o.H);
+    const int n = (int)(r / o.H);
+    const int c = g * 8, nv = min(8, o.C - c);
+    float mx[8]; int am[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { mx[k] = -INFINITY; am[k] = (2 * h) * in.W + 2 * w; }
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        float v[8];
+        load8(in.base + in.pix(n, 2 * h + dy, 2 * w + dx) + c, nv, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (v[k] > mx[k] || v[k] != v[k]) { mx[k] = v[k]; am[k] = (2 * h + dy) * in.W + 2 * w + dx; }
+      }
+    store_with_halo(o, n, h, w, c, nv, mx);
+    if (idx_nchw)
+      for (int k = 0; k < nv; ++k) idx_nchw[(((size_t)n * o.C + c + k) * o.H + h) * o.W + w] = am[k];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// bilinear x2, align_corners=True, then zero F.pad to the skip size (components.py:78,112-115), written
+// into a channel slice of the (padded, reflect-halo) concat buffer.
+// ------------------------------------------------------------------------------------------------
+__global__ void upsample_kernel(ActView in, ActView o, int off_h, int off_w) {
+  const int uh = 2 * in.H, uw = 2 * in.W;
+  const float rh = uh > 1 ? (float)(in.H - 1) / (float)(uh - 1) : 0.f;
+  const float rw = uw > 1 ? (float)(in.W - 1) / (float)(uw - 1) : 0.f;
+  const int groups = (o.C + 7) >> 3;
+  const long long total = (long long)o.N * o.H * o.W * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    long long r = i / groups;
+    const int w = (int)(r % o.W); r /= o.W;
+    const int h = (int)(r % o.H);
+    const int n = (int)(r / o.H);
+    const int c = g * 8, nv = min(8, o.C - c);
+    float out[8];
+    const int y = h - off_h, x = w - off_w;
+    if (y < 0 || y >= uh || x < 0 || x >= uw) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) out[k] = 0.f;
+    } else {
+      const float sy = rh * y, sx = rw * x;
+      const int y0 = (int)sy, x0 = (int)sx;
+      const int y1 = min(y0 + 1, in.H - 1), x1 = min(x0 + 1, in.W - 1);
+      const float ly = sy - y0, lx = sx - x0;
+      float a[8], b[8], cc[8], d[8];
+      load8(in.base + in.pix(n, y0, x0) + c, nv, a);
+      load8(in.base + in.pix(n, y0, x1) + c, nv, b);
+      load8(in.base + in.pix(n, y1, x0) + c, nv, cc);
+      load8(in.base + in.pix(n, y1, x1) + c, nv, d);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        out[k] = (1.f - ly) * ((1.f - lx) * a[k] + lx * b[k]) + ly * ((1.f - lx) * cc[k] + lx * d[k]);
+    }
+    store_with_halo(o, n, h, w, c, nv, out);
+  }
+}
+
+// backward of the above as a gather: every source pixel sums the destination pixels that sampled it
+__global__ void upsample_bwd_kernel(ActView gdst /*unpadded, skip-sized*/, ActView gsrc /*unpadded*/, int off_h, int off_w,
+                                    int accumulate) {
+  const int ih = gsrc.H, iw = gsrc.W, uh = 2 * ih, uw = 2 * iw;
+  const float rh = uh > 1 ? (float)(ih - 1) / (float)(uh - 1) : 0.f;
+  const float rw = uw > 1 ? (float)(iw - 1) / (float)(uw - 1) : 0.f;
+  const int groups = (gsrc.C + 7) >> 3;
+  const long long total = (long long)gsrc.N * ih * iw * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    long long r = i / groups;
+    const int sx = (int)(r % iw); r /= iw;
+    const int sy = (int)(r % ih);
+    const int n = (int)(r / ih);
+    const int c = g * 8, nv = min(8, gsrc.C - c);
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    // destination rows whose y0 or y1 equals sy lie in a small window around sy / rh
+    const int ylo = max(0, (int)floorf((sy - 1) / fmaxf(rh, 1e-6f)) - 1), yhi = min(uh - 1, (int)ceilf((sy + 1) / fmaxf(rh, 1e-6f)) + 1);
+    const int xlo = max(0, (int)floorf((sx - 1) / fmaxf(rw, 1e-6f)) - 1), xhi = min(uw - 1, (int)ceilf((sx + 1) / fmaxf(rw, 1e-6f)) + 1);
+    for (int y = ylo; y <= yhi; ++y) {
+      const float fy = rh * y;
+      const int y0 = (int)fy, y1 = min(y0 + 1, ih - 1);
+      const float ly = fy - y0;
+      const float wy = (y0 == sy ? 1.f - ly : 0.f) + (y1 == sy ? ly : 0.f);
+      if (wy == 0.f) continue;
+      const int dh = y + off_h;
+      if (dh < 0 || dh >= gdst.H) continue;
+      for (int x = xlo; x <= xhi; ++x) {
+        const float fx = rw * x;
+        const int x0 = (int)fx, x1 = min(x0 + 1, iw - 1);
+        const float lx = fx - x0;
+        const float wx = (x0 == sx ? 1.f - lx : 0.f) + (x1 == sx ? lx : 0.f);
+        if (wx == 0.f) continue;
+        const int dw = x + off_w;
+        if (dw < 0 || dw >= gdst.W) continue;
+        float v[8];
+        load8(gdst.base + gdst.pix(n, dh, dw) + c, nv, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += wy * wx * v[k];
+      }
+    }
+    bf16* dst = gsrc.base + gsrc.pix(n, sy, sx) + c;
+    if (accumulate) {
+      float old[8];
+      load8(dst, nv, old);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += old[k];
+    }
+    store8(dst, nv, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// gradient gather: G[n,h,w,c] = fold(dpad)[h,w] (+ max-pool backward of gpool through act)
+//   dpad  : dgrad output over the PADDED domain (H+2)x(W+2) (unpadded-style buffer of that size); the adjoint
+//           of the reflect halo adds each halo cell onto the interior pixel it mirrors.
+//   gpool : gradient w.r.t. the pooled map (unpadded, floor(H/2) x floor(W/2)); routed to the FIRST maximum of
+//           each 2x2 window of `act` (row-major window order), like nn.MaxPool2d's backward.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fold_read(const ActView& dp /*H+2,W+2 unpadded*/, int n, int h, int w, int H, int W, int c, int nv,
+                                          float acc[8]) {
+  // rows of the padded domain that map to interior row h: h+1 always; 0 if h==1; H+1 if h==H-2
+  int hs[3] = {h + 1, (h == 1) ? 0 : -1, (h == H - 2) ? H + 1 : -1};
+  int ws[3] = {w + 1, (w == 1) ? 0 : -1, (w == W - 2) ? W + 1 : -1};
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    if (hs[a] < 0) continue;
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      if (ws[b] < 0) continue;
+      float v[8];
+      load8(dp.base + dp.pix(n, hs[a], ws[b]) + c, nv, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += v[k];
+    }
+  }
+}
+
+__global__ void grad_gather_kernel(ActView dpad, int has_dpad, ActView gpool, ActView act, int has_pool, ActView gout,
+                                   int accumulate) {
+  const int groups = (gout.C + 7) >> 3;
+  const long long total = (long long)gout.N * gout.H * gout.W * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    long long r = i / groups;
+    const int w = (int)(r % gout.W); r /= gout.W;
+    const int h = (int)(r % gout.H);
+    const int n = (int)(r / gout.H);
+    const int c = g * 8, nv = min(8, gout.C - c);
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    if (has_dpad) fold_read(dpad, n, h, w, gout.H, gout.W, c, nv, acc);
+    if (has_pool) {
+      const int ph = h >> 1, pw = w >> 1;
+      if (ph < gpool.H && pw < gpool.W) {
+        float gp[8], mine[8];
+        load8(gpool.base + gpool.pix(n, ph, pw) + c, nv, gp);
+        load8(act.base + act.pix(n, h, w) + c, nv, mine);
+        bool win[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) win[k] = true;
+        const int my_rank = (h & 1) * 2 + (w & 1);
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 2; ++dx) {
+            const int rank = dy * 2 + dx;
+            if (rank == my_rank) continue;
+            float o[8];
+            load8(act.base + act.pix(n, ph * 2 + dy, pw * 2 + dx) + c, nv, o);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              // the other element beats me if it is larger, or equal and earlier in window order
+              if (o[k] > mine[k] || (o[k] == mine[k] && rank < my_rank)) win[k] = false;
+            }
+          }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (win[k]) acc[k] += gp[k];
+      }
+    }
+    bf16* dst = gout.base + gout.pix(n, h, w) + c;
+    if (accumulate) {
+      float old[8];
+      load8(dst, nv, old);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += old[k];
+    }
+    store8(dst, nv, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BN + ReLU (+dropout) backward.
+//   dz = G * drop * [scale*y + shift > 0]
+//   pass 1 (reduce): s1 = sum dz, s2 = sum dz * x_hat with x_hat = (y - mean) * invstd   -> per-block partials
+//   pass 2 (apply) : dy = scale * (dz - (s1 + x_hat * s2) / count)     [training]
+//                    dy = scale * dz                                     [eval: running stats are constants]
+// ------------------------------------------------------------------------------------------------
+__global__ void bn_bwd_reduce_kernel(ActView G, const bf16* __restrict__ y, int ycp, const float* __restrict__ scale,
+                                     const float* __restrict__ shift, const float* __restrict__ mean,
+                                     const float* __restrict__ invstd, const float* __restrict__ drop, int C,
+                                     float* __restrict__ part /*[gridDim.x][2][C]*/) {
+  // block handles a contiguous pixel range; thread (tx = channel group lane, ty = pixel lane)
+  extern __shared__ float sh[];  // [2][C] accumulators
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  const int groups = (C + 7) >> 3;
+  const long long npix = (long long)G.N * G.H * G.W;
+  const int pix_lanes = blockDim.x / groups;  // >= 1 (host guarantees groups <= blockDim.x)
+  const int g = threadIdx.x % groups, pl = threadIdx.x / groups;
+  if (pl < pix_lanes) {
+    const int c = g * 8, nv = min(8, C - c);
+    float sc[8], sf[8], mu[8], is[8], a1[8], a2[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      sc[k] = k < nv ? scale[c + k] : 0.f; sf[k] = k < nv ? shift[c + k] : 0.f;
+      mu[k] = k < nv ? mean[c + k] : 0.f;  is[k] = k < nv ? invstd[c + k] : 0.f;
+      a1[k] = 0.f; a2[k] = 0.f;
+    }
+    for (long long pidx = (long long)blockIdx.x * pix_lanes + pl; pidx < npix; pidx += (long long)gridDim.x * pix_lanes) {
+      const int w = (int)(pidx % G.W), h = (int)((pidx / G.W) % G.H), n = (int)(pidx / ((long long)G.W * G.H));
+      float gv[8], yv[8];
+      load8(G.base + G.pix(n, h, w) + c, nv, gv);
+      load8(y + (size_t)pidx * ycp + c, nv, yv);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float z = fmaf(yv[k], sc[k], sf[k]);
+        const float d = (drop && k < nv) ? drop[(size_t)n * C + c + k] : 1.f;
+        const float dz = (z > 0.f) ? gv[k] * d : 0.f;
+        a1[k] += dz;
+        a2[k] += dz * (yv[k] - mu[k]) * is[k];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (k < nv) { atomicAdd(&sh[c + k], a1[k]); atomicAdd(&sh[C + c + k], a2[k]); }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) part[(size_t)blockIdx.x * 2 * C + i] = sh[i];
+}
+
+// reduce partials -> s1,s2 ; write dgamma (= s2), dbeta (= s1), dbias_conv (eval only: scale * s1)
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int nparts, int C, float* __restrict__ s1s2 /*[2][C]*/,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias,
+                                       const float* __restrict__ scale, int training, float grad_scale, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double a = 0.0, b = 0.0;
+  for (int p = 0; p < nparts; ++p) { a += part[(size_t)p * 2 * C + c]; b += part[(size_t)p * 2 * C + C + c]; }
+  s1s2[c] = (float)a; s1s2[C + c] = (float)b;
+  if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)b * grad_scale;
+  if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)a * grad_scale;
+  // training: the conv bias cancels inside BatchNorm -> exactly zero gradient
+  if (dbias) dbias[c] = (accumulate ? dbias[c] : 0.f) + (training ? 0.f : (float)a * scale[c] * grad_scale);
+}
+
+__global__ void bn_bwd_apply_kernel(ActView G, const bf16* __restrict__ y, int ycp, const float* __restrict__ scale,
+                                    const float* __restrict__ shift, const float* __restrict__ mean,
+                                    const float* __restrict__ invstd, const float* __restrict__ drop,
+                                    const float* __restrict__ s1s2, int C, float inv_count, int training, bf16* __restrict__ dy,
+                                    int dycp) {
+  const int groups = (C + 7) >> 3;
+  const long long npix = (long long)G.N * G.H * G.W;
+  const long long total = npix * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    const long long pidx = i / groups;
+    const int w = (int)(pidx % G.W), h = (int)((pidx / G.W) % G.H), n = (int)(pidx / ((long long)G.W * G.H));
+    const int c = g * 8, nv = min(8, C - c);
+    float gv[8], yv[8], out[8];
+    load8(G.base + G.pix(n, h, w) + c, nv, gv);
+    load8(y + (size_t)pidx * ycp + c, nv, yv);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (k < nv) {
+        const float sc = scale[c + k];
+        const float z = fmaf(yv[k], sc, shift[c + k]);
+        const float d = drop ? drop[(size_t)n * C + c + k] : 1.f;
+        const float dz = (z > 0.f) ? gv[k] * d : 0.f;
+        if (training) {
+          const float xh = (yv[k] - mean[c + k]) * invstd[c + k];
+          out[k] = sc * (dz - (s1s2[c + k] + xh * s1s2[C + c + k]) * inv_count);
+        } else {
+          out[k] = sc * dz;
+        }
+      } else {
+        out[k] = 0.f;
+      }
+    }
+    // pad channels of dy are written as zeros so the tensor-core kernels never see garbage
+    const int nstore = min(8, dycp - c);
+    store8(dy + (size_t)pidx * dycp + c, nstore, out);
+  }
+}
+
+}  // namespace
+
+// ===================================== launchers =====================================
+int pack_input_launch(const float* x, long long sb, long long sc, const long long* gather, const ActView& o, cudaStream_t st) {
+  MIMO_CHECK(o.H >= 2 && o.W >= 2, MIMO_ERR_ARG, "pack_input: H,W must be >= 2");
+  const long long total = (long long)o.N * (o.H + 2 * o.pad) * (o.W + 2 * o.pad);
+  pack_input_kernel<<<grid_for(total), kBlock, 0, st>>>(x, sb, sc, gather, o);
+  MIMO_LAUNCH_CHECK();
+  return MIMO_OK;
+}
+
+int weight_pack_launch(const float* w, int cout, int cin, bf16* wf, int cin_pitch, bf16* wd, int cout_pitch, cudaStream_t st) {
+  const long long total = 9LL * cout * cin_pitch + (wd ? 9LL * cin * cout_pitch : 0);
+  weight_pack_kernel<<<grid_for(total), kBlock, 0, st>>>(w, cout, cin, wf, cin_pitch, wd, cout_pitch);
+  MIMO_LAUNCH_CHECK();
+  return MIMO_OK;
+}
+
+int bn_finalize_launch(const float* psum, const float* psq, int tiles, int cpitch, int C, double count, const float* gamma,
+                       const float* beta, const float* conv_bias, float* rm, float* rv, long long* nbt, float momentum, float eps,
+                       float* scale, float* shift, float* save_mean, float* save_invstd, cudaStream_t st) {
+  bn_finalize_kernel<<<C, 128, 0, st>>>(psum, psq, tiles, cpitch, C, count, gamma, beta, conv_bias, rm, rv, nbt, momentum, eps, scale,
+                                        shift, save_mean, save_invstd);
+  MIMO_LAUNCH_CHECK();
+  return MIMO_OK;
+}
+
+int bn_eval_affine_launch(int C, const float* gamma, const float* beta, const float* conv_bias, const float* rm, const float* rv,
+                          float eps, float* scale, float* shift, float* save_mean, float* save_invstd, cudaStream_t st) {
+  bn_eval_affine_kernel<<<ceil_div(C, 128), 128, 0, st>>>(C, gamma, beta, conv_bias, rm, rv, eps, scale, shift, save_mean, save_invstd);
+  MIMO_LAUNCH_CHECK();
+  return MIMO_OK;
+}
+
+int bn_relu_apply_launch(const bf16* y, int ycp, const float* scale, const float* shift, const float* drop, const ActView& o,
+                         const ActView* pool, cudaStream_t st) {
+  MIMO_CHECK(o.H >= 2 && o.W >= 2, MIMO_ERR_ARG, "bn_relu_apply: H,W must be >= 2");
+  ActView pv = pool ? *pool : o;
+  if (pool) MIMO_CHECK(pool->H == o.H / 2 && pool->W == o.W / 2 && pool->C == o.C && pool->N == o.N, MIMO_ERR_ARG, "bn_relu_apply: pool view shape mismatch");
+  const long long total = (long long)o.N * ((o.H + 1) / 2) * ((o.W + 1) / 2) * ((o.C + 7) / 8);
+  bn_relu_apply_kernel<<<grid_for(total), kBlock, 0, st>>>(y, ycp, scale, shift, drop, o, pv, pool ? 1 : 0);
+  MIMO_LAUNCH_CHECK();
+  return MIMO_OK;
+}
+
+int maxpool_launch(const ActView& in, const ActView& o, long long* idx_nchw, cudaStream_t st) {
+  MIMO_CHECK(o.H == in.H / 2 && o.W == in.W / 2 && o.C == in.C && o.N == in.N, MIMO_ERR_ARG, "maxpool: shape mismatch");
+  const long long total = (long long)o.N * o.H * o.W * ((o.C + 7) / 8);
+  maxpool_kernel<<<grid_for(total), kBlock, 0, st>>>(in, o, idx_nchw);
+  MIMO_LAUNCH_CHECK();
+  return MIMO_OK;
+}
+
+int upsample_launch(const ActView& in, const ActView& o, cudaStream_t st) {
+  MIMO_CHECK(o.N == in.N && o.C == in.C, MIMO_ERR_ARG, "upsample: N/C mismatch");
+  const int dY = o.H - 2 * in.H, dX = o.W - 2 * in.W;
+  MIMO_CHECK(dY >= 0 && dX >= 0, MIMO_ERR_ARG, "upsample: skip smaller than the up-sampled map");
+  const long long total = (long long)o.N * o.H * o.W * ((o.C + 7) / 8);
+  upsample_kernel<<<grid_for(total), kBlock, 0, st>>>(in, o, dY / 2, dX / 2);
+  MIMO_LAUNCH_CHECK();
+  return MIMO_OK;
+}
+
+int upsample_bwd_launch(const ActView& gdst, const ActView& gsrc, int accumulate, cudaStream_t st) {
+  MIMO_CHECK(gdst.N == gsrc.N && gdst.C == gsrc.C && gdst.pad == 0 && gsrc.pad == 0, MIMO_ERR_ARG, "upsample_bwd: view mismatch");
+  const int dY = gdst.H - 2 * gsrc.H, dX = gdst.W - 2 * gsrc.W;
+  MIMO_CHECK(dY >= 0 && dX >= 0, MIMO_ERR_ARG, "upsample_bwd: bad sizes");
+  const long long total = (long long)gsrc.N * gsrc.H * gsrc.W * ((gsrc.C + 7) / 8);
+  upsample_bwd_kernel<<<grid_for(total), kBlock, 0, st>>>(gdst, gsrc, dY / 2, dX / 2, accumulate);
+  MIMO_LAUNCH_CHECK();
+  return MIMO_OK;
+}
+
+int grad_gather_launch(const ActView* dpad, const ActView* gpool, const ActView* act, const ActView& gout, int accumulate,
+                       cudaStream_t st) {
+  MIMO_CHECK(gout.pad == 0, MIMO_ERR_ARG, "grad_gather: output must be unpadded");
+  if (dpad) MIMO_CHECK(dpad->pad == 0 && dpad->H == gout.H + 2 && dpad->W == gout.W + 2 && dpad->C == gout.C, MIMO_ERR_ARG, "grad_gather: dpad shape mismatch");
+  if (gpool) MIMO_CHECK(act && gpool->pad == 0 && gpool->H == gout.H / 2 && gpool->W == gout.W / 2 && gpool->C == gout.C && act->C == gout.C && act->H == gout.H, MIMO_ERR_ARG, "grad_gather: pool shape mismatch");
+  const long long total = (long long)gout.N * gout.H * gout.W * ((gout.C + 7) / 8);
+  grad_gather_kernel<<<grid_for(total), kBlock, 0, st>>>(dpad ? *dpad : gout, dpad ? 1 : 0, gpool ? *gpool : gout, act ? *act : gout,
+                                                        gpool ? 1 : 0, gout, accumulate);
+  MIMO_LAUNCH_CHECK();
+  return MIMO_OK;
+}
+
+int bn_bwd_parts(int C) { (void)C; return 2 * num_sms(); }
+
+int bn_bwd_launch(const ActView& G, const bf16* y, int ycp, const float* scale, const float* shift, const float* mean,
+                  const float* invstd, const float* drop, int training, float* part, float* s1s2, float* dgamma, float* dbeta,
+                  float* dbias, float grad_scale, int accumulate, bf16* dy, int dycp, cudaStream_t st) {
+  const int C = G.C;
+  MIMO_CHECK(G.pad == 0, MIMO_ERR_ARG, "bn_bwd: G must be unpadded");
+  MIMO_CHECK((C + 7) / 8 <= kBlock, MIMO_ERR_ARG, "bn_bwd: too many channels (%d)", C);
+  const int nparts = bn_bwd_parts(C);
+  bn_bwd_reduce_kernel<<<nparts, kBlock, 2 * C * sizeof(float), st>>>(G, y, ycp, scale, shift, mean, invstd, drop, C, part);
+  MIMO_LAUNCH_CHECK();
+  bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(part, nparts, C, s1s2, dgamma, dbeta, dbias, scale, training, grad_scale, accumulate);
+  MIMO_LAUNCH_CHECK();
+  const long long npix = (long long)G.N * G.H * G.W;
+  const long long total = npix * ((C + 7) / 8);
+  bn_bwd_apply_kernel<<<grid_for(total), kBlock, 0, st>>>(G, y, ycp, scale, shift, mean, invstd, drop, s1s2, C, 1.f / (float)npix,
+                                                          training, dy, dycp);
+  MIMO_LAUNCH_CHECK();
+  return MIMO_OK;
+}
+
+}  // namespace mimo

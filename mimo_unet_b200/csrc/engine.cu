@@ -1,0 +1,566 @@
+// Whole-network executor for the MIMO U-Net (bilinear path): builds the layer graph once, lays every
+// activation / gradient / scratch buffer out in ONE caller-provided workspace (no allocation, no sync), and
+// replays forward / backward as a fixed sequence of kernel launches on the caller's stream.
+//
+// Topology restated from the reference (mimo/models/mimo_components/model.py:94-117,150-175,232-243,285-297):
+//   per subnetwork s:  x[:,s] -> DoubleConv(Cin->f) = x1_s ; MaxPool ; DoubleConv(f->2f) = x2_s
+//   xc = cat_s(x2_s)  ->  down2, down3, down4 (MaxPool + DoubleConv)  ->  up1, up2, up3 (bilinear x2, cat skip)
+//   per subnetwork s:  up(u3) cat x1_s -> DoubleConv -> 1x1 head
+// Concats are never materialised as copies: producers write straight into channel slices of the consumer's
+// (reflect-haloed) input buffer.
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "ops.h"
+
+namespace mimo {
+namespace {
+
+struct Arena {
+  size_t off = 0;
+  size_t take(size_t bytes) {
+    const size_t a = (off + 255) & ~size_t(255);
+    off = a + bytes;
+    return a;
+  }
+};
+
+struct Buf {  // activation-like buffer inside the workspace
+  size_t off = 0;
+  int N = 0, H = 0, W = 0, pad = 0, cpitch = 0;
+  size_t bytes() const { return (size_t)N * (H + 2 * pad) * (W + 2 * pad) * cpitch * sizeof(bf16); }
+};
+
+struct View {  // channel slice of a Buf
+  int buf = -1;
+  int c_off = 0, C = 0;
+};
+
+struct ConvL {
+  int cin = 0, cout = 0, cin_p = 0, cout_p = 0, N = 0, H = 0, W = 0;
+  int state0 = -1;  // index of "<prefix>.weight" in the state list; +1 bias, +2 bn.w, +3 bn.b, +4 rm, +5 rv, +6 nbt
+  int m_tiles = 0;
+  size_t wf = 0, wd = 0, psum = 0, psq = 0, vec = 0 /* scale,shift,mean,invstd,s1,s2: 6*cout_p floats */, bnpart = 0, dwp = 0;
+  int y = -1, dy = -1, dpad = -1;  // Buf ids: raw output, its gradient, padded-domain input gradient
+};
+
+struct Node {  // one DoubleConv
+  std::string name;
+  ConvL c1, c2;
+  View in;        // whole buffer (c_off == 0)
+  int a1 = -1;    // Buf id of the intermediate activation
+  View out;       // destination slice
+  View pool;      // pooled destination slice (buf == -1: none)
+  int g1 = -1;    // Buf id: gradient w.r.t. a1 (unpadded)
+  View g2;        // gradient w.r.t. out (unpadded); may be a slice of a wider gradient buffer
+  bool need_in_grad = true;
+};
+
+}  // namespace
+}  // namespace mimo
+
+using namespace mimo;
+
+struct mimo_unet_plan {
+  mimo_unet_config_t cfg;
+  std::vector<Buf> bufs;
+  std::vector<Node> nodes;  // canonical double-conv order == state_dict order
+  std::map<std::string, int> node_by_name;
+  // node indices
+  std::vector<int> enc_in, enc_down, dec;
+  int down2 = -1, down3 = -1, down4 = -1, up1 = -1, up2 = -1, up3 = -1;
+  // extra buffers
+  std::vector<int> xin, dcat, p1, gp1;   // per subnetwork
+  int cat3 = -1, cat2 = -1, cat1 = -1, pxc = -1, px3 = -1, px4 = -1, x5 = -1, u1 = -1, u2 = -1, u3 = -1;
+  int g_xc = -1, g_x3 = -1, g_x4 = -1, g_x5 = -1, g_u1 = -1, g_u2 = -1, g_u3 = -1;
+  int gp_xc = -1, gp_x3 = -1, gp_x4 = -1;  // pooled-map gradients
+  int tmp0 = -1, tmp1 = -1, tmp2 = -1, tmp3 = -1;  // folded upsample-branch gradients per level
+  std::vector<int> g_feat, g_x1;         // per subnetwork
+  size_t head_part = 0;
+  int head_state0 = -1;
+  int n_state = 0;
+  size_t ws_bytes = 0;
+  // binding
+  uint8_t* ws = nullptr;
+  std::vector<void*> state, grads;
+  bool bound = false;
+  bool last_training = false;
+  bool have_forward = false;
+  const float* const* last_masks = nullptr;
+  std::vector<const float*> masks_copy;
+  int launches = 0;
+  int Hs[5], Ws[5];
+};
+
+namespace mimo {
+namespace eng {
+
+inline int p8(int c) { return round_up(c, 8); }
+
+int add_buf(mimo_unet_plan* P, Arena& A, int N, int H, int W, int pad, int C) {
+  Buf b;
+  b.N = N; b.H = H; b.W = W; b.pad = pad; b.cpitch = p8(C);
+  b.off = A.take(b.bytes());
+  P->bufs.push_back(b);
+  return (int)P->bufs.size() - 1;
+}
+
+ActView view_of(const mimo_unet_plan* P, int buf, int c_off, int C) {
+  const Buf& b = P->bufs[buf];
+  ActView v;
+  v.base = reinterpret_cast<bf16*>(P->ws + b.off);
+  v.N = b.N; v.H = b.H; v.W = b.W; v.pad = b.pad; v.cpitch = b.cpitch; v.c_off = c_off; v.C = C;
+  return v;
+}
+ActView view_of(const mimo_unet_plan* P, const View& v) { return view_of(P, v.buf, v.c_off, v.C); }
+
+void setup_conv(mimo_unet_plan* P, Arena& A, ConvL& c, int cin, int cout, int N, int H, int W, int& state_cursor) {
+  c.cin = cin; c.cout = cout; c.cin_p = p8(cin); c.cout_p = p8(cout); c.N = N; c.H = H; c.W = W;
+  c.state0 = state_cursor;
+  state_cursor += 7;
+  c.m_tiles = conv3x3_m_tiles(N, H, W);
+  c.wf = A.take((size_t)9 * cout * c.cin_p * sizeof(bf16));
+  c.wd = A.take((size_t)9 * cin * c.cout_p * sizeof(bf16));
+  c.psum = A.take((size_t)c.m_tiles * c.cout_p * sizeof(float));
+  c.psq = A.take((size_t)c.m_tiles * c.cout_p * sizeof(float));
+  c.vec = A.take((size_t)6 * c.cout_p * sizeof(float));
+  c.bnpart = A.take((size_t)bn_bwd_parts(cout) * 2 * cout * sizeof(float));
+  c.dwp = A.take((size_t)9 * cout * c.cin_p * sizeof(float));
+  c.y = add_buf(P, A, N, H, W, 0, cout);
+  c.dy = add_buf(P, A, N, H, W, 0, cout);
+  c.dpad = add_buf(P, A, N, H + 2, W + 2, 0, cin);
+}
+
+int add_node(mimo_unet_plan* P, Arena& A, const std::string& name, View in, int cin, int cmid, int cout, View out, View pool,
+             int level, int& state_cursor) {
+  Node n;
+  n.name = name;
+  const int N = P->cfg.batch, H = P->Hs[level], W = P->Ws[level];
+  setup_conv(P, A, n.c1, cin, cmid, N, H, W, state_cursor);
+  setup_conv(P, A, n.c2, cmid, cout, N, H, W, state_cursor);
+  n.in = in;
+  n.a1 = add_buf(P, A, N, H, W, 1, cmid);
+  n.out = out;
+  n.pool = pool;
+  n.g1 = add_buf(P, A, N, H, W, 0, cmid);
+  P->nodes.push_back(n);
+  P->node_by_name[name] = (int)P->nodes.size() - 1;
+  return (int)P->nodes.size() - 1;
+}
+
+#define RUN(expr)                 \
+  do {                            \
+    int _rc = (expr);             \
+    if (_rc != MIMO_OK) return _rc; \
+    ++P->launches;                \
+  } while (0)
+
+float* fptr(const mimo_unet_plan* P, size_t off) { return reinterpret_cast<float*>(P->ws + off); }
+bf16* bptr(const mimo_unet_plan* P, size_t off) { return reinterpret_cast<bf16*>(P->ws + off); }
+
+int conv_bn_forward(mimo_unet_plan* P, ConvL& c, const ActView& in, const ActView& out, const ActView* pool, const float* drop,
+                    bool training, cudaStream_t st) {
+  const float* w = (const float*)P->state[c.state0];
+  RUN(weight_pack_launch(w, c.cout, c.cin, bptr(P, c.wf), c.cin_p, bptr(P, c.wd), c.cout_p, st));
+  bf16* y = reinterpret_cast<bf16*>(P->ws + P->bufs[c.y].off);
+  float* vec = fptr(P, c.vec);
+  float *scale = vec, *shift = vec + c.cout_p, *mean = vec + 2 * c.cout_p, *invstd = vec + 3 * c.cout_p;
+  RUN(conv3x3_launch(in, 0, bptr(P, c.wf), c.cout, c.cin_p, y, c.cout_p, training ? fptr(P, c.psum) : nullptr,
+                     training ? fptr(P, c.psq) : nullptr, nullptr, 0, st));
+  const float* bias = (const float*)P->state[c.state0 + 1];
+  const float* gamma = (const float*)P->state[c.state0 + 2];
+  const float* beta = (const float*)P->state[c.state0 + 3];
+  float* rm = (float*)P->state[c.state0 + 4];
+  float* rv = (float*)P->state[c.state0 + 5];
+  long long* nbt = (long long*)P->state[c.state0 + 6];
+  if (training) {
+    RUN(bn_finalize_launch(fptr(P, c.psum), fptr(P, c.psq), c.m_tiles, c.cout_p, c.cout, (double)c.N * c.H * c.W, gamma, beta, bias,
+                           rm, rv, nbt, 0.1f, 1e-5f, scale, shift, mean, invstd, st));
+  } else {
+    RUN(bn_eval_affine_launch(c.cout, gamma, beta, bias, rm, rv, 1e-5f, scale, shift, mean, invstd, st));
+  }
+  RUN(bn_relu_apply_launch(y, c.cout_p, scale, shift, drop, out, pool, st));
+  return MIMO_OK;
+}
+
+int node_forward(mimo_unet_plan* P, int ni, bool training, const float* drop, cudaStream_t st) {
+  Node& n = P->nodes[ni];
+  const ActView in = view_of(P, n.in);
+  const ActView a1 = view_of(P, n.a1, 0, n.c1.cout);
+  const ActView out = view_of(P, n.out);
+  int rc = conv_bn_forward(P, n.c1, in, a1, nullptr, nullptr, training, st);
+  if (rc) return rc;
+  if (n.pool.buf >= 0) {
+    const ActView pool = view_of(P, n.pool);
+    return conv_bn_forward(P, n.c2, a1, out, &pool, drop, training, st);
+  }
+  return conv_bn_forward(P, n.c2, a1, out, nullptr, drop, training, st);
+}
+
+int conv_bn_backward(mimo_unet_plan* P, ConvL& c, const ActView& G, const ActView& in, const float* drop, bool training,
+                     bool need_in_grad, int accumulate, cudaStream_t st) {
+  float* vec = fptr(P, c.vec);
+  float *scale = vec, *shift = vec + c.cout_p, *mean = vec + 2 * c.cout_p, *invstd = vec + 3 * c.cout_p, *s1s2 = vec + 4 * c.cout_p;
+  const bf16* y = bptr(P, P->bufs[c.y].off);
+  bf16* dy = bptr(P, P->bufs[c.dy].off);
+  RUN(bn_bwd_launch(G, y, c.cout_p, scale, shift, mean, invstd, drop, training ? 1 : 0, fptr(P, c.bnpart), s1s2,
+                    (float*)P->grads[c.state0 + 2], (float*)P->grads[c.state0 + 3], (float*)P->grads[c.state0 + 1], 1.f, accumulate,
+                    dy, c.cout_p, st));
+  ++P->launches; ++P->launches;  // bn_bwd is three kernels
+  const ActView dyv = view_of(P, c.dy, 0, c.cout);
+  if (P->grads[c.state0] != nullptr) {
+    RUN(conv3x3_wgrad_launch(dyv, in, fptr(P, c.dwp), c.cin_p, st));
+    RUN(wgrad_unpack_launch(fptr(P, c.dwp), (float*)P->grads[c.state0], c.cout, c.cin, c.cin_p, 1.f, accumulate, st));
+  }
+  if (need_in_grad) {
+    bf16* dpad = bptr(P, P->bufs[c.dpad].off);
+    RUN(conv3x3_launch(dyv, 1, bptr(P, c.wd), c.cin, c.cout_p, dpad, c.cin_p, nullptr, nullptr, nullptr, 0, st));
+  }
+  return MIMO_OK;
+}
+
+int node_backward(mimo_unet_plan* P, int ni, bool training, const float* drop, int accumulate, cudaStream_t st) {
+  Node& n = P->nodes[ni];
+  const ActView G2 = view_of(P, n.g2);
+  const ActView a1 = view_of(P, n.a1, 0, n.c1.cout);
+  int rc = conv_bn_backward(P, n.c2, G2, a1, drop, training, true, accumulate, st);
+  if (rc) return rc;
+  const ActView dpad2 = view_of(P, n.c2.dpad, 0, n.c2.cin);
+  const ActView G1 = view_of(P, n.g1, 0, n.c1.cout);
+  RUN(grad_gather_launch(&dpad2, nullptr, nullptr, G1, 0, st));
+  const ActView in = view_of(P, n.in);
+  return conv_bn_backward(P, n.c1, G1, in, nullptr, training, n.need_in_grad, accumulate, st);
+}
+
+__global__ void unpack_input_grad_kernel(ActView dpad /* (H+2)x(W+2) domain */, int H, int W, int C, float* dx, long long sb, long long sc) {
+  const long long total = (long long)dpad.N * H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W), h = (int)((i / W) % H), n = (int)(i / ((long long)W * H));
+    int hs[3] = {h + 1, (h == 1) ? 0 : -1, (h == H - 2) ? H + 1 : -1};
+    int ws[3] = {w + 1, (w == 1) ? 0 : -1, (w == W - 2) ? W + 1 : -1};
+    for (int c = 0; c < C; ++c) {
+      float a = 0.f;
+      for (int p = 0; p < 3; ++p) {
+        if (hs[p] < 0) continue;
+        for (int q = 0; q < 3; ++q) {
+          if (ws[q] < 0) continue;
+          a += __bfloat162float(dpad.base[dpad.pix(n, hs[p], ws[q]) + c]);
+        }
+      }
+      dx[n * sb + c * sc + (long long)h * W + w] = a;
+    }
+  }
+}
+
+}  // namespace eng
+}  // namespace mimo
+using namespace mimo::eng;
+
+// ============================================================================================
+// C ABI
+// ============================================================================================
+extern "C" {
+
+int mimo_unet_plan_create(const mimo_unet_config_t* cfg, mimo_unet_plan_t** out) {
+  MIMO_CHECK(cfg && out, MIMO_ERR_ARG, "plan_create: null argument");
+  MIMO_CHECK(cfg->num_subnetworks >= 1 && cfg->num_subnetworks <= 16, MIMO_ERR_ARG, "plan_create: num_subnetworks must be in [1,16]");
+  MIMO_CHECK(cfg->in_channels >= 1 && cfg->out_channels >= 1 && cfg->out_channels <= 8, MIMO_ERR_ARG, "plan_create: out_channels must be in [1,8]");
+  MIMO_CHECK(cfg->filter_base_count >= 1 && cfg->batch >= 1, MIMO_ERR_ARG, "plan_create: bad filter_base_count / batch");
+  MIMO_CHECK(cfg->height / 16 >= 2 && cfg->width / 16 >= 2, MIMO_ERR_ARG,
+             "plan_create: H and W must be >= 32 (reflect padding needs every feature map >= 2 px), got %dx%d", cfg->height, cfg->width);
+  mimo_unet_plan* P = new mimo_unet_plan();
+  P->cfg = *cfg;
+  const int S = cfg->num_subnetworks, f = cfg->filter_base_count, N = cfg->batch, Cin = cfg->in_channels;
+  P->Hs[0] = cfg->height; P->Ws[0] = cfg->width;
+  for (int l = 1; l < 5; ++l) { P->Hs[l] = P->Hs[l - 1] / 2; P->Ws[l] = P->Ws[l - 1] / 2; }
+  const int c = 2 * f * S;
+  Arena A;
+  auto buf = [&](int level, int pad, int C) { return add_buf(P, A, N, P->Hs[level], P->Ws[level], pad, C); };
+  for (int s = 0; s < S; ++s) {
+    P->xin.push_back(buf(0, 1, Cin));
+    P->dcat.push_back(buf(0, 1, f + c / 2));
+    P->p1.push_back(buf(1, 1, f));
+    P->gp1.push_back(buf(1, 0, f));
+    P->g_feat.push_back(buf(0, 0, f));
+    P->g_x1.push_back(buf(0, 0, f));
+  }
+  P->cat3 = buf(1, 1, 2 * c); P->pxc = buf(2, 1, c);
+  P->cat2 = buf(2, 1, 4 * c); P->px3 = buf(3, 1, 2 * c);
+  P->cat1 = buf(3, 1, 8 * c); P->px4 = buf(4, 1, 4 * c);
+  P->x5 = buf(4, 1, 4 * c); P->u1 = buf(3, 1, 2 * c); P->u2 = buf(2, 1, c); P->u3 = buf(1, 1, c / 2);
+  P->g_xc = buf(1, 0, c); P->g_x3 = buf(2, 0, 2 * c); P->g_x4 = buf(3, 0, 4 * c); P->g_x5 = buf(4, 0, 4 * c);
+  P->g_u1 = buf(3, 0, 2 * c); P->g_u2 = buf(2, 0, c); P->g_u3 = buf(1, 0, c / 2);
+  P->gp_xc = buf(2, 0, c); P->gp_x3 = buf(3, 0, 2 * c); P->gp_x4 = buf(4, 0, 4 * c);
+  P->tmp0 = buf(0, 0, c / 2); P->tmp1 = buf(1, 0, c); P->tmp2 = buf(2, 0, 2 * c); P->tmp3 = buf(3, 0, 4 * c);
+
+  int cur = 0;
+  auto V = [](int b, int off, int C) { View v; v.buf = b; v.c_off = off; v.C = C; return v; };
+  const View none = V(-1, 0, 0);
+  // canonical (state_dict) order: encoder.in_convs.*, encoder.down1s.*, core.*, decoder.up4s.*, decoder.outcs.*
+  for (int s = 0; s < S; ++s) {
+    int ni = add_node(P, A, "encoder.in_convs." + std::to_string(s), V(P->xin[s], 0, Cin), Cin, f, f, V(P->dcat[s], 0, f),
+                      V(P->p1[s], 0, f), 0, cur);
+    P->nodes[ni].need_in_grad = false;
+    P->nodes[ni].g2 = V(P->g_x1[s], 0, f);
+    P->enc_in.push_back(ni);
+  }
+  for (int s = 0; s < S; ++s) {
+    int ni = add_node(P, A, "encoder.down1s." + std::to_string(s), V(P->p1[s], 0, f), f, 2 * f, 2 * f, V(P->cat3, 2 * f * s, 2 * f),
+                      V(P->pxc, 2 * f * s, 2 * f), 1, cur);
+    P->nodes[ni].g2 = V(P->g_xc, 2 * f * s, 2 * f);
+    P->enc_down.push_back(ni);
+  }
+  P->down2 = add_node(P, A, "core.down2", V(P->pxc, 0, c), c, 2 * c, 2 * c, V(P->cat2, 0, 2 * c), V(P->px3, 0, 2 * c), 2, cur);
+  P->nodes[P->down2].g2 = V(P->g_x3, 0, 2 * c);
+  P->down3 = add_node(P, A, "core.down3", V(P->px3, 0, 2 * c), 2 * c, 4 * c, 4 * c, V(P->cat1, 0, 4 * c), V(P->px4, 0, 4 * c), 3, cur);
+  P->nodes[P->down3].g2 = V(P->g_x4, 0, 4 * c);
+  P->down4 = add_node(P, A, "core.down4", V(P->px4, 0, 4 * c), 4 * c, 4 * c, 4 * c, V(P->x5, 0, 4 * c), none, 4, cur);
+  P->nodes[P->down4].g2 = V(P->g_x5, 0, 4 * c);
+  P->up1 = add_node(P, A, "core.up1", V(P->cat1, 0, 8 * c), 8 * c, 4 * c, 2 * c, V(P->u1, 0, 2 * c), none, 3, cur);
+  P->nodes[P->up1].g2 = V(P->g_u1, 0, 2 * c);
+  P->up2 = add_node(P, A, "core.up2", V(P->cat2, 0, 4 * c), 4 * c, 2 * c, c, V(P->u2, 0, c), none, 2, cur);
+  P->nodes[P->up2].g2 = V(P->g_u2, 0, c);
+  P->up3 = add_node(P, A, "core.up3", V(P->cat3, 0, 2 * c), 2 * c, c, c / 2, V(P->u3, 0, c / 2), none, 1, cur);
+  P->nodes[P->up3].g2 = V(P->g_u3, 0, c / 2);
+  const int d = c / 2 + f;
+  for (int s = 0; s < S; ++s) {
+    // the decoder feature map is only read by the 1x1 head: it still gets a halo for uniformity
+    int featb = buf(0, 1, f);
+    int ni = add_node(P, A, "decoder.up4s." + std::to_string(s), V(P->dcat[s], 0, d), d, d / 2, f, V(featb, 0, f), none, 0, cur);
+    P->nodes[ni].g2 = V(P->g_feat[s], 0, f);
+    P->dec.push_back(ni);
+  }
+  P->head_state0 = cur;
+  cur += 2 * S;
+  P->n_state = cur;
+  P->head_part = A.take((size_t)head_bwd_parts() * (cfg->out_channels * f + cfg->out_channels) * sizeof(float));
+  P->ws_bytes = A.off + 256;
+  *out = P;
+  return MIMO_OK;
+}
+
+void mimo_unet_plan_destroy(mimo_unet_plan_t* plan) { delete plan; }
+size_t mimo_unet_workspace_bytes(const mimo_unet_plan_t* plan) { return plan ? plan->ws_bytes : 0; }
+int mimo_unet_num_state(const mimo_unet_plan_t* plan) { return plan ? plan->n_state : 0; }
+int mimo_unet_num_double_convs(const mimo_unet_plan_t* plan) { return plan ? (int)plan->nodes.size() : 0; }
+int mimo_unet_dropout_channels(const mimo_unet_plan_t* plan, int i) {
+  if (!plan || i < 0 || i >= (int)plan->nodes.size()) return 0;
+  return plan->nodes[i].c2.cout;
+}
+int mimo_unet_last_launches(const mimo_unet_plan_t* plan) { return plan ? plan->launches : 0; }
+
+int mimo_unet_bind(mimo_unet_plan_t* P, void* workspace, size_t workspace_bytes, void* const* state, void* const* grads, int n) {
+  MIMO_CHECK(P && workspace && state, MIMO_ERR_ARG, "bind: null argument");
+  MIMO_CHECK(n == P->n_state, MIMO_ERR_ARG, "bind: expected %d state entries, got %d", P->n_state, n);
+  MIMO_CHECK(workspace_bytes >= P->ws_bytes, MIMO_ERR_ARG, "bind: workspace too small (%zu < %zu)", workspace_bytes, P->ws_bytes);
+  MIMO_CHECK(((uintptr_t)workspace % 256) == 0, MIMO_ERR_ALIGN, "bind: workspace must be 256-byte aligned");
+  P->ws = (uint8_t*)workspace;
+  P->state.assign(state, state + n);
+  if (grads) P->grads.assign(grads, grads + n);
+  else P->grads.assign(n, nullptr);
+  P->bound = true;
+  P->have_forward = false;
+  return MIMO_OK;
+}
+
+int mimo_unet_forward(mimo_unet_plan_t* P, const float* x, const long long* gather, int training, const float* const* drop_masks,
+                      float* out, void* stream) {
+  MIMO_CHECK(P && P->bound, MIMO_ERR_STATE, "forward: plan is not bound");
+  MIMO_CHECK(x && out, MIMO_ERR_ARG, "forward: null tensor");
+  cudaStream_t st = (cudaStream_t)stream;
+  const mimo_unet_config_t& cfg = P->cfg;
+  const int S = cfg.num_subnetworks, f = cfg.filter_base_count, Cin = cfg.in_channels, B = cfg.batch;
+  const long long HW = (long long)cfg.height * cfg.width;
+  const int c = 2 * f * S;
+  P->launches = 0;
+  P->masks_copy.assign(P->nodes.size(), nullptr);
+  if (drop_masks)
+    for (size_t i = 0; i < P->nodes.size(); ++i) P->masks_copy[i] = drop_masks[i];
+  auto mask = [&](int ni) { return P->masks_copy[ni]; };
+  const bool tr = training != 0;
+
+  for (int s = 0; s < S; ++s) {
+    const ActView xin = view_of(P, P->xin[s], 0, Cin);
+    RUN(pack_input_launch(x + (long long)s * Cin * HW, (long long)S * Cin * HW, HW, gather ? gather + (long long)s * B : nullptr, xin, st));
+    int rc = node_forward(P, P->enc_in[s], tr, mask(P->enc_in[s]), st);
+    if (rc) return rc;
+    rc = node_forward(P, P->enc_down[s], tr, mask(P->enc_down[s]), st);
+    if (rc) return rc;
+  }
+  int rc;
+  if ((rc = node_forward(P, P->down2, tr, mask(P->down2), st))) return rc;
+  if ((rc = node_forward(P, P->down3, tr, mask(P->down3), st))) return rc;
+  if ((rc = node_forward(P, P->down4, tr, mask(P->down4), st))) return rc;
+  RUN(upsample_launch(view_of(P, P->x5, 0, 4 * c), view_of(P, P->cat1, 4 * c, 4 * c), st));
+  if ((rc = node_forward(P, P->up1, tr, mask(P->up1), st))) return rc;
+  RUN(upsample_launch(view_of(P, P->u1, 0, 2 * c), view_of(P, P->cat2, 2 * c, 2 * c), st));
+  if ((rc = node_forward(P, P->up2, tr, mask(P->up2), st))) return rc;
+  RUN(upsample_launch(view_of(P, P->u2, 0, c), view_of(P, P->cat3, c, c), st));
+  if ((rc = node_forward(P, P->up3, tr, mask(P->up3), st))) return rc;
+  const int K = cfg.out_channels;
+  for (int s = 0; s < S; ++s) {
+    RUN(upsample_launch(view_of(P, P->u3, 0, c / 2), view_of(P, P->dcat[s], f, c / 2), st));
+    if ((rc = node_forward(P, P->dec[s], tr, mask(P->dec[s]), st))) return rc;
+    const ActView feat = view_of(P, P->nodes[P->dec[s]].out);
+    RUN(head_fwd_launch(feat, (const float*)P->state[P->head_state0 + 2 * s], (const float*)P->state[P->head_state0 + 2 * s + 1], K,
+                        out + (long long)s * K * HW, (long long)S * K * HW, st));
+  }
+  P->last_training = tr;
+  P->have_forward = true;
+  return MIMO_OK;
+}
+
+int mimo_unet_backward(mimo_unet_plan_t* P, const float* dout, const float* grad_scale, float* dx, int accumulate, void* stream) {
+  MIMO_CHECK(P && P->bound, MIMO_ERR_STATE, "backward: plan is not bound");
+  MIMO_CHECK(P->have_forward, MIMO_ERR_STATE, "backward: no forward pass to differentiate");
+  MIMO_CHECK(dout, MIMO_ERR_ARG, "backward: null dout");
+  cudaStream_t st = (cudaStream_t)stream;
+  const mimo_unet_config_t& cfg = P->cfg;
+  const int S = cfg.num_subnetworks, f = cfg.filter_base_count, Cin = cfg.in_channels, K = cfg.out_channels;
+  const long long HW = (long long)cfg.height * cfg.width;
+  const int c = 2 * f * S;
+  const bool tr = P->last_training;
+  P->launches = 0;
+  auto mask = [&](int ni) { return P->masks_copy[ni]; };
+  for (int s = 0; s < S; ++s) P->nodes[P->enc_in[s]].need_in_grad = (dx != nullptr);
+  int rc;
+
+  // ---- decoders ----
+  for (int s = 0; s < S; ++s) {
+    Node& n = P->nodes[P->dec[s]];
+    const ActView feat = view_of(P, n.out);
+    const ActView G = view_of(P, n.g2);
+    RUN(head_bwd_launch(feat, (const float*)P->state[P->head_state0 + 2 * s], K, dout + (long long)s * K * HW, (long long)S * K * HW,
+                        grad_scale, G, fptr(P, P->head_part), (float*)P->grads[P->head_state0 + 2 * s],
+                        (float*)P->grads[P->head_state0 + 2 * s + 1], accumulate, st));
+    ++P->launches;
+    if ((rc = node_backward(P, P->dec[s], tr, mask(P->dec[s]), accumulate, st))) return rc;
+    // gradient of the shared up-sampled core output: fold the [f, f + c/2) slice, then bilinear backward
+    const ActView dp = view_of(P, n.c1.dpad, f, c / 2);
+    const ActView t0 = view_of(P, P->tmp0, 0, c / 2);
+    RUN(grad_gather_launch(&dp, nullptr, nullptr, t0, 0, st));
+    RUN(upsample_bwd_launch(t0, view_of(P, P->g_u3, 0, c / 2), s > 0 ? 1 : 0, st));
+  }
+  // ---- core up path ----
+  if ((rc = node_backward(P, P->up3, tr, mask(P->up3), accumulate, st))) return rc;
+  {
+    const ActView dp = view_of(P, P->nodes[P->up3].c1.dpad, c, c);
+    const ActView t = view_of(P, P->tmp1, 0, c);
+    RUN(grad_gather_launch(&dp, nullptr, nullptr, t, 0, st));
+    RUN(upsample_bwd_launch(t, view_of(P, P->g_u2, 0, c), 0, st));
+  }
+  if ((rc = node_backward(P, P->up2, tr, mask(P->up2), accumulate, st))) return rc;
+  {
+    const ActView dp = view_of(P, P->nodes[P->up2].c1.dpad, 2 * c, 2 * c);
+    const ActView t = view_of(P, P->tmp2, 0, 2 * c);
+    RUN(grad_gather_launch(&dp, nullptr, nullptr, t, 0, st));
+    RUN(upsample_bwd_launch(t, view_of(P, P->g_u1, 0, 2 * c), 0, st));
+  }
+  if ((rc = node_backward(P, P->up1, tr, mask(P->up1), accumulate, st))) return rc;
+  {
+    const ActView dp = view_of(P, P->nodes[P->up1].c1.dpad, 4 * c, 4 * c);
+    const ActView t = view_of(P, P->tmp3, 0, 4 * c);
+    RUN(grad_gather_launch(&dp, nullptr, nullptr, t, 0, st));
+    RUN(upsample_bwd_launch(t, view_of(P, P->g_x5, 0, 4 * c), 0, st));
+  }
+  // ---- core down path: skip gradient (fold of the concat slice) + max-pool backward ----
+  if ((rc = node_backward(P, P->down4, tr, mask(P->down4), accumulate, st))) return rc;
+  {
+    const ActView dpp = view_of(P, P->nodes[P->down4].c1.dpad, 0, 4 * c);
+    const ActView gp = view_of(P, P->gp_x4, 0, 4 * c);
+    RUN(grad_gather_launch(&dpp, nullptr, nullptr, gp, 0, st));
+    const ActView dskip = view_of(P, P->nodes[P->up1].c1.dpad, 0, 4 * c);
+    const ActView act = view_of(P, P->cat1, 0, 4 * c);
+    RUN(grad_gather_launch(&dskip, &gp, &act, view_of(P, P->g_x4, 0, 4 * c), 0, st));
+  }
+  if ((rc = node_backward(P, P->down3, tr, mask(P->down3), accumulate, st))) return rc;
+  {
+    const ActView dpp = view_of(P, P->nodes[P->down3].c1.dpad, 0, 2 * c);
+    const ActView gp = view_of(P, P->gp_x3, 0, 2 * c);
+    RUN(grad_gather_launch(&dpp, nullptr, nullptr, gp, 0, st));
+    const ActView dskip = view_of(P, P->nodes[P->up2].c1.dpad, 0, 2 * c);
+    const ActView act = view_of(P, P->cat2, 0, 2 * c);
+    RUN(grad_gather_launch(&dskip, &gp, &act, view_of(P, P->g_x3, 0, 2 * c), 0, st));
+  }
+  if ((rc = node_backward(P, P->down2, tr, mask(P->down2), accumulate, st))) return rc;
+  {
+    const ActView dpp = view_of(P, P->nodes[P->down2].c1.dpad, 0, c);
+    const ActView gp = view_of(P, P->gp_xc, 0, c);
+    RUN(grad_gather_launch(&dpp, nullptr, nullptr, gp, 0, st));
+    const ActView dskip = view_of(P, P->nodes[P->up3].c1.dpad, 0, c);
+    const ActView act = view_of(P, P->cat3, 0, c);
+    RUN(grad_gather_launch(&dskip, &gp, &act, view_of(P, P->g_xc, 0, c), 0, st));
+  }
+  // ---- encoders ----
+  for (int s = 0; s < S; ++s) {
+    if ((rc = node_backward(P, P->enc_down[s], tr, mask(P->enc_down[s]), accumulate, st))) return rc;
+    const ActView dpp = view_of(P, P->nodes[P->enc_down[s]].c1.dpad, 0, f);
+    const ActView gp = view_of(P, P->gp1[s], 0, f);
+    RUN(grad_gather_launch(&dpp, nullptr, nullptr, gp, 0, st));
+    const ActView dskip = view_of(P, P->nodes[P->dec[s]].c1.dpad, 0, f);
+    const ActView act = view_of(P, P->dcat[s], 0, f);
+    RUN(grad_gather_launch(&dskip, &gp, &act, view_of(P, P->g_x1[s], 0, f), 0, st));
+    if ((rc = node_backward(P, P->enc_in[s], tr, mask(P->enc_in[s]), accumulate, st))) return rc;
+    if (dx) {
+      const ActView dp = view_of(P, P->nodes[P->enc_in[s]].c1.dpad, 0, Cin);
+      const long long total = (long long)cfg.batch * HW;
+      int grid = (int)((total + 255) / 256);
+      if (grid > num_sms() * 16) grid = num_sms() * 16;
+      unpack_input_grad_kernel<<<grid, 256, 0, st>>>(dp, cfg.height, cfg.width, Cin, dx + (long long)s * Cin * HW, (long long)S * Cin * HW, HW);
+      MIMO_LAUNCH_CHECK();
+      ++P->launches;
+    }
+  }
+  return MIMO_OK;
+}
+
+int mimo_unet_debug_view(const mimo_unet_plan_t* P, const char* name, mimo_act_t* view, int* kind) {
+  MIMO_CHECK(P && name && view && kind, MIMO_ERR_ARG, "debug_view: null argument");
+  MIMO_CHECK(P->bound, MIMO_ERR_STATE, "debug_view: plan is not bound");
+  const std::string full(name);
+  const size_t dot = full.rfind('.');
+  MIMO_CHECK(dot != std::string::npos, MIMO_ERR_ARG, "debug_view: bad name %s", name);
+  std::string node = full.substr(0, dot), what = full.substr(dot + 1);
+  const ConvL* cl = nullptr;
+  // "<node>.c1.y" style names carry one more component
+  if (what == "y" || what == "dy" || what == "dpad" || what == "scale" || what == "shift" || what == "mean" || what == "invstd") {
+    const size_t dot2 = node.rfind('.');
+    MIMO_CHECK(dot2 != std::string::npos, MIMO_ERR_ARG, "debug_view: bad name %s", name);
+    const std::string which = node.substr(dot2 + 1);
+    node = node.substr(0, dot2);
+    auto it = P->node_by_name.find(node);
+    MIMO_CHECK(it != P->node_by_name.end(), MIMO_ERR_ARG, "debug_view: unknown node %s", node.c_str());
+    cl = which == "c1" ? &P->nodes[it->second].c1 : &P->nodes[it->second].c2;
+  }
+  auto fill = [&](const ActView& v) {
+    view->ptr = v.base; view->n = v.N; view->h = v.H; view->w = v.W; view->pad = v.pad; view->cpitch = v.cpitch; view->c_off = v.c_off; view->c = v.C;
+  };
+  *kind = 0;
+  if (cl) {
+    if (what == "y") fill(view_of(P, cl->y, 0, cl->cout));
+    else if (what == "dy") fill(view_of(P, cl->dy, 0, cl->cout));
+    else if (what == "dpad") fill(view_of(P, cl->dpad, 0, cl->cin));
+    else {
+      const int k = what == "scale" ? 0 : what == "shift" ? 1 : what == "mean" ? 2 : 3;
+      *kind = 1;
+      view->ptr = (void*)(fptr(P, cl->vec) + k * cl->cout_p);
+      view->n = view->h = view->w = 1; view->pad = 0; view->cpitch = cl->cout_p; view->c_off = 0; view->c = cl->cout;
+    }
+    return MIMO_OK;
+  }
+  auto it = P->node_by_name.find(node);
+  MIMO_CHECK(it != P->node_by_name.end(), MIMO_ERR_ARG, "debug_view: unknown node %s", node.c_str());
+  const Node& n = P->nodes[it->second];
+  if (what == "in") fill(view_of(P, n.in));
+  else if (what == "a1") fill(view_of(P, n.a1, 0, n.c1.cout));
+  else if (what == "out") fill(view_of(P, n.out));
+  else if (what == "pool") { MIMO_CHECK(n.pool.buf >= 0, MIMO_ERR_ARG, "debug_view: node has no pooled output"); fill(view_of(P, n.pool)); }
+  else if (what == "g1") fill(view_of(P, n.g1, 0, n.c1.cout));
+  else if (what == "g2") fill(view_of(P, n.g2));
+  else { set_error("debug_view: unknown buffer %s", what.c_str()); return MIMO_ERR_ARG; }
+  return MIMO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,515 @@
+// Output heads, Laplace negative log-likelihood, loss-buffer softmax weighting and ensemble aggregation.
+// All memory-bound: coalesced, vectorised where alignment allows, warp-shuffle + per-block partial reductions
+// (finalised deterministically by a one-block kernel, never by float atomics across the grid).
+//
+// Replaces: OutConv (components.py:123-129), LaplaceNLL.forward (losses.py:132-164) and its autograd,
+// _calculate_train_loss (mimo_unet.py:223-247), LossBuffer (loss_buffer.py:18-74) and compute_uncertainties
+// (models/utils.py:76-101).
+#include "common.cuh"
+#include "ops.h"
+
+namespace mimo {
+namespace {
+
+constexpr int kBlock = 256;
+
+__device__ __forceinline__ float block_sum(float v, float* sh /*[32]*/) {
+  v = warp_sum(v);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  float r = 0.f;
+  if (warp == 0) {
+    r = (lane < (int)(blockDim.x >> 5)) ? sh[lane] : 0.f;
+    r = warp_sum(r);
+  }
+  return r;  // valid in warp 0
+}
+
+// ------------------------------------------------------------------------------------------------
+// 1x1 head: out[b, s, k, h, w] = bias[k] + sum_c W[k][c] * feat[b, h, w, c]      (fp32 out, NCHW planes)
+// ------------------------------------------------------------------------------------------------
+__global__ void head_fwd_kernel(ActView f, const float* __restrict__ W, const float* __restrict__ bias, int K,
+                                float* __restrict__ out, long long out_bstride /*elements between batch entries*/) {
+  extern __shared__ float shw[];  // [K][C] + [K]
+  const int C = f.C;
+  for (int i = threadIdx.x; i < K * C; i += blockDim.x) shw[i] = W[i];
+  for (int i = threadIdx.x; i < K; i += blockDim.x) shw[K * C + i] = bias[i];
+  __syncthreads();
+  const long long HW = (long long)f.H * f.W, total = (long long)f.N * HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(i % f.W), h = (int)((i / f.W) % f.H), n = (int)(i / HW);
+    const bf16* src = f.base + f.pix(n, h, w);
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = (k < K) ? shw[K * C + k] : 0.f;
+    for (int c0 = 0; c0 < C; c0 += 8) {
+      float v[8];
+      load8(src + c0, min(8, C - c0), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (c0 + j < C) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (k < K) acc[k] = fmaf(v[j], shw[k * C + c0 + j], acc[k]);
+        }
+      }
+    }
+    float* dst = out + (long long)n * out_bstride + (long long)h * f.W + w;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (k < K) dst[k * HW] = acc[k];
+  }
+}
+
+// backward of the head: G[n,h,w,c] = gs * sum_k dOut[n,k,h,w] * W[k][c]  (bf16, unpadded NHWC)
+//                       dW[k][c]  (+)= gs * sum_pix dOut * feat ;  db[k] (+)= gs * sum_pix dOut
+// gs = *grad_scale (device scalar, e.g. the AMP loss scale) or 1.
+__global__ void head_bwd_kernel(ActView f, const float* __restrict__ W, int K, const float* __restrict__ dout,
+                                long long out_bstride, const float* __restrict__ grad_scale, ActView G,
+                                float* __restrict__ part /*[gridDim.x][K*C + K]*/) {
+  extern __shared__ float sh[];
+  const int C = f.C;
+  float* shw = sh;                 // [K][C]
+  float* sd = shw + K * C;         // [K][kBlock]   dOut tile
+  float* sf = sd + K * kBlock;     // [kBlock][C+1] feature tile
+  const float gs = grad_scale ? *grad_scale : 1.f;
+  for (int i = threadIdx.x; i < K * C; i += blockDim.x) shw[i] = W[i];
+  const long long HW = (long long)f.H * f.W, total = (long long)f.N * HW;
+  const int pairs = K * C + K;
+  // each thread owns up to 2 (k,c) accumulators (pairs <= 2*kBlock enforced by the host)
+  float acc0 = 0.f, acc1 = 0.f;
+  const long long tiles = (total + kBlock - 1) / kBlock;
+  for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+    __syncthreads();
+    const long long i = t * kBlock + threadIdx.x;
+    const bool ok = i < total;
+    int w = 0, h = 0, n = 0;
+    if (ok) { w = (int)(i % f.W); h = (int)((i / f.W) % f.H); n = (int)(i / HW); }
+    float d[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      d[k] = (ok && k < K) ? gs * dout[(long long)n * out_bstride + k * HW + (long long)h * f.W + w] : 0.f;
+      if (k < K) sd[k * kBlock + threadIdx.x] = d[k];
+    }
+    const bf16* src = f.base + f.pix(n, h, w);
+    bf16* gdst = G.base + G.pix(n, h, w);
+    for (int c0 = 0; c0 < C; c0 += 8) {
+      const int nv = min(8, C - c0);
+      float v[8], g[8];
+      if (ok) load8(src + c0, nv, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (!ok) v[j] = 0.f;
+        if (j < nv) sf[threadIdx.x * (C + 1) + c0 + j] = v[j];
+        float a = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (k < K && j < nv) a = fmaf(d[k], shw[k * C + c0 + j], a);
+        g[j] = a;
+      }
+      // pad channels of G are written as zeros (G.cpitch multiple of 8)
+      if (ok) store8(gdst + c0, min(8, G.cpitch - c0), g);
+    }
+    __syncthreads();
+    for (int rep = 0; rep < 2; ++rep) {
+      const int pr = threadIdx.x + rep * kBlock;
+      if (pr >= pairs) break;
+      float a = 0.f;
+      if (pr < K * C) {
+        const int k = pr / C, c = pr - k * C;
+        for (int p = 0; p < kBlock; ++p) a = fmaf(sd[k * kBlock + p], sf[p * (C + 1) + c], a);
+      } else {
+        const int k = pr - K * C;
+        for (int p = 0; p < kBlock; ++p) a += sd[k * kBlock + p];
+      }
+      if (rep == 0) acc0 += a; else acc1 += a;
+    }
+  }
+  if ((int)threadIdx.x < pairs) part[(size_t)blockIdx.x * pairs + threadIdx.x] = acc0;
+  if ((int)threadIdx.x + kBlock < pairs) part[(size_t)blockIdx.x * pairs + threadIdx.x + kBlock] = acc1;
+}
+
+__global__ void head_bwd_finalize_kernel(const float* __restrict__ part, int nparts, int K, int C, float* __restrict__ dW,
+                                         float* __restrict__ db, int accumulate) {
+  const int pairs = K * C + K;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= pairs) return;
+  double a = 0.0;
+  for (int p = 0; p < nparts; ++p) a += part[(size_t)p * pairs + i];
+  float* dst = (i < K * C) ? dW + i : db + (i - K * C);
+  *dst = (accumulate ? *dst : 0.f) + (float)a;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Laplace NLL element math
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void laplace_elem(float mu, float ls, float y, float m, float eps_min, float eps_max, float* loss,
+                                             float* g_mu, float* g_ls) {
+  const float d = mu - y;
+  const float s_raw = expf(ls);
+  const float s_c = fminf(fmaxf(s_raw, eps_min), eps_max);
+  const float inv = 1.f / s_c;
+  const float ad = fabsf(d);
+  *loss = (logf(s_c) + ad * inv) * m;
+  *g_mu = ((d > 0.f) ? inv : ((d < 0.f) ? -inv : 0.f)) * m;
+  *g_ls = (inv - ad * inv * inv) * s_raw * m;
+}
+
+// generic elementwise forward over [rows][cols] with per-tensor row strides (covers the strided p1/p2 views)
+__global__ void laplace_fwd_kernel(const float* __restrict__ mu, long long mu_rs, const float* __restrict__ ls, long long ls_rs,
+                                   const float* __restrict__ y, long long y_rs, const float* __restrict__ mask, long long m_rs,
+                                   long long rows, long long cols, float eps_min, float eps_max, float* __restrict__ out_elem,
+                                   float* __restrict__ part /*[gridDim.x] or null*/) {
+  __shared__ float sh[32];
+  const long long total = rows * cols;
+  float acc = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols, c = i - r * cols;
+    float l, a, b;
+    laplace_elem(mu[r * mu_rs + c], ls[r * ls_rs + c], y[r * y_rs + c], mask ? mask[r * m_rs + c] : 1.f, eps_min, eps_max, &l, &a, &b);
+    if (out_elem) out_elem[i] = l;
+    acc += l;
+  }
+  if (part) {
+    const float s = block_sum(acc, sh);
+    if (threadIdx.x == 0) part[blockIdx.x] = s;
+  }
+}
+
+__global__ void sum_partials_kernel(const float* __restrict__ part, int n, float scale, float* __restrict__ out) {
+  __shared__ float sh[32];
+  float a = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) a += part[i];
+  const float s = block_sum(a, sh);
+  if (threadIdx.x == 0) *out = s * scale;
+}
+
+// generic elementwise backward: g_mu = up * dl/dmu, g_ls = up * dl/dlog_s, up = upstream[i] (elementwise) or
+// *upstream * scalar (reduce_mean path)
+__global__ void laplace_bwd_kernel(const float* __restrict__ mu, long long mu_rs, const float* __restrict__ ls, long long ls_rs,
+                                   const float* __restrict__ y, long long y_rs, const float* __restrict__ mask, long long m_rs,
+                                   long long rows, long long cols, float eps_min, float eps_max, const float* __restrict__ up,
+                                   int up_is_scalar, float up_scale, float* __restrict__ g_mu, float* __restrict__ g_ls) {
+  const long long total = rows * cols;
+  const float us = up_is_scalar ? (*up) * up_scale : 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols, c = i - r * cols;
+    float l, a, b;
+    laplace_elem(mu[r * mu_rs + c], ls[r * ls_rs + c], y[r * y_rs + c], mask ? mask[r * m_rs + c] : 1.f, eps_min, eps_max, &l, &a, &b);
+    const float u = up_is_scalar ? us : up[i];
+    g_mu[i] = a * u;
+    g_ls[i] = b * u;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused training loss: one pass over out[B,S,2C,H,W] and the labels
+//   weights w[s] = S * softmax(mean_rows(buffer) / T)     (read BEFORE the new loss enters the buffer)
+//   loss[s]     = mean_{b,c,h,w} l
+//   dOut        = w[s] / (S * B*C*H*W) * dl/d(mu, log_s)  (gradient of mean_s(w_s * loss_s))
+// grid = (blocks_per_row, B*S). Partials per (row, block) are finalised by laplace_train_finalize_kernel,
+// which also advances the loss buffer -- no host round trip (the reference syncs twice per step here).
+// ------------------------------------------------------------------------------------------------
+struct LossBufferState {  // device-resident mirror of loss_buffer.py:LossBuffer
+  int index;
+  int size;
+  int S;
+  float temperature;
+  // followed by float buf[size * S]
+};
+
+__device__ __forceinline__ void buffer_weights(const LossBufferState* st, const float* buf, float* w /*[S]*/) {
+  // mean over ALL rows (zeros included, loss_buffer.py:61-62), softmax with temperature, times S
+  const int S = st->S;
+  float mx = -INFINITY;
+  for (int s = 0; s < S; ++s) {
+    float m = 0.f;
+    for (int r = 0; r < st->size; ++r) m += buf[r * S + s];
+    m = st->size > 0 ? m / (float)st->size : 0.f;
+    w[s] = m / st->temperature;
+    mx = fmaxf(mx, w[s]);
+  }
+  float den = 0.f;
+  for (int s = 0; s < S; ++s) { w[s] = expf(w[s] - mx); den += w[s]; }
+  for (int s = 0; s < S; ++s) w[s] = w[s] / den * (float)S;
+}
+
+__global__ void laplace_train_kernel(const float* __restrict__ out, const float* __restrict__ y, long long y_bs, long long y_ss,
+                                     const float* __restrict__ mask, long long m_bs, long long m_ss,
+                                     const long long* __restrict__ gather /*[S][B] or null*/, int B, int S, int C, long long HW,
+                                     float eps_min, float eps_max, const LossBufferState* __restrict__ lb,
+                                     const float* __restrict__ fixed_w /*[S] or null*/, float* __restrict__ dout,
+                                     float* __restrict__ part /*[B*S][gridDim.x]*/) {
+  __shared__ float sh[32];
+  __shared__ float sw;
+  const int row = blockIdx.y;  // b*S + s
+  const int b = row / S, s = row - b * S;
+  if (threadIdx.x == 0) {
+    float w[64];
+    if (fixed_w) sw = fixed_w[s];
+    else if (lb) { buffer_weights(lb, reinterpret_cast<const float*>(lb + 1), w); sw = w[s]; }
+    else sw = 1.f;
+  }
+  __syncthreads();
+  const long long n = (long long)C * HW;
+  const float coef = sw / ((float)S * (float)B * (float)n);
+  const long long src_b = gather ? gather[(long long)s * B + b] : b;
+  const float* mu = out + (long long)row * 2 * n;
+  const float* ls = mu + n;
+  const float* yy = y + src_b * y_bs + s * y_ss;
+  const float* mm = mask ? mask + src_b * m_bs + s * m_ss : nullptr;
+  float* gmu = dout ? dout + (long long)row * 2 * n : nullptr;
+  float* gls = dout ? gmu + n : nullptr;
+  float acc = 0.f;
+  const bool vec = ((n & 3) == 0) && ((reinterpret_cast<uintptr_t>(mu) & 15) == 0) && ((reinterpret_cast<uintptr_t>(yy) & 15) == 0) &&
+                   (!mm || (reinterpret_cast<uintptr_t>(mm) & 15) == 0) && (!dout || (reinterpret_cast<uintptr_t>(gmu) & 15) == 0);
+  if (vec) {
+    const long long n4 = n >> 2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+      const float4 a = reinterpret_cast<const float4*>(mu)[i];
+      const float4 l4 = reinterpret_cast<const float4*>(ls)[i];
+      const float4 t = reinterpret_cast<const float4*>(yy)[i];
+      float4 m4 = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (mm) m4 = reinterpret_cast<const float4*>(mm)[i];
+      float4 ga, gl;
+      float l;
+      laplace_elem(a.x, l4.x, t.x, m4.x, eps_min, eps_max, &l, &ga.x, &gl.x); acc += l;
+      laplace_elem(a.y, l4.y, t.y, m4.y, eps_min, eps_max, &l, &ga.y, &gl.y); acc += l;
+      laplace_elem(a.z, l4.z, t.z, m4.z, eps_min, eps_max, &l, &ga.z, &gl.z); acc += l;
+      laplace_elem(a.w, l4.w, t.w, m4.w, eps_min, eps_max, &l, &ga.w, &gl.w); acc += l;
+      if (dout) {
+        ga.x *= coef; ga.y *= coef; ga.z *= coef; ga.w *= coef;
+        gl.x *= coef; gl.y *= coef; gl.z *= coef; gl.w *= coef;
+        reinterpret_cast<float4*>(gmu)[i] = ga;
+        reinterpret_cast<float4*>(gls)[i] = gl;
+      }
+    }
+  } else {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+      float l, ga, gl;
+      laplace_elem(mu[i], ls[i], yy[i], mm ? mm[i] : 1.f, eps_min, eps_max, &l, &ga, &gl);
+      acc += l;
+      if (dout) { gmu[i] = ga * coef; gls[i] = gl * coef; }
+    }
+  }
+  const float sres = block_sum(acc, sh);
+  if (threadIdx.x == 0) part[(size_t)row * gridDim.x + blockIdx.x] = sres;
+}
+
+// one block: loss[s] = sum over (b, blocks) / (B*n); weights; weighted mean; buffer update
+__global__ void laplace_train_finalize_kernel(const float* __restrict__ part, int nblk, int B, int S, double count,
+                                              LossBufferState* lb, const float* __restrict__ fixed_w, int update_buffer,
+                                              float* __restrict__ loss /*[S]*/, float* __restrict__ weights /*[S]*/,
+                                              float* __restrict__ weighted /*[1]*/) {
+  __shared__ float sh[32];
+  __shared__ float sl[64];
+  for (int s = 0; s < S; ++s) {
+    float a = 0.f;
+    for (int i = threadIdx.x; i < B * nblk; i += blockDim.x) {
+      const int b = i / nblk, k = i - b * nblk;
+      a += part[(size_t)(b * S + s) * nblk + k];
+    }
+    const float t = block_sum(a, sh);
+    if (threadIdx.x == 0) sl[s] = (float)((double)t / count);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    float w[64];
+    float* buf = lb ? reinterpret_cast<float*>(lb + 1) : nullptr;
+    if (fixed_w) for (int s = 0; s < S; ++s) w[s] = fixed_w[s];
+    else if (lb) buffer_weights(lb, buf, w);
+    else for (int s = 0; s < S; ++s) w[s] = 1.f;
+    float tot = 0.f;
+    for (int s = 0; s < S; ++s) {
+      loss[s] = sl[s];
+      if (weights) weights[s] = w[s];
+      tot += w[s] * sl[s];
+    }
+    if (weighted) *weighted = tot / (float)S;
+    if (lb && update_buffer && lb->size > 0) {  // loss_buffer.py:43-52
+      for (int s = 0; s < S; ++s) buf[lb->index * S + s] = sl[s];
+      lb->index = (lb->index + 1) % lb->size;
+    }
+  }
+}
+
+__global__ void lossbuffer_weights_kernel(const LossBufferState* lb, float* w) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    float t[64];
+    buffer_weights(lb, reinterpret_cast<const float*>(lb + 1), t);
+    for (int s = 0; s < lb->S; ++s) w[s] = t[s];
+  }
+}
+__global__ void lossbuffer_add_kernel(LossBufferState* lb, const float* loss) {
+  if (threadIdx.x == 0 && blockIdx.x == 0 && lb->size > 0) {
+    float* buf = reinterpret_cast<float*>(lb + 1);
+    for (int s = 0; s < lb->S; ++s) buf[lb->index * lb->S + s] = loss[s];
+    lb->index = (lb->index + 1) % lb->size;
+  }
+}
+__global__ void lossbuffer_init_kernel(LossBufferState* lb, int S, int size, float T) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) { lb->index = 0; lb->size = size; lb->S = S; lb->temperature = T; }
+  float* buf = reinterpret_cast<float*>(lb + 1);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < S * size; i += gridDim.x * blockDim.x) buf[i] = 0.f;
+}
+
+__global__ void scale_by_scalar_kernel(float* __restrict__ x, long long n, const float* __restrict__ s) {
+  const float v = *s;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) x[i] *= v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Ensemble aggregation (models/utils.py:76-101): per output element over the S members
+//   mean = 1/S sum mu ; aleatoric = 1/S sum 2*exp(2*log_s) ; epistemic = sum (mu-mean)^2 / (S-1)   (0 if S == 1)
+// p1/p2 element (b, s, j) at base + b*bs + s*ss + j.
+// ------------------------------------------------------------------------------------------------
+__global__ void aggregate_kernel(const float* __restrict__ p1, long long p1_bs, long long p1_ss, const float* __restrict__ p2,
+                                 long long p2_bs, long long p2_ss, int B, int S, long long inner, float* __restrict__ mean,
+                                 float* __restrict__ alea, float* __restrict__ epi) {
+  const long long total = (long long)B * inner;
+  const float invS = 1.f / (float)S;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / inner, j = i - b * inner;
+    const float* a = p1 + b * p1_bs + j;
+    const float* l = p2 + b * p2_bs + j;
+    float m = 0.f, al = 0.f;
+    for (int s = 0; s < S; ++s) {
+      m += a[s * p1_ss];
+      const float sd = expf(l[s * p2_ss]) * 1.41421356237309515f;  // losses.py:166-167
+      al += sd * sd;
+    }
+    m *= invS;
+    float e = 0.f;
+    if (S > 1) {
+      for (int s = 0; s < S; ++s) { const float d = a[s * p1_ss] - m; e += d * d; }
+      e /= (float)(S - 1);
+    }
+    mean[i] = m; alea[i] = al * invS; epi[i] = e;
+  }
+}
+
+inline int grid_for(long long work, int per_thread = 1) {
+  long long g = ceil_div_ll(work, (long long)kBlock * per_thread);
+  const long long cap = (long long)num_sms() * 8;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace
+
+// ===================================== launchers =====================================
+int head_fwd_launch(const ActView& f, const float* W, const float* bias, int K, float* out, long long out_bstride, cudaStream_t st) {
+  MIMO_CHECK(K >= 1 && K <= 8, MIMO_ERR_ARG, "head: out_channels must be in [1,8] (got %d)", K);
+  const long long total = (long long)f.N * f.H * f.W;
+  head_fwd_kernel<<<grid_for(total), kBlock, (K * f.C + K) * sizeof(float), st>>>(f, W, bias, K, out, out_bstride);
+  MIMO_LAUNCH_CHECK();
+  return MIMO_OK;
+}
+
+int head_bwd_parts() { return 2 * num_sms(); }
+
+int head_bwd_launch(const ActView& f, const float* W, int K, const float* dout, long long out_bstride, const float* grad_scale,
+                    const ActView& G, float* part, float* dW, float* db, int accumulate, cudaStream_t st) {
+  MIMO_CHECK(K >= 1 && K <= 8, MIMO_ERR_ARG, "head: out_channels must be in [1,8] (got %d)", K);
+  MIMO_CHECK(K * f.C + K <= 2 * kBlock, MIMO_ERR_ARG, "head: K*C too large");
+  MIMO_CHECK(G.pad == 0 && G.c_off == 0 && G.C == f.C, MIMO_ERR_ARG, "head_bwd: G view mismatch");
+  const int nparts = head_bwd_parts();
+  const size_t smem = ((size_t)K * f.C + (size_t)K * kBlock + (size_t)kBlock * (f.C + 1)) * sizeof(float);
+  static bool attr = false;
+  if (!attr) { MIMO_CUDA(cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr = true; }
+  MIMO_CHECK(smem <= 160 * 1024, MIMO_ERR_ARG, "head_bwd: feature count too large for shared memory");
+  head_bwd_kernel<<<nparts, kBlock, smem, st>>>(f, W, K, dout, out_bstride, grad_scale, G, part);
+  MIMO_LAUNCH_CHECK();
+  head_bwd_finalize_kernel<<<ceil_div(K * f.C + K, 128), 128, 0, st>>>(part, nparts, K, f.C, dW, db, accumulate);
+  MIMO_LAUNCH_CHECK();
+  return MIMO_OK;
+}
+
+int laplace_parts() { return num_sms() * 8; }
+
+int laplace_fwd_launch(const float* mu, long long mu_rs, const float* ls, long long ls_rs, const float* y, long long y_rs,
+                       const float* mask, long long m_rs, long long rows, long long cols, float eps_min, float eps_max,
+                       float* out_elem, float* part, float* out_mean, cudaStream_t st) {
+  const int grid = grid_for(rows * cols, 4);
+  laplace_fwd_kernel<<<grid, kBlock, 0, st>>>(mu, mu_rs, ls, ls_rs, y, y_rs, mask, m_rs, rows, cols, eps_min, eps_max, out_elem,
+                                              out_mean ? part : nullptr);
+  MIMO_LAUNCH_CHECK();
+  if (out_mean) {
+    MIMO_CHECK(part != nullptr, MIMO_ERR_ARG, "laplace_fwd: partial buffer required for the mean");
+    sum_partials_kernel<<<1, kBlock, 0, st>>>(part, grid, (float)(1.0 / (double)(rows * cols)), out_mean);
+    MIMO_LAUNCH_CHECK();
+  }
+  return MIMO_OK;
+}
+
+int laplace_bwd_launch(const float* mu, long long mu_rs, const float* ls, long long ls_rs, const float* y, long long y_rs,
+                       const float* mask, long long m_rs, long long rows, long long cols, float eps_min, float eps_max,
+                       const float* up, int up_is_scalar, float up_scale, float* g_mu, float* g_ls, cudaStream_t st) {
+  laplace_bwd_kernel<<<grid_for(rows * cols, 4), kBlock, 0, st>>>(mu, mu_rs, ls, ls_rs, y, y_rs, mask, m_rs, rows, cols, eps_min,
+                                                                 eps_max, up, up_is_scalar, up_scale, g_mu, g_ls);
+  MIMO_LAUNCH_CHECK();
+  return MIMO_OK;
+}
+
+size_t lossbuffer_bytes(int S, int size) { return sizeof(LossBufferState) + sizeof(float) * (size_t)S * (size > 0 ? size : 1); }
+
+int lossbuffer_init_launch(void* state, int S, int size, float T, cudaStream_t st) {
+  MIMO_CHECK(T > 0.f, MIMO_ERR_ARG, "Temperature should be positive.");
+  MIMO_CHECK(S >= 1 && S <= 64, MIMO_ERR_ARG, "loss buffer supports 1..64 subnetworks");
+  lossbuffer_init_kernel<<<1, 256, 0, st>>>((LossBufferState*)state, S, size, T);
+  MIMO_LAUNCH_CHECK();
+  return MIMO_OK;
+}
+int lossbuffer_weights_launch(const void* state, float* w, cudaStream_t st) {
+  lossbuffer_weights_kernel<<<1, 32, 0, st>>>((const LossBufferState*)state, w);
+  MIMO_LAUNCH_CHECK();
+  return MIMO_OK;
+}
+int lossbuffer_add_launch(void* state, const float* loss, cudaStream_t st) {
+  lossbuffer_add_kernel<<<1, 32, 0, st>>>((LossBufferState*)state, loss);
+  MIMO_LAUNCH_CHECK();
+  return MIMO_OK;
+}
+
+int laplace_train_blocks(long long n) {
+  long long per_row = ceil_div_ll(n, (long long)kBlock * 16);
+  if (per_row < 1) per_row = 1;
+  if (per_row > 64) per_row = 64;
+  return (int)per_row;
+}
+
+int laplace_train_launch(const float* out, const float* y, long long y_bs, long long y_ss, const float* mask, long long m_bs,
+                         long long m_ss, const long long* gather, int B, int S, int C, long long HW, float eps_min, float eps_max,
+                         void* lb_state, const float* fixed_w, int update_buffer, float* dout, float* part, float* loss,
+                         float* weights, float* weighted, cudaStream_t st) {
+  MIMO_CHECK(S >= 1 && S <= 64, MIMO_ERR_ARG, "laplace_train: 1..64 subnetworks supported");
+  const long long n = (long long)C * HW;
+  const int nblk = laplace_train_blocks(n);
+  dim3 grid(nblk, B * S);
+  laplace_train_kernel<<<grid, kBlock, 0, st>>>(out, y, y_bs, y_ss, mask, m_bs, m_ss, gather, B, S, C, HW, eps_min, eps_max,
+                                                (const LossBufferState*)lb_state, fixed_w, dout, part);
+  MIMO_LAUNCH_CHECK();
+  laplace_train_finalize_kernel<<<1, kBlock, 0, st>>>(part, nblk, B, S, (double)B * (double)n, (LossBufferState*)lb_state, fixed_w,
+                                                      update_buffer, loss, weights, weighted);
+  MIMO_LAUNCH_CHECK();
+  return MIMO_OK;
+}
+
+int scale_by_scalar_launch(float* x, long long n, const float* s, cudaStream_t st) {
+  scale_by_scalar_kernel<<<grid_for(n, 4), kBlock, 0, st>>>(x, n, s);
+  MIMO_LAUNCH_CHECK();
+  return MIMO_OK;
+}
+
+int aggregate_launch(const float* p1, long long p1_bs, long long p1_ss, const float* p2, long long p2_bs, long long p2_ss, int B,
+                     int S, long long inner, float* mean, float* alea, float* epi, cudaStream_t st) {
+  MIMO_CHECK(S >= 1, MIMO_ERR_ARG, "aggregate: S must be >= 1");
+  aggregate_kernel<<<grid_for((long long)B * inner, 2), kBlock, 0, st>>>(p1, p1_bs, p1_ss, p2, p2_bs, p2_ss, B, S, inner, mean, alea, epi);
+  MIMO_LAUNCH_CHECK();
+  return MIMO_OK;
+}
+
+}  // namespace mimo

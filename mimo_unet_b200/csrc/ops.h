@@ -1,0 +1,62 @@
+// Internal C++ launch API shared by the C-ABI wrappers (api.cu) and the U-Net executor (engine.cu).
+// Every function enqueues work on `stream`, never synchronises, never allocates device memory.
+#pragma once
+#include "common.cuh"
+
+namespace mimo {
+
+// ---- tensor-core convolutions (conv_igemm.cu / conv_wgrad.cu) ----
+int conv3x3_block_n(int cout);
+int conv3x3_m_tiles(int n, int out_h, int out_w);
+int conv3x3_launch(const ActView& in, int mode, const bf16* wpacked, int cout, int cin_pitch, bf16* out, int out_cpitch,
+                   float* stat_sum, float* stat_sq, const float* bias, int relu, cudaStream_t stream);
+int conv3x3_wgrad_launch(const ActView& dy, const ActView& x, float* dw_packed, int cin_pitch, cudaStream_t stream);
+int wgrad_unpack_launch(const float* packed, float* grad_oihw, int cout, int cin, int cin_pitch, float scale, int accumulate,
+                        cudaStream_t stream);
+
+// ---- NHWC elementwise / reduction kernels (elementwise.cu) ----
+int pack_input_launch(const float* x, long long sb, long long sc, const long long* gather, const ActView& o, cudaStream_t st);
+int weight_pack_launch(const float* w, int cout, int cin, bf16* wf, int cin_pitch, bf16* wd, int cout_pitch, cudaStream_t st);
+int bn_finalize_launch(const float* psum, const float* psq, int tiles, int cpitch, int C, double count, const float* gamma,
+                       const float* beta, const float* conv_bias, float* rm, float* rv, long long* nbt, float momentum, float eps,
+                       float* scale, float* shift, float* save_mean, float* save_invstd, cudaStream_t st);
+int bn_eval_affine_launch(int C, const float* gamma, const float* beta, const float* conv_bias, const float* rm, const float* rv,
+                          float eps, float* scale, float* shift, float* save_mean, float* save_invstd, cudaStream_t st);
+int bn_relu_apply_launch(const bf16* y, int ycp, const float* scale, const float* shift, const float* drop, const ActView& o,
+                         const ActView* pool, cudaStream_t st);
+int maxpool_launch(const ActView& in, const ActView& o, long long* idx_nchw, cudaStream_t st);
+int upsample_launch(const ActView& in, const ActView& o, cudaStream_t st);
+int upsample_bwd_launch(const ActView& gdst, const ActView& gsrc, int accumulate, cudaStream_t st);
+int grad_gather_launch(const ActView* dpad, const ActView* gpool, const ActView* act, const ActView& gout, int accumulate,
+                       cudaStream_t st);
+int bn_bwd_parts(int C);
+int bn_bwd_launch(const ActView& G, const bf16* y, int ycp, const float* scale, const float* shift, const float* mean,
+                  const float* invstd, const float* drop, int training, float* part, float* s1s2, float* dgamma, float* dbeta,
+                  float* dbias, float grad_scale, int accumulate, bf16* dy, int dycp, cudaStream_t st);
+
+// ---- heads, loss, loss buffer, aggregation (head_loss.cu) ----
+int head_fwd_launch(const ActView& f, const float* W, const float* bias, int K, float* out, long long out_bstride, cudaStream_t st);
+int head_bwd_parts();
+int head_bwd_launch(const ActView& f, const float* W, int K, const float* dout, long long out_bstride, const float* grad_scale,
+                    const ActView& G, float* part, float* dW, float* db, int accumulate, cudaStream_t st);
+int laplace_parts();
+int laplace_fwd_launch(const float* mu, long long mu_rs, const float* ls, long long ls_rs, const float* y, long long y_rs,
+                       const float* mask, long long m_rs, long long rows, long long cols, float eps_min, float eps_max,
+                       float* out_elem, float* part, float* out_mean, cudaStream_t st);
+int laplace_bwd_launch(const float* mu, long long mu_rs, const float* ls, long long ls_rs, const float* y, long long y_rs,
+                       const float* mask, long long m_rs, long long rows, long long cols, float eps_min, float eps_max,
+                       const float* up, int up_is_scalar, float up_scale, float* g_mu, float* g_ls, cudaStream_t st);
+size_t lossbuffer_bytes(int S, int size);
+int lossbuffer_init_launch(void* state, int S, int size, float T, cudaStream_t st);
+int lossbuffer_weights_launch(const void* state, float* w, cudaStream_t st);
+int lossbuffer_add_launch(void* state, const float* loss, cudaStream_t st);
+int laplace_train_blocks(long long n);
+int laplace_train_launch(const float* out, const float* y, long long y_bs, long long y_ss, const float* mask, long long m_bs,
+                         long long m_ss, const long long* gather, int B, int S, int C, long long HW, float eps_min, float eps_max,
+                         void* lb_state, const float* fixed_w, int update_buffer, float* dout, float* part, float* loss,
+                         float* weights, float* weighted, cudaStream_t st);
+int scale_by_scalar_launch(float* x, long long n, const float* s, cudaStream_t st);
+int aggregate_launch(const float* p1, long long p1_bs, long long p1_ss, const float* p2, long long p2_bs, long long p2_ss, int B,
+                     int S, long long inner, float* mean, float* alea, float* epi, cudaStream_t st);
+
+}  // namespace mimo

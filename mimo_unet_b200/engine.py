@@ -1,0 +1,115 @@
+"""UNetPlan: python handle of the C++ whole-network executor (csrc/engine.cu).
+
+PyTorch is plumbing here: it owns the memory (one workspace tensor, one flat gradient tensor) and the
+stream; every FLOP of the network runs in libmimo_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import Act, UnetConfig, check
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class UNetPlan:
+    """Fixed-shape execution plan for MimoUNet (bilinear path) on the current CUDA device."""
+
+    def __init__(self, in_channels: int, out_channels: int, num_subnetworks: int, filter_base_count: int,
+                 batch: int, height: int, width: int, device: torch.device):
+        self.lib = _lib.lib()
+        check(self.lib.mimo_check_device(), "mimo_check_device")
+        self.cfg = UnetConfig(in_channels, out_channels, num_subnetworks, filter_base_count, batch, height, width)
+        self.key = (in_channels, out_channels, num_subnetworks, filter_base_count, batch, height, width)
+        h = C.c_void_p()
+        check(self.lib.mimo_unet_plan_create(C.byref(self.cfg), C.byref(h)), "mimo_unet_plan_create")
+        self.handle = h
+        self.device = device
+        self.ws_bytes = int(self.lib.mimo_unet_workspace_bytes(h))
+        self.workspace = torch.empty(self.ws_bytes, dtype=torch.uint8, device=device)
+        self.n_state = int(self.lib.mimo_unet_num_state(h))
+        self.n_dconv = int(self.lib.mimo_unet_num_double_convs(h))
+        self.drop_channels = [int(self.lib.mimo_unet_dropout_channels(h, i)) for i in range(self.n_dconv)]
+        self._state_keepalive: List[torch.Tensor] = []
+        self._bound_sig = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None) is not None:
+                self.lib.mimo_unet_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    # -- binding -------------------------------------------------------------------------------
+    def bind(self, state: Sequence[torch.Tensor], grads: Sequence[Optional[torch.Tensor]]):
+        """state: tensors in MimoUNet.state_dict() order; grads: matching fp32 destinations or None."""
+        assert len(state) == self.n_state and len(grads) == self.n_state
+        sig = tuple(t.data_ptr() for t in state) + tuple(-1 if g is None else g.data_ptr() for g in grads)
+        if sig == self._bound_sig:
+            return
+        for t in state:
+            assert t.is_cuda and t.is_contiguous(), "parameters must be contiguous CUDA tensors"
+        sp = (C.c_void_p * self.n_state)(*[t.data_ptr() for t in state])
+        gp = (C.c_void_p * self.n_state)(*[_ptr(g) for g in grads])
+        check(self.lib.mimo_unet_bind(self.handle, self.workspace.data_ptr(), self.ws_bytes, sp, gp, self.n_state), "mimo_unet_bind")
+        self._state_keepalive = list(state) + [g for g in grads if g is not None]
+        self._bound_sig = sig
+
+    # -- execution -----------------------------------------------------------------------------
+    def forward(self, x: torch.Tensor, out: torch.Tensor, training: bool, gather: Optional[torch.Tensor] = None,
+                drop_masks: Optional[Sequence[Optional[torch.Tensor]]] = None):
+        assert x.is_contiguous() and x.dtype == torch.float32 and out.is_contiguous() and out.dtype == torch.float32
+        mp = None
+        if drop_masks is not None:
+            assert len(drop_masks) == self.n_dconv
+            mp = (C.c_void_p * self.n_dconv)(*[_ptr(m) for m in drop_masks])
+            self._mask_keepalive = list(drop_masks)
+        check(self.lib.mimo_unet_forward(self.handle, x.data_ptr(), _ptr(gather), int(training), mp, out.data_ptr(), stream_ptr()),
+              "mimo_unet_forward")
+
+    def backward(self, dout: torch.Tensor, dx: Optional[torch.Tensor] = None, grad_scale: Optional[torch.Tensor] = None,
+                 accumulate: bool = False):
+        assert dout.is_contiguous() and dout.dtype == torch.float32
+        check(self.lib.mimo_unet_backward(self.handle, dout.data_ptr(), _ptr(grad_scale), _ptr(dx), int(accumulate), stream_ptr()),
+              "mimo_unet_backward")
+
+    @property
+    def last_launches(self) -> int:
+        return int(self.lib.mimo_unet_last_launches(self.handle))
+
+    # -- test hook -----------------------------------------------------------------------------
+    def debug_tensor(self, name: str) -> torch.Tensor:
+        """Returns an fp32 NCHW copy of a named intermediate (interior only) or an fp32 vector."""
+        a = Act()
+        kind = C.c_int()
+        check(self.lib.mimo_unet_debug_view(self.handle, name.encode(), C.byref(a), C.byref(kind)), "mimo_unet_debug_view")
+        base = self.workspace.data_ptr()
+        off = a.ptr - base
+        if kind.value == 1:
+            return self.workspace[off: off + 4 * a.c].view(torch.float32).clone()
+        Hp, Wp = a.h + 2 * a.pad, a.w + 2 * a.pad
+        nbytes = a.n * Hp * Wp * a.cpitch * 2
+        t = self.workspace[off: off + nbytes].view(torch.bfloat16).view(a.n, Hp, Wp, a.cpitch)
+        t = t[:, a.pad: a.pad + a.h, a.pad: a.pad + a.w, a.c_off: a.c_off + a.c]
+        return t.permute(0, 3, 1, 2).float().contiguous()
+
+    def debug_tensor_padded(self, name: str) -> torch.Tensor:
+        """fp32 NCHW copy including the halo."""
+        a = Act()
+        kind = C.c_int()
+        check(self.lib.mimo_unet_debug_view(self.handle, name.encode(), C.byref(a), C.byref(kind)), "mimo_unet_debug_view")
+        off = a.ptr - self.workspace.data_ptr()
+        Hp, Wp = a.h + 2 * a.pad, a.w + 2 * a.pad
+        t = self.workspace[off: off + a.n * Hp * Wp * a.cpitch * 2].view(torch.bfloat16).view(a.n, Hp, Wp, a.cpitch)
+        return t[..., a.c_off: a.c_off + a.c].permute(0, 3, 1, 2).float().contiguous()

@@ -1,0 +1,355 @@
+"""Per-kernel ("teacher-forced") parity on the GPU: every kernel gets bf16-rounded oracle inputs and is compared
+with the oracle result rounded at the same storage point (SURVEY 8c / App. F protocol).
+Tolerances: rel-L2 <= 1e-3 for bf16 tensor-core kernels (fp32 accumulate), bit-exact for indices."""
+import ctypes as C
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from mimo_unet_b200 import _lib
+from oracle import mimo_oracle as O
+from tests.util import act_of, bf16r, get_nchw, make_buffer, p8, put_nchw, rel_l2, stream
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def lib():
+    l = _lib.lib()
+    _lib.check(l.mimo_check_device(), "check_device")
+    return l
+
+
+def _pack_weights(lib, w):
+    cout, cin = w.shape[0], w.shape[1]
+    wf = torch.zeros(9, cout, p8(cin), dtype=torch.bfloat16, device="cuda")
+    wd = torch.zeros(9, cin, p8(cout), dtype=torch.bfloat16, device="cuda")
+    _lib.check(lib.mimo_weight_pack(w.data_ptr(), cout, cin, wf.data_ptr(), p8(cin), wd.data_ptr(), p8(cout), stream()))
+    return wf, wd
+
+
+CONV_CASES = [
+    # N, Cin, Cout, H, W
+    (2, 3, 21, 32, 32),
+    (2, 21, 21, 37, 45),
+    (3, 63, 31, 16, 24),
+    (2, 84, 168, 16, 20),
+    (1, 168, 336, 8, 10),
+    (2, 672, 336, 8, 10),
+    (4, 64, 64, 64, 64),
+    (2, 30, 45, 2, 3),
+]
+
+
+@pytest.mark.parametrize("N,Cin,Cout,H,W", CONV_CASES)
+def test_weight_pack_and_conv_fprop(lib, N, Cin, Cout, H, W):
+    torch.manual_seed(1)
+    x = bf16r(torch.randn(N, Cin, H, W, device="cuda"))
+    w = torch.randn(Cout, Cin, 3, 3, device="cuda") / math.sqrt(9 * Cin)
+    wf, wd = _pack_weights(lib, w)
+    wq = bf16r(w)
+    # packing parity (bit exact)
+    assert torch.equal(wf[:, :, :Cin].float(), wq.permute(2, 3, 0, 1).reshape(9, Cout, Cin))
+    assert torch.equal(wd[:, :, :Cout].float(), wq.flip(2, 3).permute(2, 3, 1, 0).reshape(9, Cin, Cout))
+    xb = make_buffer(N, H, W, 1, p8(Cin))
+    put_nchw(xb, x, 1)
+    yb = make_buffer(N, H, W, 0, p8(Cout))
+    tiles = lib.mimo_conv3x3_m_tiles(N, H, W)
+    ssum = torch.full((tiles, p8(Cout)), float("nan"), device="cuda")
+    ssq = torch.full((tiles, p8(Cout)), float("nan"), device="cuda")
+    _lib.check(lib.mimo_conv3x3(act_of(xb, 1, 0, Cin), 0, wf.data_ptr(), Cout, p8(Cin), yb.data_ptr(), p8(Cout), ssum.data_ptr(),
+                                ssq.data_ptr(), None, 0, stream()), "conv3x3")
+    torch.cuda.synchronize()
+    ref = O.conv3x3_reflect(x, wq, None)
+    got = get_nchw(yb, 0, 0, Cout)
+    err = rel_l2(got, bf16r(ref))
+    assert err <= TOL, f"fprop rel-L2 {err}"
+    # pad channels are written as exact zeros
+    if p8(Cout) > Cout:
+        assert torch.all(yb[..., Cout:] == 0)
+    # BatchNorm partial statistics of the stored values
+    s = ssum.sum(0)[:Cout]
+    q = ssq.sum(0)[:Cout]
+    assert rel_l2(s, got.sum(dim=(0, 2, 3))) <= 1e-4 or float((s - got.sum(dim=(0, 2, 3))).abs().max()) < 1e-2
+    assert rel_l2(q, (got * got).sum(dim=(0, 2, 3))) <= 1e-4
+
+
+@pytest.mark.parametrize("N,Cin,Cout,H,W", CONV_CASES)
+def test_conv_dgrad(lib, N, Cin, Cout, H, W):
+    torch.manual_seed(2)
+    dy = bf16r(torch.randn(N, Cout, H, W, device="cuda"))
+    w = torch.randn(Cout, Cin, 3, 3, device="cuda") / math.sqrt(9 * Cin)
+    wf, wd = _pack_weights(lib, w)
+    dyb = make_buffer(N, H, W, 0, p8(Cout), fill=0.0)
+    put_nchw(dyb, dy, 0)
+    dpad = make_buffer(N, H + 2, W + 2, 0, p8(Cin))
+    _lib.check(lib.mimo_conv3x3(act_of(dyb, 0, 0, Cout), 1, wd.data_ptr(), Cin, p8(Cout), dpad.data_ptr(), p8(Cin), None, None, None, 0,
+                                stream()), "dgrad")
+    # gradient w.r.t. the PADDED input of a valid conv == full correlation with the flipped kernel
+    ref_pad = F.conv_transpose2d(dy, bf16r(w))
+    got_pad = get_nchw(dpad, 0, 0, Cin)
+    assert rel_l2(got_pad, bf16r(ref_pad)) <= TOL
+    # fold the reflect halo back (adjoint of F.pad reflect) and compare with autograd of the oracle conv
+    g = make_buffer(N, H, W, 0, p8(Cin))
+    a = act_of(dpad, 0, 0, Cin)
+    _lib.check(lib.mimo_grad_gather(C.byref(a), None, None, act_of(g, 0, 0, Cin), 0, stream()), "grad_gather")
+    xg = torch.zeros(N, Cin, H, W, device="cuda", requires_grad=True)
+    O.conv3x3_reflect(xg, bf16r(w), None).backward(dy)
+    # the fold sums up to 4 bf16-rounded values, so compare against the fold of the rounded padded gradient
+    ref_fold = torch.zeros(N, Cin, H, W, device="cuda", requires_grad=True)
+    F.pad(ref_fold, (1, 1, 1, 1), mode="reflect").backward(got_pad)
+    assert rel_l2(get_nchw(g, 0, 0, Cin), bf16r(ref_fold.grad)) <= TOL
+    assert rel_l2(get_nchw(g, 0, 0, Cin), xg.grad) <= 4e-3  # vs exact autograd: two bf16 roundings
+
+
+@pytest.mark.parametrize("N,Cin,Cout,H,W", CONV_CASES)
+def test_conv_wgrad(lib, N, Cin, Cout, H, W):
+    torch.manual_seed(3)
+    x = bf16r(torch.randn(N, Cin, H, W, device="cuda"))
+    dy = bf16r(torch.randn(N, Cout, H, W, device="cuda"))
+    xb = make_buffer(N, H, W, 1, p8(Cin))
+    put_nchw(xb, x, 1)
+    dyb = make_buffer(N, H, W, 0, p8(Cout), fill=0.0)
+    put_nchw(dyb, dy, 0)
+    scratch = torch.empty(9 * Cout * p8(Cin), device="cuda")
+    grad = torch.full((Cout, Cin, 3, 3), float("nan"), device="cuda")
+    _lib.check(lib.mimo_conv3x3_wgrad(act_of(dyb, 0, 0, Cout), act_of(xb, 1, 0, Cin), scratch.data_ptr(), p8(Cin), grad.data_ptr(), 0,
+                                      stream()), "wgrad")
+    w = torch.zeros(Cout, Cin, 3, 3, device="cuda", requires_grad=True)
+    O.conv3x3_reflect(x, w, None).backward(dy)
+    assert rel_l2(grad, w.grad) <= TOL
+    # accumulate mode adds onto the existing gradient
+    _lib.check(lib.mimo_conv3x3_wgrad(act_of(dyb, 0, 0, Cout), act_of(xb, 1, 0, Cin), scratch.data_ptr(), p8(Cin), grad.data_ptr(), 1,
+                                      stream()), "wgrad")
+    assert rel_l2(grad, 2 * w.grad) <= TOL
+
+
+def test_conv_eval_epilogue_bias_relu(lib):
+    torch.manual_seed(4)
+    N, Cin, Cout, H, W = 2, 16, 24, 12, 20
+    x = bf16r(torch.randn(N, Cin, H, W, device="cuda"))
+    w = torch.randn(Cout, Cin, 3, 3, device="cuda") / math.sqrt(9 * Cin)
+    b = torch.randn(Cout, device="cuda")
+    wf, _ = _pack_weights(lib, w)
+    xb = make_buffer(N, H, W, 1, p8(Cin))
+    put_nchw(xb, x, 1)
+    yb = make_buffer(N, H, W, 0, p8(Cout))
+    _lib.check(lib.mimo_conv3x3(act_of(xb, 1, 0, Cin), 0, wf.data_ptr(), Cout, p8(Cin), yb.data_ptr(), p8(Cout), None, None,
+                                b.data_ptr(), 1, stream()))
+    ref = F.relu(O.conv3x3_reflect(x, bf16r(w), b))
+    assert rel_l2(get_nchw(yb, 0, 0, Cout), bf16r(ref)) <= TOL
+
+
+def test_pack_input_gather_and_halo(lib):
+    torch.manual_seed(5)
+    B, S, Cc, H, W = 5, 2, 3, 9, 11
+    x = torch.rand(B, S, Cc, H, W, device="cuda")
+    gather = torch.tensor([3, 1, 4, 0, 2], device="cuda")
+    for s in range(S):
+        buf = make_buffer(B, H, W, 1, 8)
+        _lib.check(lib.mimo_pack_input(x[:, s].data_ptr(), S * Cc * H * W, H * W, gather.data_ptr(), act_of(buf, 1, 0, Cc), stream()))
+        ref = F.pad(bf16r(x[gather, s]), (1, 1, 1, 1), mode="reflect")
+        assert torch.equal(get_nchw(buf, 1, 0, Cc, with_halo=True), ref)
+
+
+@pytest.mark.parametrize("H,W,CH,c_off,cp", [(8, 10, 21, 0, 24), (9, 11, 42, 42, 88), (3, 3, 5, 8, 16), (2, 2, 8, 0, 8), (37, 45, 21, 0, 64)])
+def test_bn_finalize_apply_pool(lib, H, W, CH, c_off, cp):
+    torch.manual_seed(6)
+    N = 3
+    y = bf16r(torch.randn(N, CH, H, W, device="cuda") * 2 + 0.5)
+    yb = make_buffer(N, H, W, 0, p8(CH), fill=0.0)
+    put_nchw(yb, y, 0)
+    gamma, beta, bias = torch.rand(CH, device="cuda") + 0.5, torch.randn(CH, device="cuda") * 0.2, torch.randn(CH, device="cuda") * 0.1
+    rm, rv = torch.randn(CH, device="cuda") * 0.2, torch.rand(CH, device="cuda") + 0.5
+    rm0, rv0 = rm.clone(), rv.clone()
+    nbt = torch.tensor(3, device="cuda")
+    # partial statistics as the conv epilogue would produce them (2 fake tiles)
+    ssum = torch.zeros(2, p8(CH), device="cuda")
+    ssq = torch.zeros(2, p8(CH), device="cuda")
+    ssum[0, :CH] = y[:1].sum(dim=(0, 2, 3)); ssum[1, :CH] = y[1:].sum(dim=(0, 2, 3))
+    ssq[0, :CH] = (y[:1] ** 2).sum(dim=(0, 2, 3)); ssq[1, :CH] = (y[1:] ** 2).sum(dim=(0, 2, 3))
+    vec = torch.empty(4, p8(CH), device="cuda")
+    _lib.check(lib.mimo_bn_finalize(ssum.data_ptr(), ssq.data_ptr(), 2, p8(CH), CH, float(N * H * W), gamma.data_ptr(), beta.data_ptr(),
+                                    bias.data_ptr(), rm.data_ptr(), rv.data_ptr(), nbt.data_ptr(), 0.1, 1e-5, vec[0].data_ptr(),
+                                    vec[1].data_ptr(), vec[2].data_ptr(), vec[3].data_ptr(), stream()))
+    out_ref, mean, var = O.batchnorm_train(y, gamma, beta)
+    erm, erv = O.updated_running_stats(rm0, rv0, mean + bias, var, N * H * W)
+    assert torch.allclose(vec[2, :CH], mean, atol=1e-5) and torch.allclose(vec[3, :CH], torch.rsqrt(var + 1e-5), rtol=1e-4)
+    assert torch.allclose(rm, erm, atol=1e-5) and torch.allclose(rv, erv, rtol=1e-5) and int(nbt) == 4
+    drop = (torch.rand(N, CH, device="cuda") > 0.3).float() / 0.7
+    ob = make_buffer(N, H, W, 1, cp)
+    pb = make_buffer(N, H // 2, W // 2, 1, cp) if H // 2 >= 2 and W // 2 >= 2 else None
+    pool_act = act_of(pb, 1, c_off, CH) if pb is not None else None
+    _lib.check(lib.mimo_bn_relu_apply(yb.data_ptr(), p8(CH), vec[0].data_ptr(), vec[1].data_ptr(), drop.data_ptr(), act_of(ob, 1, c_off, CH),
+                                      C.byref(pool_act) if pool_act is not None else None, stream()))
+    act_ref = bf16r(F.relu(out_ref) * drop[:, :, None, None])
+    got = get_nchw(ob, 1, c_off, CH, with_halo=True)
+    assert rel_l2(got[:, :, 1:-1, 1:-1], act_ref) <= TOL
+    # halo == reflect padding of the stored interior (bit exact)
+    assert torch.equal(got, F.pad(got[:, :, 1:-1, 1:-1], (1, 1, 1, 1), mode="reflect"))
+    if pb is not None:
+        gp = get_nchw(pb, 1, c_off, CH, with_halo=True)
+        assert torch.equal(gp[:, :, 1:-1, 1:-1], F.max_pool2d(got[:, :, 1:-1, 1:-1], 2))
+        assert torch.equal(gp, F.pad(gp[:, :, 1:-1, 1:-1], (1, 1, 1, 1), mode="reflect"))
+    # channels outside the slice are untouched (still NaN)
+    if c_off > 0:
+        assert torch.isnan(ob[..., :c_off].float()).all()
+
+
+def test_bn_eval_affine(lib):
+    C_ = 21
+    gamma, beta, bias = torch.rand(C_, device="cuda") + 0.5, torch.randn(C_, device="cuda"), torch.randn(C_, device="cuda")
+    rm, rv = torch.randn(C_, device="cuda"), torch.rand(C_, device="cuda") + 0.5
+    vec = torch.empty(4, 24, device="cuda")
+    _lib.check(lib.mimo_bn_eval_affine(C_, gamma.data_ptr(), beta.data_ptr(), bias.data_ptr(), rm.data_ptr(), rv.data_ptr(), 1e-5,
+                                       vec[0].data_ptr(), vec[1].data_ptr(), vec[2].data_ptr(), vec[3].data_ptr(), stream()))
+    y = torch.randn(2, C_, 4, 4, device="cuda")
+    ref = O.batchnorm_eval(y + bias[None, :, None, None], gamma, beta, rm, rv)
+    got = y * vec[0, :C_][None, :, None, None] + vec[1, :C_][None, :, None, None]
+    assert torch.allclose(got, ref, atol=1e-5, rtol=1e-5)
+
+
+def test_maxpool_indices_golden(lib, golden_dir):
+    g = torch.load(f"{golden_dir}/op_cases.pt")["components"]["maxpool"]
+    x, pooled, idx = g["x"].cuda(), g["pooled"].cuda(), g["idx"].cuda()
+    xq = bf16r(x)
+    N, Cc, H, W = x.shape
+    xb = make_buffer(N, H, W, 1, p8(Cc))
+    put_nchw(xb, xq, 1)
+    ob = make_buffer(N, H // 2, W // 2, 0, p8(Cc))
+    ib = torch.full((N, Cc, H // 2, W // 2), -1, dtype=torch.int64, device="cuda")
+    _lib.check(lib.mimo_maxpool2x2(act_of(xb, 1, 0, Cc), act_of(ob, 0, 0, Cc), ib.data_ptr(), stream()))
+    # values are bf16-rounded before pooling -> compare with the oracle fed the same rounded input
+    pr, ir = F.max_pool2d(xq, 2, return_indices=True)
+    assert torch.equal(get_nchw(ob, 0, 0, Cc), pr)
+    assert torch.equal(ib, ir)
+    # rounding is monotone, so the indices also equal the reference's fp32 indices wherever there is no new tie
+    same = (ib == idx)
+    assert same.float().mean() > 0.99
+    assert ib[0, 0, 0, 0] == 0  # tie -> first element wins (reference fixture plants the tie)
+
+
+def test_upsample_fwd_bwd(lib, golden_dir):
+    g = torch.load(f"{golden_dir}/op_cases.pt")["components"]["bilinear"]
+    x = bf16r(g["x"].cuda())
+    N, Cc, H, W = x.shape
+    xb = make_buffer(N, H, W, 1, p8(Cc))
+    put_nchw(xb, x, 1)
+    for (OH, OW) in [(2 * H, 2 * W), (2 * H + 1, 2 * W + 1)]:
+        ob = make_buffer(N, OH, OW, 1, 24)
+        _lib.check(lib.mimo_upsample_bilinear2x(act_of(xb, 1, 0, Cc), act_of(ob, 1, 10, Cc), stream()))
+        ref = O.pad_to(O.upsample_bilinear2x_ac(x), OH, OW)
+        got = get_nchw(ob, 1, 10, Cc, with_halo=True)
+        assert rel_l2(got[:, :, 1:-1, 1:-1], bf16r(ref)) <= TOL
+        assert torch.equal(got, F.pad(got[:, :, 1:-1, 1:-1], (1, 1, 1, 1), mode="reflect"))
+        # backward (gather form) against autograd
+        gdst = bf16r(torch.randn(N, Cc, OH, OW, device="cuda"))
+        gb = make_buffer(N, OH, OW, 0, p8(Cc), fill=0.0)
+        put_nchw(gb, gdst, 0)
+        gs = make_buffer(N, H, W, 0, p8(Cc))
+        _lib.check(lib.mimo_upsample_bilinear2x_bwd(act_of(gb, 0, 0, Cc), act_of(gs, 0, 0, Cc), 0, stream()))
+        xg = x.clone().requires_grad_(True)
+        O.pad_to(O.upsample_bilinear2x_ac(xg), OH, OW).backward(gdst)
+        assert rel_l2(get_nchw(gs, 0, 0, Cc), bf16r(xg.grad)) <= TOL
+    # the reference's golden forward (fp32) within bf16 storage error
+    ob = make_buffer(N, 2 * H, 2 * W, 1, p8(Cc))
+    _lib.check(lib.mimo_upsample_bilinear2x(act_of(xb, 1, 0, Cc), act_of(ob, 1, 0, Cc), stream()))
+    assert rel_l2(get_nchw(ob, 1, 0, Cc), g["y"].cuda()) <= 6e-3
+
+
+@pytest.mark.parametrize("H,W", [(8, 10), (9, 11), (3, 3)])
+def test_grad_gather_fold_and_pool_bwd(lib, H, W):
+    torch.manual_seed(7)
+    N, Cc = 2, 13
+    act = bf16r(torch.randn(N, Cc, H, W, device="cuda"))
+    act[0, 0, 0, 0] = act[0, 0, 0, 1] = 3.0  # tie inside the first window
+    ab = make_buffer(N, H, W, 1, 16)
+    put_nchw(ab, act, 1)
+    dpad = bf16r(torch.randn(N, Cc, H + 2, W + 2, device="cuda"))
+    db = make_buffer(N, H + 2, W + 2, 0, 16, fill=0.0)
+    put_nchw(db, dpad, 0)
+    gp = bf16r(torch.randn(N, Cc, H // 2, W // 2, device="cuda"))
+    gpb = make_buffer(N, max(H // 2, 1), max(W // 2, 1), 0, 16, fill=0.0)
+    put_nchw(gpb, gp, 0)
+    gout = make_buffer(N, H, W, 0, 16)
+    a, b, c = act_of(db, 0, 0, Cc), act_of(gpb, 0, 0, Cc), act_of(ab, 1, 0, Cc)
+    _lib.check(lib.mimo_grad_gather(C.byref(a), C.byref(b), C.byref(c), act_of(gout, 0, 0, Cc), 0, stream()))
+    xa = act.clone().requires_grad_(True)
+    (F.pad(xa, (1, 1, 1, 1), mode="reflect") * dpad).sum().backward()
+    fold = xa.grad.clone()
+    xa.grad = None
+    (F.max_pool2d(xa, 2) * gp).sum().backward()
+    ref = fold + xa.grad
+    assert rel_l2(get_nchw(gout, 0, 0, Cc), bf16r(ref)) <= TOL
+
+
+@pytest.mark.parametrize("training", [1, 0])
+@pytest.mark.parametrize("C_,c_off,gcp", [(21, 0, 24), (42, 42, 88), (336, 0, 336)])
+def test_bn_relu_bwd(lib, training, C_, c_off, gcp):
+    torch.manual_seed(8)
+    N, H, W = 3, 6, 7
+    y = bf16r(torch.randn(N, C_, H, W, device="cuda") * 1.5 + 0.3)
+    G = bf16r(torch.randn(N, C_, H, W, device="cuda"))
+    gamma, beta = torch.rand(C_, device="cuda") + 0.5, torch.randn(C_, device="cuda") * 0.3
+    drop = (torch.rand(N, C_, device="cuda") > 0.2).float() / 0.8
+    yq = y.clone().requires_grad_(True)
+    gq, bq = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    if training:
+        z, mean, var = O.batchnorm_train(yq, gq, bq)
+        invstd = torch.rsqrt(var + 1e-5).detach()
+        mean = mean.detach()
+    else:
+        mean, invstd = torch.randn(C_, device="cuda") * 0.2, torch.rsqrt(torch.rand(C_, device="cuda") + 0.5)
+        z = (yq - mean[None, :, None, None]) * (invstd * gq)[None, :, None, None] + bq[None, :, None, None]
+    (F.relu(z) * drop[:, :, None, None] * G).sum().backward()
+    scale = (gamma * invstd).contiguous()
+    shift = (beta - mean * gamma * invstd).contiguous()
+    yb = make_buffer(N, H, W, 0, p8(C_), fill=0.0)
+    put_nchw(yb, y, 0)
+    gb = make_buffer(N, H, W, 0, gcp, fill=0.0)
+    put_nchw(gb, G, 0, c_off)
+    dyb = make_buffer(N, H, W, 0, p8(C_))
+    part = torch.empty(int(lib.mimo_bn_bwd_scratch_floats(C_)), device="cuda")
+    s1s2 = torch.empty(2 * C_, device="cuda")
+    dgamma, dbeta, dbias = (torch.full((C_,), float("nan"), device="cuda") for _ in range(3))
+    _lib.check(lib.mimo_bn_relu_bwd(act_of(gb, 0, c_off, C_), yb.data_ptr(), p8(C_), scale.data_ptr(), shift.data_ptr(), mean.contiguous().data_ptr(),
+                                    invstd.contiguous().data_ptr(), drop.data_ptr(), training, part.data_ptr(), s1s2.data_ptr(), dgamma.data_ptr(),
+                                    dbeta.data_ptr(), dbias.data_ptr(), 0, dyb.data_ptr(), p8(C_), stream()))
+    assert rel_l2(get_nchw(dyb, 0, 0, C_), bf16r(yq.grad)) <= TOL
+    assert rel_l2(dgamma, gq.grad) <= 1e-4 and rel_l2(dbeta, bq.grad) <= 1e-4
+    if training:
+        assert torch.all(dbias == 0)
+    else:
+        assert rel_l2(dbias, yq.grad.sum(dim=(0, 2, 3))) <= 1e-2
+    if p8(C_) > C_:
+        assert torch.all(dyb[..., C_:] == 0)
+
+
+def test_head_fwd_bwd(lib):
+    torch.manual_seed(9)
+    B, S, f, K, H, W = 3, 2, 21, 2, 9, 11
+    feat = bf16r(torch.rand(B, f, H, W, device="cuda"))
+    w, b = torch.randn(K, f, device="cuda") * 0.3, torch.randn(K, device="cuda")
+    fb = make_buffer(B, H, W, 1, p8(f))
+    put_nchw(fb, feat, 1)
+    out = torch.full((B, S, K, H, W), float("nan"), device="cuda")
+    s = 1
+    _lib.check(lib.mimo_head1x1(act_of(fb, 1, 0, f), w.data_ptr(), b.data_ptr(), K, out[:, s].data_ptr(), S * K * H * W, stream()))
+    ref = F.conv2d(feat, w[:, :, None, None], b)
+    assert torch.allclose(out[:, s], ref, atol=1e-5, rtol=1e-5) and torch.isnan(out[:, 0]).all()
+    dout = torch.randn(B, S, K, H, W, device="cuda")
+    gs = torch.tensor(4.0, device="cuda")
+    gb = make_buffer(B, H, W, 0, p8(f))
+    part = torch.empty(int(lib.mimo_head1x1_bwd_scratch_floats(K, f)), device="cuda")
+    dw, db = torch.full((K, f), float("nan"), device="cuda"), torch.full((K,), float("nan"), device="cuda")
+    _lib.check(lib.mimo_head1x1_bwd(act_of(fb, 1, 0, f), w.data_ptr(), K, dout[:, s].data_ptr(), S * K * H * W, gs.data_ptr(),
+                                    act_of(gb, 0, 0, f), part.data_ptr(), dw.data_ptr(), db.data_ptr(), 0, stream()))
+    fq = feat.clone().requires_grad_(True)
+    wq, bq = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    (F.conv2d(fq, wq[:, :, None, None], bq) * dout[:, s] * 4.0).sum().backward()
+    assert rel_l2(get_nchw(gb, 0, 0, f), bf16r(fq.grad)) <= TOL
+    assert rel_l2(dw, wq.grad) <= 1e-5 and rel_l2(db, bq.grad) <= 1e-5
+    assert torch.all(gb[..., f:] == 0)
