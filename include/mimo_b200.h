@@ -97,6 +97,12 @@ int mimo_maxpool2x2(mimo_act_t in, mimo_act_t out, long long* idx_nchw, void* st
 /* nn.Upsample(x2, bilinear, align_corners=True) + F.pad to the skip size (components.py:78,112-115) into `out` */
 int mimo_upsample_bilinear2x(mimo_act_t in, mimo_act_t out, void* stream);
 int mimo_upsample_bilinear2x_bwd(mimo_act_t g_out, mimo_act_t g_in, int accumulate, void* stream);
+/* nn.MaxUnpool2d(2) (components.py:87): `in` pooled map, idx_nchw int64 [n][c][h][w] (flat h*W+w of the output) */
+int mimo_maxunpool2x2(mimo_act_t in, const long long* idx_nchw, mimo_act_t out, void* stream);
+/* nn.ConvTranspose2d(cin, cout, kernel_size=2, stride=2) (components.py:96-98): w fp32 [cin][cout][2][2] */
+int mimo_convtranspose2x2(mimo_act_t in, const float* w, const float* bias, mimo_act_t out, void* stream);
+/* NHWC bf16 view -> contiguous fp32 NCHW (component-level API boundary) */
+int mimo_unpack_nchw(mimo_act_t in, float* out, void* stream);
 /* G = fold_reflect(dpad) [+ maxpool backward of gpool through act]; any of dpad / (gpool, act) may be NULL */
 int mimo_grad_gather(const mimo_act_t* dpad, const mimo_act_t* gpool, const mimo_act_t* act, mimo_act_t g_out,
                      int accumulate, void* stream);
@@ -171,8 +177,10 @@ int mimo_unet_dropout_channels(const mimo_unet_plan_t* plan, int i);
 /* state[i]: device pointer of state_dict entry i; grads[i]: fp32 gradient destination or NULL */
 int mimo_unet_bind(mimo_unet_plan_t* plan, void* workspace, size_t workspace_bytes, void* const* state, void* const* grads,
                    int n);
-/* x fp32 [B][S][Cin][H][W]; gather: device int64 [S][B] or NULL; drop_masks[i]: device fp32 or NULL (may be NULL
- * altogether); out fp32 [B][S][Cout][H][W]. training: batch statistics (+ running-stat update) vs running stats. */
+/* x fp32 [B][S][Cin][H][W] when gather == NULL; with gather (device int64 [S][B]) x is the un-shuffled batch
+ * [B][Cin][H][W] and subnetwork s reads image gather[s*B + b] (apply_input_transform, mimo/models/utils.py:27-41).
+ * drop_masks[i]: device fp32 [B][channels] keep-scales of double conv i or NULL (array may be NULL altogether);
+ * out fp32 [B][S][Cout][H][W]. training: batch statistics (+ running-stat update) vs running statistics. */
 int mimo_unet_forward(mimo_unet_plan_t* plan, const float* x, const long long* gather, int training,
                       const float* const* drop_masks, float* out, void* stream);
 /* dout fp32 like out; grad_scale: device scalar multiplier or NULL; dx: fp32 like x or NULL (input gradient,
@@ -184,6 +192,11 @@ int mimo_unet_backward(mimo_unet_plan_t* plan, const float* dout, const float* g
 int mimo_unet_debug_view(const mimo_unet_plan_t* plan, const char* name, mimo_act_t* view, int* kind);
 /* number of kernels the last forward / backward enqueued (bench.py's gpu_launches) */
 int mimo_unet_last_launches(const mimo_unet_plan_t* plan);
+/* optional per-launch CUDA-event timing by kernel class (records events on the caller's stream; read synchronises) */
+int mimo_unet_profile_classes(void);
+const char* mimo_unet_profile_class_name(int i);
+int mimo_unet_profile_enable(mimo_unet_plan_t* plan, int on);
+int mimo_unet_profile_read(mimo_unet_plan_t* plan, float* ms_by_class, int* count_by_class);
 
 #ifdef __cplusplus
 }

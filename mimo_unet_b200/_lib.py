@@ -62,6 +62,9 @@ SIGNATURES = {
     "mimo_maxpool2x2": (i32, [Act, Act, vp, vp]),
     "mimo_upsample_bilinear2x": (i32, [Act, Act, vp]),
     "mimo_upsample_bilinear2x_bwd": (i32, [Act, Act, i32, vp]),
+    "mimo_maxunpool2x2": (i32, [Act, vp, Act, vp]),
+    "mimo_convtranspose2x2": (i32, [Act, vp, vp, Act, vp]),
+    "mimo_unpack_nchw": (i32, [Act, vp, vp]),
     "mimo_grad_gather": (i32, [ActP, ActP, ActP, Act, i32, vp]),
     "mimo_bn_bwd_scratch_floats": (sz, [i32]),
     "mimo_bn_relu_bwd": (i32, [Act, vp, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, i32, vp, i32, vp]),
@@ -91,6 +94,10 @@ SIGNATURES = {
     "mimo_unet_backward": (i32, [vp, vp, vp, vp, i32, vp]),
     "mimo_unet_debug_view": (i32, [vp, C.c_char_p, ActP, C.POINTER(i32)]),
     "mimo_unet_last_launches": (i32, [vp]),
+    "mimo_unet_profile_classes": (i32, []),
+    "mimo_unet_profile_class_name": (C.c_char_p, [i32]),
+    "mimo_unet_profile_enable": (i32, [vp, i32]),
+    "mimo_unet_profile_read": (i32, [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
 }
 
 

@@ -84,6 +84,21 @@ int mimo_upsample_bilinear2x(mimo_act_t in, mimo_act_t out, void* stream) {
   return upsample_launch(make_view(in), make_view(out), (cudaStream_t)stream);
 }
 
+int mimo_maxunpool2x2(mimo_act_t in, const long long* idx_nchw, mimo_act_t out, void* stream) {
+  MIMO_CHECK(in.ptr && idx_nchw && out.ptr, MIMO_ERR_ARG, "maxunpool: null pointer");
+  return maxunpool_launch(make_view(in), idx_nchw, make_view(out), (cudaStream_t)stream);
+}
+
+int mimo_convtranspose2x2(mimo_act_t in, const float* w, const float* bias, mimo_act_t out, void* stream) {
+  MIMO_CHECK(in.ptr && w && out.ptr, MIMO_ERR_ARG, "convtranspose2x2: null pointer");
+  return convtranspose2x2_launch(make_view(in), w, bias, make_view(out), (cudaStream_t)stream);
+}
+
+int mimo_unpack_nchw(mimo_act_t in, float* out, void* stream) {
+  MIMO_CHECK(in.ptr && out, MIMO_ERR_ARG, "unpack_nchw: null pointer");
+  return unpack_nchw_launch(make_view(in), out, (cudaStream_t)stream);
+}
+
 int mimo_upsample_bilinear2x_bwd(mimo_act_t g_out, mimo_act_t g_in, int accumulate, void* stream) {
   MIMO_CHECK(g_out.ptr && g_in.ptr, MIMO_ERR_ARG, "upsample_bwd: null pointer");
   return upsample_bwd_launch(make_view(g_out), make_view(g_in), accumulate, (cudaStream_t)stream);

@@ -500,6 +500,80 @@ __global__ void bn_bwd_apply_kernel(ActView G, const bf16* __restrict__ y, int y
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Component-level up-sampling alternatives of `Up` (components.py:86-98). The reference cannot run them at
+// whole-model level, so they are plain CUDA-core kernels, not tensor-core paths.
+// ------------------------------------------------------------------------------------------------
+// nn.MaxUnpool2d(2): scatter by the pooling indices, expressed as a gather over the output
+__global__ void maxunpool_kernel(ActView in, const long long* __restrict__ idx_nchw, ActView o, int off_h, int off_w) {
+  const int groups = (o.C + 7) >> 3;
+  const long long total = (long long)o.N * o.H * o.W * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    long long r = i / groups;
+    const int w = (int)(r % o.W); r /= o.W;
+    const int h = (int)(r % o.H);
+    const int n = (int)(r / o.H);
+    const int c = g * 8, nv = min(8, o.C - c);
+    float v[8], out[8];
+    const int y = h - off_h, x = w - off_w;  // position inside the exact-2x unpooled map (rest is F.pad zeros)
+    const int ph = y >> 1, pw = x >> 1;
+    const bool inside = y >= 0 && x >= 0 && ph < in.H && pw < in.W;
+    if (inside) load8(in.base + in.pix(n, ph, pw) + c, nv, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      out[k] = 0.f;
+      if (inside && k < nv) {
+        const long long id = idx_nchw[(((size_t)n * o.C + c + k) * in.H + ph) * in.W + pw];
+        if (id == (long long)y * (2 * in.W) + x) out[k] = v[k];
+      }
+    }
+    store_with_halo(o, n, h, w, c, nv, out);
+  }
+}
+
+// nn.ConvTranspose2d(cin, cout, kernel_size=2, stride=2): every input pixel writes a disjoint 2x2 block
+__global__ void convtranspose2x2_kernel(ActView in, const float* __restrict__ wt /*[cin][cout][2][2]*/, const float* __restrict__ bias,
+                                        ActView o, int off_h, int off_w) {
+  const int groups = (o.C + 7) >> 3;
+  const long long total = (long long)o.N * o.H * o.W * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    long long r = i / groups;
+    const int w = (int)(r % o.W); r /= o.W;
+    const int h = (int)(r % o.H);
+    const int n = (int)(r / o.H);
+    const int c = g * 8, nv = min(8, o.C - c);
+    const int y = h - off_h, x = w - off_w;
+    const bool inside = y >= 0 && x >= 0 && (y >> 1) < in.H && (x >> 1) < in.W;
+    const int tap = (y & 1) * 2 + (x & 1);
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = (inside && k < nv && bias) ? bias[c + k] : 0.f;
+    const bf16* src = in.base + in.pix(n, inside ? (y >> 1) : 0, inside ? (x >> 1) : 0);
+    for (int ci = 0; inside && ci < in.C; ++ci) {
+      const float x = __bfloat162float(src[ci]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (k < nv) acc[k] = fmaf(x, wt[((size_t)ci * o.C + c + k) * 4 + tap], acc[k]);
+    }
+    store_with_halo(o, n, h, w, c, nv, acc);
+  }
+}
+
+// NHWC bf16 view -> fp32 NCHW tensor (component-level API boundary)
+__global__ void unpack_nchw_kernel(ActView in, float* __restrict__ out) {
+  const long long total = (long long)in.N * in.C * in.H * in.W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(i % in.W);
+    long long r = i / in.W;
+    const int h = (int)(r % in.H); r /= in.H;
+    const int c = (int)(r % in.C);
+    const int n = (int)(r / in.C);
+    out[i] = __bfloat162float(in.base[in.pix(n, h, w) + c]);
+  }
+}
+
 }  // namespace
 
 // ===================================== launchers =====================================
@@ -602,6 +676,29 @@ int bn_bwd_launch(const ActView& G, const bf16* y, int ycp, const float* scale, 
   const long long total = npix * ((C + 7) / 8);
   bn_bwd_apply_kernel<<<grid_for(total), kBlock, 0, st>>>(G, y, ycp, scale, shift, mean, invstd, drop, s1s2, C, 1.f / (float)npix,
                                                           training, dy, dycp);
+  MIMO_LAUNCH_CHECK();
+  return MIMO_OK;
+}
+
+int maxunpool_launch(const ActView& in, const long long* idx_nchw, const ActView& o, cudaStream_t st) {
+  MIMO_CHECK(o.N == in.N && o.C == in.C && o.H >= 2 * in.H && o.W >= 2 * in.W, MIMO_ERR_ARG, "maxunpool: shape mismatch");
+  const long long total = (long long)o.N * o.H * o.W * ((o.C + 7) / 8);
+  maxunpool_kernel<<<grid_for(total), kBlock, 0, st>>>(in, idx_nchw, o, (o.H - 2 * in.H) / 2, (o.W - 2 * in.W) / 2);
+  MIMO_LAUNCH_CHECK();
+  return MIMO_OK;
+}
+
+int convtranspose2x2_launch(const ActView& in, const float* wt, const float* bias, const ActView& o, cudaStream_t st) {
+  MIMO_CHECK(o.N == in.N && o.H >= 2 * in.H && o.W >= 2 * in.W, MIMO_ERR_ARG, "convtranspose2x2: output smaller than twice the input");
+  const long long total = (long long)o.N * o.H * o.W * ((o.C + 7) / 8);
+  convtranspose2x2_kernel<<<grid_for(total), kBlock, 0, st>>>(in, wt, bias, o, (o.H - 2 * in.H) / 2, (o.W - 2 * in.W) / 2);
+  MIMO_LAUNCH_CHECK();
+  return MIMO_OK;
+}
+
+int unpack_nchw_launch(const ActView& in, float* out, cudaStream_t st) {
+  const long long total = (long long)in.N * in.C * in.H * in.W;
+  unpack_nchw_kernel<<<grid_for(total), kBlock, 0, st>>>(in, out);
   MIMO_LAUNCH_CHECK();
   return MIMO_OK;
 }

@@ -92,6 +92,11 @@ struct mimo_unet_plan {
   std::vector<const float*> masks_copy;
   int launches = 0;
   int Hs[5], Ws[5];
+  // optional per-launch CUDA-event profiling (bench.py roofline numbers)
+  bool prof = false;
+  std::vector<cudaEvent_t> ev;   // pairs
+  std::vector<int> ev_cls;
+  int ev_used = 0;
 };
 
 namespace mimo {
@@ -150,11 +155,30 @@ int add_node(mimo_unet_plan* P, Arena& A, const std::string& name, View in, int 
   return (int)P->nodes.size() - 1;
 }
 
-#define RUN(expr)                 \
-  do {                            \
-    int _rc = (expr);             \
+enum ProfClass { kPackW = 0, kPackIn, kConvFprop, kBnFinalize, kBnApply, kUpsample, kHeadFwd, kHeadBwd, kBnBwd, kConvWgrad,
+                 kWgradUnpack, kConvDgrad, kGradGather, kUpsampleBwd, kOther, kNumProfClasses };
+static const char* kProfNames[kNumProfClasses] = {"weight_pack", "pack_input", "conv_fprop", "bn_finalize", "bn_relu_apply", "upsample",
+                                                  "head_fwd", "head_bwd", "bn_relu_bwd", "conv_wgrad", "wgrad_unpack", "conv_dgrad",
+                                                  "grad_gather", "upsample_bwd", "other"};
+
+inline void prof_begin(mimo_unet_plan* P, int cls, cudaStream_t st) {
+  if (!P->prof || (size_t)(2 * P->ev_used + 1) >= P->ev.size()) return;
+  cudaEventRecord(P->ev[2 * P->ev_used], st);
+  P->ev_cls[P->ev_used] = cls;
+}
+inline void prof_end(mimo_unet_plan* P, cudaStream_t st) {
+  if (!P->prof || (size_t)(2 * P->ev_used + 1) >= P->ev.size()) return;
+  cudaEventRecord(P->ev[2 * P->ev_used + 1], st);
+  ++P->ev_used;
+}
+
+#define RUN(cls, expr)              \
+  do {                              \
+    prof_begin(P, (cls), st);       \
+    int _rc = (expr);               \
+    prof_end(P, st);                \
     if (_rc != MIMO_OK) return _rc; \
-    ++P->launches;                \
+    ++P->launches;                  \
   } while (0)
 
 float* fptr(const mimo_unet_plan* P, size_t off) { return reinterpret_cast<float*>(P->ws + off); }
@@ -163,11 +187,11 @@ bf16* bptr(const mimo_unet_plan* P, size_t off) { return reinterpret_cast<bf16*>
 int conv_bn_forward(mimo_unet_plan* P, ConvL& c, const ActView& in, const ActView& out, const ActView* pool, const float* drop,
                     bool training, cudaStream_t st) {
   const float* w = (const float*)P->state[c.state0];
-  RUN(weight_pack_launch(w, c.cout, c.cin, bptr(P, c.wf), c.cin_p, bptr(P, c.wd), c.cout_p, st));
+  RUN(kPackW, weight_pack_launch(w, c.cout, c.cin, bptr(P, c.wf), c.cin_p, bptr(P, c.wd), c.cout_p, st));
   bf16* y = reinterpret_cast<bf16*>(P->ws + P->bufs[c.y].off);
   float* vec = fptr(P, c.vec);
   float *scale = vec, *shift = vec + c.cout_p, *mean = vec + 2 * c.cout_p, *invstd = vec + 3 * c.cout_p;
-  RUN(conv3x3_launch(in, 0, bptr(P, c.wf), c.cout, c.cin_p, y, c.cout_p, training ? fptr(P, c.psum) : nullptr,
+  RUN(kConvFprop, conv3x3_launch(in, 0, bptr(P, c.wf), c.cout, c.cin_p, y, c.cout_p, training ? fptr(P, c.psum) : nullptr,
                      training ? fptr(P, c.psq) : nullptr, nullptr, 0, st));
   const float* bias = (const float*)P->state[c.state0 + 1];
   const float* gamma = (const float*)P->state[c.state0 + 2];
@@ -176,12 +200,12 @@ int conv_bn_forward(mimo_unet_plan* P, ConvL& c, const ActView& in, const ActVie
   float* rv = (float*)P->state[c.state0 + 5];
   long long* nbt = (long long*)P->state[c.state0 + 6];
   if (training) {
-    RUN(bn_finalize_launch(fptr(P, c.psum), fptr(P, c.psq), c.m_tiles, c.cout_p, c.cout, (double)c.N * c.H * c.W, gamma, beta, bias,
+    RUN(kBnFinalize, bn_finalize_launch(fptr(P, c.psum), fptr(P, c.psq), c.m_tiles, c.cout_p, c.cout, (double)c.N * c.H * c.W, gamma, beta, bias,
                            rm, rv, nbt, 0.1f, 1e-5f, scale, shift, mean, invstd, st));
   } else {
-    RUN(bn_eval_affine_launch(c.cout, gamma, beta, bias, rm, rv, 1e-5f, scale, shift, mean, invstd, st));
+    RUN(kBnFinalize, bn_eval_affine_launch(c.cout, gamma, beta, bias, rm, rv, 1e-5f, scale, shift, mean, invstd, st));
   }
-  RUN(bn_relu_apply_launch(y, c.cout_p, scale, shift, drop, out, pool, st));
+  RUN(kBnApply, bn_relu_apply_launch(y, c.cout_p, scale, shift, drop, out, pool, st));
   return MIMO_OK;
 }
 
@@ -205,18 +229,18 @@ int conv_bn_backward(mimo_unet_plan* P, ConvL& c, const ActView& G, const ActVie
   float *scale = vec, *shift = vec + c.cout_p, *mean = vec + 2 * c.cout_p, *invstd = vec + 3 * c.cout_p, *s1s2 = vec + 4 * c.cout_p;
   const bf16* y = bptr(P, P->bufs[c.y].off);
   bf16* dy = bptr(P, P->bufs[c.dy].off);
-  RUN(bn_bwd_launch(G, y, c.cout_p, scale, shift, mean, invstd, drop, training ? 1 : 0, fptr(P, c.bnpart), s1s2,
+  RUN(kBnBwd, bn_bwd_launch(G, y, c.cout_p, scale, shift, mean, invstd, drop, training ? 1 : 0, fptr(P, c.bnpart), s1s2,
                     (float*)P->grads[c.state0 + 2], (float*)P->grads[c.state0 + 3], (float*)P->grads[c.state0 + 1], 1.f, accumulate,
                     dy, c.cout_p, st));
   ++P->launches; ++P->launches;  // bn_bwd is three kernels
   const ActView dyv = view_of(P, c.dy, 0, c.cout);
   if (P->grads[c.state0] != nullptr) {
-    RUN(conv3x3_wgrad_launch(dyv, in, fptr(P, c.dwp), c.cin_p, st));
-    RUN(wgrad_unpack_launch(fptr(P, c.dwp), (float*)P->grads[c.state0], c.cout, c.cin, c.cin_p, 1.f, accumulate, st));
+    RUN(kConvWgrad, conv3x3_wgrad_launch(dyv, in, fptr(P, c.dwp), c.cin_p, st));
+    RUN(kWgradUnpack, wgrad_unpack_launch(fptr(P, c.dwp), (float*)P->grads[c.state0], c.cout, c.cin, c.cin_p, 1.f, accumulate, st));
   }
   if (need_in_grad) {
     bf16* dpad = bptr(P, P->bufs[c.dpad].off);
-    RUN(conv3x3_launch(dyv, 1, bptr(P, c.wd), c.cin, c.cout_p, dpad, c.cin_p, nullptr, nullptr, nullptr, 0, st));
+    RUN(kConvDgrad, conv3x3_launch(dyv, 1, bptr(P, c.wd), c.cin, c.cout_p, dpad, c.cin_p, nullptr, nullptr, nullptr, 0, st));
   }
   return MIMO_OK;
 }
@@ -229,7 +253,7 @@ int node_backward(mimo_unet_plan* P, int ni, bool training, const float* drop, i
   if (rc) return rc;
   const ActView dpad2 = view_of(P, n.c2.dpad, 0, n.c2.cin);
   const ActView G1 = view_of(P, n.g1, 0, n.c1.cout);
-  RUN(grad_gather_launch(&dpad2, nullptr, nullptr, G1, 0, st));
+  RUN(kGradGather, grad_gather_launch(&dpad2, nullptr, nullptr, G1, 0, st));
   const ActView in = view_of(P, n.in);
   return conv_bn_backward(P, n.c1, G1, in, nullptr, training, n.need_in_grad, accumulate, st);
 }
@@ -341,7 +365,11 @@ int mimo_unet_plan_create(const mimo_unet_config_t* cfg, mimo_unet_plan_t** out)
   return MIMO_OK;
 }
 
-void mimo_unet_plan_destroy(mimo_unet_plan_t* plan) { delete plan; }
+void mimo_unet_plan_destroy(mimo_unet_plan_t* plan) {
+  if (plan)
+    for (auto& e : plan->ev) cudaEventDestroy(e);
+  delete plan;
+}
 size_t mimo_unet_workspace_bytes(const mimo_unet_plan_t* plan) { return plan ? plan->ws_bytes : 0; }
 int mimo_unet_num_state(const mimo_unet_plan_t* plan) { return plan ? plan->n_state : 0; }
 int mimo_unet_num_double_convs(const mimo_unet_plan_t* plan) { return plan ? (int)plan->nodes.size() : 0; }
@@ -350,6 +378,34 @@ int mimo_unet_dropout_channels(const mimo_unet_plan_t* plan, int i) {
   return plan->nodes[i].c2.cout;
 }
 int mimo_unet_last_launches(const mimo_unet_plan_t* plan) { return plan ? plan->launches : 0; }
+
+int mimo_unet_profile_classes(void) { return kNumProfClasses; }
+const char* mimo_unet_profile_class_name(int i) { return (i >= 0 && i < kNumProfClasses) ? kProfNames[i] : ""; }
+int mimo_unet_profile_enable(mimo_unet_plan_t* P, int on) {
+  MIMO_CHECK(P, MIMO_ERR_ARG, "profile_enable: null plan");
+  if (on && P->ev.empty()) {
+    P->ev.resize(2 * 4096);
+    P->ev_cls.assign(4096, 0);
+    for (auto& e : P->ev) MIMO_CUDA(cudaEventCreate(&e));
+  }
+  P->prof = on != 0;
+  P->ev_used = 0;
+  return MIMO_OK;
+}
+int mimo_unet_profile_read(mimo_unet_plan_t* P, float* ms_by_class, int* count_by_class) {
+  MIMO_CHECK(P && ms_by_class && count_by_class, MIMO_ERR_ARG, "profile_read: null argument");
+  MIMO_CUDA(cudaDeviceSynchronize());
+  for (int i = 0; i < kNumProfClasses; ++i) { ms_by_class[i] = 0.f; count_by_class[i] = 0; }
+  for (int i = 0; i < P->ev_used; ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, P->ev[2 * i], P->ev[2 * i + 1]) == cudaSuccess) {
+      ms_by_class[P->ev_cls[i]] += ms;
+      count_by_class[P->ev_cls[i]] += 1;
+    }
+  }
+  P->ev_used = 0;
+  return MIMO_OK;
+}
 
 int mimo_unet_bind(mimo_unet_plan_t* P, void* workspace, size_t workspace_bytes, void* const* state, void* const* grads, int n) {
   MIMO_CHECK(P && workspace && state, MIMO_ERR_ARG, "bind: null argument");
@@ -383,7 +439,9 @@ int mimo_unet_forward(mimo_unet_plan_t* P, const float* x, const long long* gath
 
   for (int s = 0; s < S; ++s) {
     const ActView xin = view_of(P, P->xin[s], 0, Cin);
-    RUN(pack_input_launch(x + (long long)s * Cin * HW, (long long)S * Cin * HW, HW, gather ? gather + (long long)s * B : nullptr, xin, st));
+    // with a gather table x is the un-shuffled batch [B][Cin][H][W] shared by all subnetworks
+    if (gather) RUN(kPackIn, pack_input_launch(x, (long long)Cin * HW, HW, gather + (long long)s * B, xin, st));
+    else RUN(kPackIn, pack_input_launch(x + (long long)s * Cin * HW, (long long)S * Cin * HW, HW, nullptr, xin, st));
     int rc = node_forward(P, P->enc_in[s], tr, mask(P->enc_in[s]), st);
     if (rc) return rc;
     rc = node_forward(P, P->enc_down[s], tr, mask(P->enc_down[s]), st);
@@ -393,18 +451,18 @@ int mimo_unet_forward(mimo_unet_plan_t* P, const float* x, const long long* gath
   if ((rc = node_forward(P, P->down2, tr, mask(P->down2), st))) return rc;
   if ((rc = node_forward(P, P->down3, tr, mask(P->down3), st))) return rc;
   if ((rc = node_forward(P, P->down4, tr, mask(P->down4), st))) return rc;
-  RUN(upsample_launch(view_of(P, P->x5, 0, 4 * c), view_of(P, P->cat1, 4 * c, 4 * c), st));
+  RUN(kUpsample, upsample_launch(view_of(P, P->x5, 0, 4 * c), view_of(P, P->cat1, 4 * c, 4 * c), st));
   if ((rc = node_forward(P, P->up1, tr, mask(P->up1), st))) return rc;
-  RUN(upsample_launch(view_of(P, P->u1, 0, 2 * c), view_of(P, P->cat2, 2 * c, 2 * c), st));
+  RUN(kUpsample, upsample_launch(view_of(P, P->u1, 0, 2 * c), view_of(P, P->cat2, 2 * c, 2 * c), st));
   if ((rc = node_forward(P, P->up2, tr, mask(P->up2), st))) return rc;
-  RUN(upsample_launch(view_of(P, P->u2, 0, c), view_of(P, P->cat3, c, c), st));
+  RUN(kUpsample, upsample_launch(view_of(P, P->u2, 0, c), view_of(P, P->cat3, c, c), st));
   if ((rc = node_forward(P, P->up3, tr, mask(P->up3), st))) return rc;
   const int K = cfg.out_channels;
   for (int s = 0; s < S; ++s) {
-    RUN(upsample_launch(view_of(P, P->u3, 0, c / 2), view_of(P, P->dcat[s], f, c / 2), st));
+    RUN(kUpsample, upsample_launch(view_of(P, P->u3, 0, c / 2), view_of(P, P->dcat[s], f, c / 2), st));
     if ((rc = node_forward(P, P->dec[s], tr, mask(P->dec[s]), st))) return rc;
     const ActView feat = view_of(P, P->nodes[P->dec[s]].out);
-    RUN(head_fwd_launch(feat, (const float*)P->state[P->head_state0 + 2 * s], (const float*)P->state[P->head_state0 + 2 * s + 1], K,
+    RUN(kHeadFwd, head_fwd_launch(feat, (const float*)P->state[P->head_state0 + 2 * s], (const float*)P->state[P->head_state0 + 2 * s + 1], K,
                         out + (long long)s * K * HW, (long long)S * K * HW, st));
   }
   P->last_training = tr;
@@ -432,7 +490,7 @@ int mimo_unet_backward(mimo_unet_plan_t* P, const float* dout, const float* grad
     Node& n = P->nodes[P->dec[s]];
     const ActView feat = view_of(P, n.out);
     const ActView G = view_of(P, n.g2);
-    RUN(head_bwd_launch(feat, (const float*)P->state[P->head_state0 + 2 * s], K, dout + (long long)s * K * HW, (long long)S * K * HW,
+    RUN(kHeadBwd, head_bwd_launch(feat, (const float*)P->state[P->head_state0 + 2 * s], K, dout + (long long)s * K * HW, (long long)S * K * HW,
                         grad_scale, G, fptr(P, P->head_part), (float*)P->grads[P->head_state0 + 2 * s],
                         (float*)P->grads[P->head_state0 + 2 * s + 1], accumulate, st));
     ++P->launches;
@@ -440,75 +498,77 @@ int mimo_unet_backward(mimo_unet_plan_t* P, const float* dout, const float* grad
     // gradient of the shared up-sampled core output: fold the [f, f + c/2) slice, then bilinear backward
     const ActView dp = view_of(P, n.c1.dpad, f, c / 2);
     const ActView t0 = view_of(P, P->tmp0, 0, c / 2);
-    RUN(grad_gather_launch(&dp, nullptr, nullptr, t0, 0, st));
-    RUN(upsample_bwd_launch(t0, view_of(P, P->g_u3, 0, c / 2), s > 0 ? 1 : 0, st));
+    RUN(kGradGather, grad_gather_launch(&dp, nullptr, nullptr, t0, 0, st));
+    RUN(kUpsampleBwd, upsample_bwd_launch(t0, view_of(P, P->g_u3, 0, c / 2), s > 0 ? 1 : 0, st));
   }
   // ---- core up path ----
   if ((rc = node_backward(P, P->up3, tr, mask(P->up3), accumulate, st))) return rc;
   {
     const ActView dp = view_of(P, P->nodes[P->up3].c1.dpad, c, c);
     const ActView t = view_of(P, P->tmp1, 0, c);
-    RUN(grad_gather_launch(&dp, nullptr, nullptr, t, 0, st));
-    RUN(upsample_bwd_launch(t, view_of(P, P->g_u2, 0, c), 0, st));
+    RUN(kGradGather, grad_gather_launch(&dp, nullptr, nullptr, t, 0, st));
+    RUN(kUpsampleBwd, upsample_bwd_launch(t, view_of(P, P->g_u2, 0, c), 0, st));
   }
   if ((rc = node_backward(P, P->up2, tr, mask(P->up2), accumulate, st))) return rc;
   {
     const ActView dp = view_of(P, P->nodes[P->up2].c1.dpad, 2 * c, 2 * c);
     const ActView t = view_of(P, P->tmp2, 0, 2 * c);
-    RUN(grad_gather_launch(&dp, nullptr, nullptr, t, 0, st));
-    RUN(upsample_bwd_launch(t, view_of(P, P->g_u1, 0, 2 * c), 0, st));
+    RUN(kGradGather, grad_gather_launch(&dp, nullptr, nullptr, t, 0, st));
+    RUN(kUpsampleBwd, upsample_bwd_launch(t, view_of(P, P->g_u1, 0, 2 * c), 0, st));
   }
   if ((rc = node_backward(P, P->up1, tr, mask(P->up1), accumulate, st))) return rc;
   {
     const ActView dp = view_of(P, P->nodes[P->up1].c1.dpad, 4 * c, 4 * c);
     const ActView t = view_of(P, P->tmp3, 0, 4 * c);
-    RUN(grad_gather_launch(&dp, nullptr, nullptr, t, 0, st));
-    RUN(upsample_bwd_launch(t, view_of(P, P->g_x5, 0, 4 * c), 0, st));
+    RUN(kGradGather, grad_gather_launch(&dp, nullptr, nullptr, t, 0, st));
+    RUN(kUpsampleBwd, upsample_bwd_launch(t, view_of(P, P->g_x5, 0, 4 * c), 0, st));
   }
   // ---- core down path: skip gradient (fold of the concat slice) + max-pool backward ----
   if ((rc = node_backward(P, P->down4, tr, mask(P->down4), accumulate, st))) return rc;
   {
     const ActView dpp = view_of(P, P->nodes[P->down4].c1.dpad, 0, 4 * c);
     const ActView gp = view_of(P, P->gp_x4, 0, 4 * c);
-    RUN(grad_gather_launch(&dpp, nullptr, nullptr, gp, 0, st));
+    RUN(kGradGather, grad_gather_launch(&dpp, nullptr, nullptr, gp, 0, st));
     const ActView dskip = view_of(P, P->nodes[P->up1].c1.dpad, 0, 4 * c);
     const ActView act = view_of(P, P->cat1, 0, 4 * c);
-    RUN(grad_gather_launch(&dskip, &gp, &act, view_of(P, P->g_x4, 0, 4 * c), 0, st));
+    RUN(kGradGather, grad_gather_launch(&dskip, &gp, &act, view_of(P, P->g_x4, 0, 4 * c), 0, st));
   }
   if ((rc = node_backward(P, P->down3, tr, mask(P->down3), accumulate, st))) return rc;
   {
     const ActView dpp = view_of(P, P->nodes[P->down3].c1.dpad, 0, 2 * c);
     const ActView gp = view_of(P, P->gp_x3, 0, 2 * c);
-    RUN(grad_gather_launch(&dpp, nullptr, nullptr, gp, 0, st));
+    RUN(kGradGather, grad_gather_launch(&dpp, nullptr, nullptr, gp, 0, st));
     const ActView dskip = view_of(P, P->nodes[P->up2].c1.dpad, 0, 2 * c);
     const ActView act = view_of(P, P->cat2, 0, 2 * c);
-    RUN(grad_gather_launch(&dskip, &gp, &act, view_of(P, P->g_x3, 0, 2 * c), 0, st));
+    RUN(kGradGather, grad_gather_launch(&dskip, &gp, &act, view_of(P, P->g_x3, 0, 2 * c), 0, st));
   }
   if ((rc = node_backward(P, P->down2, tr, mask(P->down2), accumulate, st))) return rc;
   {
     const ActView dpp = view_of(P, P->nodes[P->down2].c1.dpad, 0, c);
     const ActView gp = view_of(P, P->gp_xc, 0, c);
-    RUN(grad_gather_launch(&dpp, nullptr, nullptr, gp, 0, st));
+    RUN(kGradGather, grad_gather_launch(&dpp, nullptr, nullptr, gp, 0, st));
     const ActView dskip = view_of(P, P->nodes[P->up3].c1.dpad, 0, c);
     const ActView act = view_of(P, P->cat3, 0, c);
-    RUN(grad_gather_launch(&dskip, &gp, &act, view_of(P, P->g_xc, 0, c), 0, st));
+    RUN(kGradGather, grad_gather_launch(&dskip, &gp, &act, view_of(P, P->g_xc, 0, c), 0, st));
   }
   // ---- encoders ----
   for (int s = 0; s < S; ++s) {
     if ((rc = node_backward(P, P->enc_down[s], tr, mask(P->enc_down[s]), accumulate, st))) return rc;
     const ActView dpp = view_of(P, P->nodes[P->enc_down[s]].c1.dpad, 0, f);
     const ActView gp = view_of(P, P->gp1[s], 0, f);
-    RUN(grad_gather_launch(&dpp, nullptr, nullptr, gp, 0, st));
+    RUN(kGradGather, grad_gather_launch(&dpp, nullptr, nullptr, gp, 0, st));
     const ActView dskip = view_of(P, P->nodes[P->dec[s]].c1.dpad, 0, f);
     const ActView act = view_of(P, P->dcat[s], 0, f);
-    RUN(grad_gather_launch(&dskip, &gp, &act, view_of(P, P->g_x1[s], 0, f), 0, st));
+    RUN(kGradGather, grad_gather_launch(&dskip, &gp, &act, view_of(P, P->g_x1[s], 0, f), 0, st));
     if ((rc = node_backward(P, P->enc_in[s], tr, mask(P->enc_in[s]), accumulate, st))) return rc;
     if (dx) {
       const ActView dp = view_of(P, P->nodes[P->enc_in[s]].c1.dpad, 0, Cin);
       const long long total = (long long)cfg.batch * HW;
       int grid = (int)((total + 255) / 256);
       if (grid > num_sms() * 16) grid = num_sms() * 16;
+      prof_begin(P, kOther, st);
       unpack_input_grad_kernel<<<grid, 256, 0, st>>>(dp, cfg.height, cfg.width, Cin, dx + (long long)s * Cin * HW, (long long)S * Cin * HW, HW);
+      prof_end(P, st);
       MIMO_LAUNCH_CHECK();
       ++P->launches;
     }

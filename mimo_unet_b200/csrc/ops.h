@@ -29,6 +29,9 @@ int upsample_launch(const ActView& in, const ActView& o, cudaStream_t st);
 int upsample_bwd_launch(const ActView& gdst, const ActView& gsrc, int accumulate, cudaStream_t st);
 int grad_gather_launch(const ActView* dpad, const ActView* gpool, const ActView* act, const ActView& gout, int accumulate,
                        cudaStream_t st);
+int maxunpool_launch(const ActView& in, const long long* idx_nchw, const ActView& o, cudaStream_t st);
+int convtranspose2x2_launch(const ActView& in, const float* wt, const float* bias, const ActView& o, cudaStream_t st);
+int unpack_nchw_launch(const ActView& in, float* out, cudaStream_t st);
 int bn_bwd_parts(int C);
 int bn_bwd_launch(const ActView& G, const bf16* y, int ycp, const float* scale, const float* shift, const float* mean,
                   const float* invstd, const float* drop, int training, float* part, float* s1s2, float* dgamma, float* dbeta,

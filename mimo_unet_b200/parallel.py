@@ -1,0 +1,71 @@
+"""Data-parallel plumbing (one process per GPU, torch.distributed): bucketed all-reduce of the flat gradient
+buffer and the [S] per-subnetwork loss exchange that keeps every rank's loss buffer identical.
+
+The reference defines no multi-GPU behaviour (devices=1 everywhere); semantics follow standard DDP: per-rank
+BatchNorm statistics, per-rank shuffles, gradients averaged over ranks."""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+def world_size() -> int:
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+class GradientSynchronizer:
+    """Averages one flat fp32 gradient tensor over all ranks in `num_buckets` contiguous buckets.
+
+    Bucket boundaries are aligned to 128 elements. With NCCL the reductions are issued asynchronously on the
+    communicator's stream (so the first buckets travel over NVLink while later ones are still being enqueued) and
+    joined in wait(); with gloo (CPU tests) AVG is emulated as SUM / world."""
+
+    def __init__(self, num_buckets: int = 4, group=None):
+        self.num_buckets = max(1, int(num_buckets))
+        self.group = group
+        self._work: List = []
+        self._views: List[torch.Tensor] = []
+
+    @staticmethod
+    def bucket_ranges(numel: int, num_buckets: int):
+        per = (numel + num_buckets - 1) // num_buckets
+        per = (per + 127) // 128 * 128
+        out, start = [], 0
+        while start < numel:
+            end = min(numel, start + per)
+            out.append((start, end))
+            start = end
+        return out
+
+    def start(self, flat: torch.Tensor):
+        if world_size() == 1:
+            return
+        avg_ok = flat.is_cuda
+        self._views = [flat[a:b] for a, b in self.bucket_ranges(flat.numel(), self.num_buckets)]
+        # issue in REVERSE order: the tail of the flat buffer holds decoder gradients, produced first by backward
+        for v in reversed(self._views):
+            op = dist.ReduceOp.AVG if avg_ok else dist.ReduceOp.SUM
+            self._work.append((dist.all_reduce(v, op=op, group=self.group, async_op=True), v, avg_ok))
+
+    def wait(self):
+        w = world_size()
+        for work, v, avg_ok in self._work:
+            work.wait()
+            if not avg_ok:
+                v.div_(w)
+        self._work = []
+
+
+def allreduce_mean_(t: torch.Tensor, group=None) -> torch.Tensor:
+    """In-place mean over ranks (used for the [S] loss vector that feeds the loss buffer)."""
+    w = world_size()
+    if w == 1:
+        return t
+    if t.is_cuda:
+        dist.all_reduce(t, op=dist.ReduceOp.AVG, group=group)
+    else:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        t.div_(w)
+    return t

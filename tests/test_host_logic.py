@@ -1,0 +1,89 @@
+"""CPU tests of host-side logic: product module construction, loud failure without CUDA, row-view factorisation,
+bucket planning and the world_size-2 gloo data-parallel exchange."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from mimo_unet_b200 import MimoError
+from mimo_unet_b200.functional import _common_rows_view
+from mimo_unet_b200.parallel import GradientSynchronizer, allreduce_mean_
+from oracle import mimo_oracle as O
+
+
+def test_state_dict_layout_and_cpu_failure():
+    from mimo.models.mimo_unet import MimoUnetModel
+    m = MimoUnetModel(3, 2, 2, 8, 0, 0, 0, 0, 0, "laplace_nll", 0.0, 1e-3, 1, 10, 0.3)
+    names = [n for n, _, _ in O.state_dict_spec(3, 2, 2, 8)]
+    assert list(m.model.state_dict().keys()) == names
+    assert m.hparams["trainable_params"] == sum(p.numel() for p in m.model.parameters())
+    m.load_state_dict({k.replace("model.", "model._orig_mod."): v for k, v in m.state_dict().items()})  # compiled-checkpoint keys
+    with pytest.raises(MimoError):
+        m(torch.zeros(1, 2, 3, 32, 32))
+    with pytest.raises(ValueError):
+        from mimo.losses import UncertaintyLoss
+        UncertaintyLoss.from_name("nope")
+    assert m.compile() is None
+
+
+def test_rows_view_factorisation():
+    out = torch.zeros(3, 2, 2, 5, 7)
+    p1, p2, y = out[:, :, :1], out[:, :, 1:], torch.zeros(3, 2, 1, 5, 7)
+    ts, rows, cols, rs = _common_rows_view([p1, p2, y], p1.shape)
+    assert (rows, cols, rs) == (6, 35, [70, 70, 35]) and ts[0].data_ptr() == p1.data_ptr()  # no copy of the strided views
+    ts, rows, cols, rs = _common_rows_view([y, y], y.shape)
+    assert (rows, cols) == (1, 210)
+
+
+def test_bucket_ranges_cover_everything():
+    for n in (1, 127, 128, 1000, 7383622):
+        for k in (1, 4, 8):
+            r = GradientSynchronizer.bucket_ranges(n, k)
+            assert r[0][0] == 0 and r[-1][1] == n and all(a[1] == b[0] for a, b in zip(r, r[1:])) and len(r) <= k
+            assert all(a % 128 == 0 for a, _ in r)
+
+
+def _dp_worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    S, f = 2, 4
+    sd = O.make_state_dict(3, 2, S, f, seed=1)
+    x_all, y_all = torch.rand(4, S, 3, 32, 32), torch.rand(4, S, 1, 32, 32)
+    shard = slice(rank * 2, rank * 2 + 2)
+    p = {k: (v.clone().requires_grad_(True) if v.dtype == torch.float32 and "running" not in k else v.clone()) for k, v in sd.items()}
+    out = O.mimo_unet_forward(x_all[shard], p, S, training=True)       # per-rank BatchNorm statistics
+    loss, total = O.train_loss(out, y_all[shard], None, torch.ones(S))
+    total.backward()
+    learn = [v for v in p.values() if v.requires_grad]
+    flat = torch.cat([(v.grad if v.grad is not None else torch.zeros_like(v)).reshape(-1) for v in learn])
+    sync = GradientSynchronizer(num_buckets=3)
+    sync.start(flat)
+    sync.wait()
+    l = allreduce_mean_(loss.detach().clone())
+    torch.save({"flat": flat, "loss": l}, os.path.join(tmp, f"r{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_data_parallel_exchange_gloo_world2(tmp_path):
+    port = 29500 + os.getpid() % 2000
+    mp.spawn(_dp_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = torch.load(tmp_path / "r0.pt"), torch.load(tmp_path / "r1.pt")
+    assert torch.equal(r0["flat"], r1["flat"]) and torch.equal(r0["loss"], r1["loss"])
+    # R-replica simulation of the oracle in one process (SURVEY 8e parity definition)
+    torch.manual_seed(0)
+    S, f = 2, 4
+    sd = O.make_state_dict(3, 2, S, f, seed=1)
+    x_all, y_all = torch.rand(4, S, 3, 32, 32), torch.rand(4, S, 1, 32, 32)
+    flats, losses = [], []
+    for r in range(2):
+        p = {k: (v.clone().requires_grad_(True) if v.dtype == torch.float32 and "running" not in k else v.clone()) for k, v in sd.items()}
+        out = O.mimo_unet_forward(x_all[r * 2: r * 2 + 2], p, S, training=True)
+        loss, total = O.train_loss(out, y_all[r * 2: r * 2 + 2], None, torch.ones(S))
+        total.backward()
+        flats.append(torch.cat([(v.grad if v.grad is not None else torch.zeros_like(v)).reshape(-1) for v in p.values() if v.requires_grad]))
+        losses.append(loss.detach())
+    assert torch.allclose(r0["flat"], (flats[0] + flats[1]) / 2, rtol=1e-5, atol=1e-8)
+    assert torch.allclose(r0["loss"], (losses[0] + losses[1]) / 2, rtol=1e-6)
