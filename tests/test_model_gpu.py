@@ -115,7 +115,7 @@ def test_train_backward_vs_oracle(cases, name):
         assert torch.isfinite(g).all(), k
         if k.endswith("double_conv.0.bias") or k.endswith("double_conv.3.bias"):
             assert float(g.abs().max()) == 0.0, k  # analytically zero
-            assert float(g32[k].abs().max()) < 1e-5
+            assert g32[k] is None or float(g32[k].abs().max()) < 1e-5  # the oracle drops the bias under train-mode BN
             continue
         cos_emu.append(_cos(g, gem[k]))
         cos_32.append(_cos(g, g32[k]))
