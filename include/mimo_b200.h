@@ -197,6 +197,11 @@ int mimo_unet_profile_classes(void);
 const char* mimo_unet_profile_class_name(int i);
 int mimo_unet_profile_enable(mimo_unet_plan_t* plan, int on);
 int mimo_unet_profile_read(mimo_unet_plan_t* plan, float* ms_by_class, int* count_by_class);
+/* per-launch variant: fills up to max_n entries (ms, class, tag = 2*double_conv_index + second_conv or -1) in
+ * enqueue order and returns how many; resets the recording like mimo_unet_profile_read. */
+int mimo_unet_profile_read_launches(mimo_unet_plan_t* plan, int max_n, float* ms, int* cls, int* tag);
+/* state_dict prefix of double conv i ("core.down2", "decoder.up4s.1", ...) */
+const char* mimo_unet_node_name(const mimo_unet_plan_t* plan, int i);
 
 #ifdef __cplusplus
 }

@@ -95,8 +95,9 @@ struct mimo_unet_plan {
   // optional per-launch CUDA-event profiling (bench.py roofline numbers)
   bool prof = false;
   std::vector<cudaEvent_t> ev;   // pairs
-  std::vector<int> ev_cls;
+  std::vector<int> ev_cls, ev_tag;
   int ev_used = 0;
+  int cur_tag = -1;              // 2*node + (second conv) of the launch being enqueued, -1 outside a DoubleConv
 };
 
 namespace mimo {
@@ -165,6 +166,7 @@ inline void prof_begin(mimo_unet_plan* P, int cls, cudaStream_t st) {
   if (!P->prof || (size_t)(2 * P->ev_used + 1) >= P->ev.size()) return;
   cudaEventRecord(P->ev[2 * P->ev_used], st);
   P->ev_cls[P->ev_used] = cls;
+  P->ev_tag[P->ev_used] = P->cur_tag;
 }
 inline void prof_end(mimo_unet_plan* P, cudaStream_t st) {
   if (!P->prof || (size_t)(2 * P->ev_used + 1) >= P->ev.size()) return;
@@ -214,13 +216,18 @@ int node_forward(mimo_unet_plan* P, int ni, bool training, const float* drop, cu
   const ActView in = view_of(P, n.in);
   const ActView a1 = view_of(P, n.a1, 0, n.c1.cout);
   const ActView out = view_of(P, n.out);
+  P->cur_tag = 2 * ni;
   int rc = conv_bn_forward(P, n.c1, in, a1, nullptr, nullptr, training, st);
   if (rc) return rc;
+  P->cur_tag = 2 * ni + 1;
   if (n.pool.buf >= 0) {
     const ActView pool = view_of(P, n.pool);
-    return conv_bn_forward(P, n.c2, a1, out, &pool, drop, training, st);
+    rc = conv_bn_forward(P, n.c2, a1, out, &pool, drop, training, st);
+  } else {
+    rc = conv_bn_forward(P, n.c2, a1, out, nullptr, drop, training, st);
   }
-  return conv_bn_forward(P, n.c2, a1, out, nullptr, drop, training, st);
+  P->cur_tag = -1;
+  return rc;
 }
 
 int conv_bn_backward(mimo_unet_plan* P, ConvL& c, const ActView& G, const ActView& in, const float* drop, bool training,
@@ -249,13 +256,17 @@ int node_backward(mimo_unet_plan* P, int ni, bool training, const float* drop, i
   Node& n = P->nodes[ni];
   const ActView G2 = view_of(P, n.g2);
   const ActView a1 = view_of(P, n.a1, 0, n.c1.cout);
+  P->cur_tag = 2 * ni + 1;
   int rc = conv_bn_backward(P, n.c2, G2, a1, drop, training, true, accumulate, st);
   if (rc) return rc;
   const ActView dpad2 = view_of(P, n.c2.dpad, 0, n.c2.cin);
   const ActView G1 = view_of(P, n.g1, 0, n.c1.cout);
+  P->cur_tag = 2 * ni;
   RUN(kGradGather, grad_gather_launch(&dpad2, nullptr, nullptr, G1, 0, st));
   const ActView in = view_of(P, n.in);
-  return conv_bn_backward(P, n.c1, G1, in, nullptr, training, n.need_in_grad, accumulate, st);
+  rc = conv_bn_backward(P, n.c1, G1, in, nullptr, training, n.need_in_grad, accumulate, st);
+  P->cur_tag = -1;
+  return rc;
 }
 
 __global__ void unpack_input_grad_kernel(ActView dpad /* (H+2)x(W+2) domain */, int H, int W, int C, float* dx, long long sb, long long sc) {
@@ -386,6 +397,7 @@ int mimo_unet_profile_enable(mimo_unet_plan_t* P, int on) {
   if (on && P->ev.empty()) {
     P->ev.resize(2 * 4096);
     P->ev_cls.assign(4096, 0);
+    P->ev_tag.assign(4096, -1);
     for (auto& e : P->ev) MIMO_CUDA(cudaEventCreate(&e));
   }
   P->prof = on != 0;
@@ -405,6 +417,22 @@ int mimo_unet_profile_read(mimo_unet_plan_t* P, float* ms_by_class, int* count_b
   }
   P->ev_used = 0;
   return MIMO_OK;
+}
+
+int mimo_unet_profile_read_launches(mimo_unet_plan_t* P, int max_n, float* ms, int* cls, int* tag) {
+  MIMO_CHECK(P && ms && cls && tag, MIMO_ERR_ARG, "profile_read_launches: null argument");
+  MIMO_CUDA(cudaDeviceSynchronize());
+  int n = P->ev_used < max_n ? P->ev_used : max_n;
+  for (int i = 0; i < n; ++i) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, P->ev[2 * i], P->ev[2 * i + 1]);
+    ms[i] = t; cls[i] = P->ev_cls[i]; tag[i] = P->ev_tag[i];
+  }
+  P->ev_used = 0;
+  return n;
+}
+const char* mimo_unet_node_name(const mimo_unet_plan_t* P, int i) {
+  return (P && i >= 0 && i < (int)P->nodes.size()) ? P->nodes[i].name.c_str() : "";
 }
 
 int mimo_unet_bind(mimo_unet_plan_t* P, void* workspace, size_t workspace_bytes, void* const* state, void* const* grads, int n) {
