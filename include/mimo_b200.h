@@ -36,11 +36,14 @@ typedef enum {
 } mimo_status;
 
 /* NHWC bf16 activation view.
- * element (n,h,w,c) at ptr[((n*(h_+2*pad) + h+pad)*(w_+2*pad) + w+pad)*cpitch + c_off + c]   (bf16 elements) */
+ * element (n,h,w,c) at ptr[((n*hb + h+o)*wb + w+o)*cpitch + c_off + c] (bf16 elements), hb = h_+(pad?2:0),
+ * wb = w_+(pad?2:0), o = (pad==1) */
 typedef struct {
   void* ptr;   /* base of the whole buffer (16-byte aligned) */
   int n, h, w; /* logical (un-haloed) extent */
-  int pad;     /* 0, or 1 = one-pixel reflect halo stored around every image */
+  int pad;     /* 0 = dense; 1 = one-pixel reflect halo stored around every image (buffer [n][h+2][w+2], interior at
+                * (1,1)); 2 = zero tail: buffer [n][h+2][w+2], interior at (0,0), the 2 extra columns / rows stay zero
+                * (gradient buffers read by the flat dgrad / wgrad kernels) */
   int cpitch;  /* channels per pixel in memory, multiple of 8 */
   int c_off;   /* first channel of the view */
   int c;       /* channels of the view */
@@ -107,12 +110,12 @@ int mimo_unpack_nchw(mimo_act_t in, float* out, void* stream);
 int mimo_grad_gather(const mimo_act_t* dpad, const mimo_act_t* gpool, const mimo_act_t* act, mimo_act_t g_out,
                      int accumulate, void* stream);
 /* BN + ReLU (+dropout) backward: dy, dgamma, dbeta (dbias_conv == 0 in training). part: fp32 scratch of
- * mimo_bn_bwd_scratch_floats(c) floats; s1s2: fp32 [2][c]. */
+ * mimo_bn_bwd_scratch_floats(c) floats; s1s2: fp32 [2][c]. dy: whole-buffer view (c_off 0), pad 0 (dense) or
+ * pad 2 (zero tail, the layout the flat dgrad / wgrad kernels read); only interior pixels are written. */
 size_t mimo_bn_bwd_scratch_floats(int c);
 int mimo_bn_relu_bwd(mimo_act_t g, const void* y, int y_cpitch, const float* scale, const float* shift,
                      const float* save_mean, const float* save_invstd, const float* drop, int training, float* part,
-                     float* s1s2, float* dgamma, float* dbeta, float* dbias, int accumulate, void* dy, int dy_cpitch,
-                     void* stream);
+                     float* s1s2, float* dgamma, float* dbeta, float* dbias, int accumulate, mimo_act_t dy, void* stream);
 
 /* ------------------------------------------------------------------ heads / loss / aggregation ------------ */
 /* OutConv 1x1 (components.py:123-129): out fp32 planes, element (n,k,h,w) at out[n*out_bstride + k*h*w + ...] */

@@ -32,7 +32,7 @@ int mimo_weight_pack(const float* w, int cout, int cin, void* wf, int cin_pitch,
   return weight_pack_launch(w, cout, cin, (bf16*)wf, cin_pitch, (bf16*)wd, cout_pitch, (cudaStream_t)stream);
 }
 
-int mimo_conv3x3_m_tiles(int n, int out_h, int out_w) { return conv3x3_m_tiles(n, out_h, out_w); }
+int mimo_conv3x3_m_tiles(int n, int out_h, int out_w) { (void)n; (void)out_h; (void)out_w; return conv3x3_stat_rows(); }
 
 int mimo_conv3x3(mimo_act_t in, int mode, const void* w_packed, int cout, int cin_pitch, void* out, int out_cpitch, float* stat_sum,
                  float* stat_sq, const float* bias, int relu, void* stream) {
@@ -119,10 +119,10 @@ size_t mimo_bn_bwd_scratch_floats(int c) { return (size_t)bn_bwd_parts(c) * 2 * 
 
 int mimo_bn_relu_bwd(mimo_act_t g, const void* y, int y_cpitch, const float* scale, const float* shift, const float* save_mean,
                      const float* save_invstd, const float* drop, int training, float* part, float* s1s2, float* dgamma, float* dbeta,
-                     float* dbias, int accumulate, void* dy, int dy_cpitch, void* stream) {
-  MIMO_CHECK(g.ptr && y && scale && shift && save_mean && save_invstd && part && s1s2 && dy, MIMO_ERR_ARG, "bn_relu_bwd: null pointer");
+                     float* dbias, int accumulate, mimo_act_t dy, void* stream) {
+  MIMO_CHECK(g.ptr && y && scale && shift && save_mean && save_invstd && part && s1s2 && dy.ptr, MIMO_ERR_ARG, "bn_relu_bwd: null pointer");
   return bn_bwd_launch(make_view(g), (const bf16*)y, y_cpitch, scale, shift, save_mean, save_invstd, drop, training, part, s1s2, dgamma,
-                       dbeta, dbias, 1.f, accumulate, (bf16*)dy, dy_cpitch, (cudaStream_t)stream);
+                       dbeta, dbias, 1.f, accumulate, make_view(dy), (cudaStream_t)stream);
 }
 
 int mimo_head1x1(mimo_act_t feat, const float* w, const float* bias, int k, float* out, long long out_bstride, void* stream) {

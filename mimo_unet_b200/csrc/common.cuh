@@ -55,18 +55,25 @@ static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 
 int num_sms();
 
 // ---------------------------------------------------------------------------------------------
-// Activation view: NHWC bf16 with an optional 1-pixel halo and an optional channel slice.
-// element (n,h,w,c) lives at base[((n*(H+2*pad) + h+pad)*(W+2*pad) + w+pad)*cpitch + c_off + c]
+// Activation view: NHWC bf16 with an optional halo and an optional channel slice.
+//   pad == 0: dense [N][H][W]
+//   pad == 1: one-pixel halo all around, buffer [N][H+2][W+2], interior at (1,1)   (reflect halo of conv inputs)
+//   pad == 2: two-pixel ZERO TAIL, buffer [N][H+2][W+2], interior at (0,0); the two extra columns / rows after every
+//             image row / image stay zero, so a flattened pixel index can run across row ends (conv_flat.cu)
+// element (n,h,w,c) lives at base[((n*hb() + h+org())*wb() + w+org())*cpitch + c_off + c]
 // ---------------------------------------------------------------------------------------------
 struct ActView {
   bf16* base;
   int N, H, W;
-  int pad;     // 0 or 1
+  int pad;     // 0, 1 or 2 (see above)
   int cpitch;  // channels per pixel in memory (multiple of 8)
   int c_off;   // first channel of this view
   int C;       // channels in this view
+  __host__ __device__ inline int hb() const { return H + (pad ? 2 : 0); }
+  __host__ __device__ inline int wb() const { return W + (pad ? 2 : 0); }
+  __host__ __device__ inline int org() const { return pad == 1 ? 1 : 0; }
   __host__ __device__ inline long long pix(int n, int h, int w) const {
-    return ((long long)(n * (H + 2 * pad) + h + pad) * (W + 2 * pad) + (w + pad)) * cpitch + c_off;
+    return ((long long)(n * hb() + h + org()) * wb() + (w + org())) * cpitch + c_off;
   }
 };
 
@@ -180,6 +187,12 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* m, uint64_t* bar,
       : "memory");
 }
 
+// L2 prefetch of a 2-D box (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1)
+               : "memory");
+}
+
 // --- tcgen05 ---
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
@@ -234,10 +247,48 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 }
 constexpr uint32_t kLayoutSW128 = 2;
 
+// The same descriptor as two 32-bit words. The elected MMA thread is a single thread executing a dependent
+// instruction stream (~4+ cycles per instruction), so building 64-bit descriptors with shifts/ors per MMA makes the
+// ISSUE loop the bottleneck (measured: ~110 cycles per MMA). Instead the high word is a constant and the low word is
+// advanced with ONE 32-bit add in 16-byte units (all shared-memory addresses are < 256 KB, so the 14-bit start
+// address field never carries into the LBO field).
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__host__ __device__ constexpr uint32_t desc_hi(uint32_t sbo_bytes, uint32_t layout) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | ((layout & 7u) << 29);
+}
+__device__ __forceinline__ void umma_bf16_w(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// same, with the matrix base offset field (bits [49,52)): (start_address >> 7) & 7 when the start address is not
+// aligned to the 1024-byte swizzle-128B repeat (row-shifted windows of a larger tile)
+__device__ __forceinline__ uint64_t make_smem_desc_bo(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout,
+                                                      uint32_t base_offset) {
+  return make_smem_desc(saddr, lbo_bytes, sbo_bytes, layout) | ((uint64_t)(base_offset & 7) << 49);
+}
+
 // UMMA instruction descriptor for kind::f16 with bf16 A/B and fp32 D (cute::UMMA::InstrDescriptor).
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// One lane of a fully converged warp. The TMA / MMA warps run their loops warp-uniformly and only the issue
+// instructions sit under this predicate: with an `if (lane == 0)` around the whole loop ptxas treats every operand as
+// divergent and wraps each UTCHMMA / UTMALDG in a vote + R2UR uniformisation loop (~15 instructions per MMA).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {

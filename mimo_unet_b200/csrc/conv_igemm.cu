@@ -19,7 +19,10 @@
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
 // warps 2..5 = epilogue (TMEM lane quarter = warp_idx % 4).
 #include "common.cuh"
+#include "conv_epilogue.cuh"
 #include "ops.h"
+
+#include <stdlib.h>
 
 namespace mimo {
 
@@ -43,12 +46,8 @@ struct ConvParams {
   int out_cpitch;             // channels per output pixel in memory (multiple of 8, >= cout)
   int stages;
   int b_stage_bytes;
-  int stage_pitch;            // epilogue staging row pitch in bytes
-  bf16* out;                  // [n_img][out_h][out_w][out_cpitch]
-  float* stat_sum;            // [m_tiles][out_cpitch] or nullptr
-  float* stat_sq;             // [m_tiles][out_cpitch] or nullptr
-  const float* bias;          // optional per-cout bias added before the store (eval path), or nullptr
-  int relu;                   // apply ReLU before the store (eval path with folded BN)
+  int ko;                     // diagnostic knock-outs (env MIMO_KO): 1 no global stores, 2 no A loads, 4 no MMAs
+  EpiArgs epi;                // output tensor, BatchNorm statistics rows, optional fused bias / ReLU
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -59,14 +58,13 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_c
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem_a + (size_t)p.stages * kABytes;
-  uint8_t* smem_stage = smem_b + (size_t)p.stages * p.b_stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stage + (size_t)kBlockM * p.stage_pitch);
+  uint8_t* smem_epi = smem_b + (size_t)p.stages * p.b_stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + ((epi_smem_bytes(p.block_n, p.epi.out_cpitch) + 15) & ~size_t(15)));
   uint64_t* full_bar = bars;                     // [stages]
   uint64_t* empty_bar = bars + kMaxStages;       // [stages]
   uint64_t* tmem_full = bars + 2 * kMaxStages;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;          // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  uint32_t* row_valid = tmem_ptr + 4;            // [128] validity of each tile row (epilogue scratch)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -101,143 +99,94 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_c
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int mt = t / p.n_tiles, nt = t - mt * p.n_tiles;
-        const int twi = mt % p.tiles_w;
-        const int thi = (mt / p.tiles_w) % p.tiles_h;
-        const int tni = mt / (p.tiles_w * p.tiles_h);
-        const int w0 = twi * p.tw + p.origin, h0 = thi * p.th + p.origin, n0 = tni * p.tn;
-        const int co0 = nt * p.block_n;
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          const int tap = kb / p.cin_chunks;
-          const int cc = kb - tap * p.cin_chunks;
-          const int kh = tap / 3, kw = tap - kh * 3;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], kABytes + p.b_stage_bytes);
-          tma_load_4d(&tmap_in, &full_bar[stage], smem_a + (size_t)stage * kABytes, cc * kBlockK, w0 + kw, h0 + kh, n0);
-          tma_load_3d(&tmap_w, &full_bar[stage], smem_b + (size_t)stage * p.b_stage_bytes, cc * kBlockK, co0, tap);
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+    // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int mt = t / p.n_tiles, nt = t - mt * p.n_tiles;
+      const int twi = mt % p.tiles_w;
+      const int thi = (mt / p.tiles_w) % p.tiles_h;
+      const int tni = mt / (p.tiles_w * p.tiles_h);
+      const int w0 = twi * p.tw + p.origin, h0 = thi * p.th + p.origin, n0 = tni * p.tn;
+      const int co0 = nt * p.block_n;
+      int kh = 0, kw = 0, cc = 0;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&full_bar[stage], ((p.ko & 2) ? 0 : kABytes) + p.b_stage_bytes);
+          if (!(p.ko & 2)) tma_load_4d(&tmap_in, &full_bar[stage], smem_a + (size_t)stage * kABytes, cc * kBlockK, w0 + kw, h0 + kh, n0);
+          tma_load_3d(&tmap_w, &full_bar[stage], smem_b + (size_t)stage * p.b_stage_bytes, cc * kBlockK, co0, kh * 3 + kw);
         }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        if (++cc == p.cin_chunks) { cc = 0; if (++kw == 3) { kw = 0; ++kh; } }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(kBlockM, p.block_n, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase[2] = {0, 0};
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        mbar_wait(&tmem_empty[acc], acc_phase[acc] ^ 1);
+    // The loop is warp-uniform and only the tcgen05 instructions sit under elect_one(); descriptor words are
+    // precomputed (high word constant, low word advanced by 32-bit adds), so issuing one MMA costs a handful of
+    // uniform-datapath instructions instead of a 64-bit descriptor build + uniformisation loop.
+    const uint32_t idesc = make_idesc_bf16(kBlockM, p.block_n, 0, 0);
+    constexpr uint32_t hi = desc_hi(1024, kLayoutSW128);
+    const uint32_t a_lo0 = desc_lo(smem_u32(smem_a), 16);
+    const uint32_t b_lo0 = desc_lo(smem_u32(smem_b), 16);
+    const uint32_t b_step = (uint32_t)p.b_stage_bytes >> 4;
+    const bool no_mma = (p.ko & 4) != 0;
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t it = 0;  // tile counter of this CTA: accumulator = it & 1, its use count = it >> 1
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const uint32_t acc = it & 1u;
+      mbar_wait(&tmem_empty[acc], ((it >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t d_addr = tmem_base + acc * (uint32_t)p.block_n;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_addr = tmem_base + (uint32_t)(acc * p.block_n);
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem_a + (size_t)stage * kABytes);
-          const uint32_t b_addr = smem_u32(smem_b + (size_t)stage * p.b_stage_bytes);
-#pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            const uint64_t ad = make_smem_desc(a_addr + k * 32, 16, 1024, kLayoutSW128);
-            const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, 1024, kLayoutSW128);
-            umma_bf16(d_addr, ad, bd, idesc, (kb | k) != 0);
+        const uint32_t a_lo = a_lo0 + (uint32_t)stage * (kABytes >> 4);
+        const uint32_t b_lo = b_lo0 + (uint32_t)stage * b_step;
+        if (elect_one()) {
+          if (!no_mma) {
+            umma_bf16_w(d_addr, a_lo, hi, b_lo, hi, idesc, kb != 0);
+            umma_bf16_w(d_addr, a_lo + 2, hi, b_lo + 2, hi, idesc, 1);
+            umma_bf16_w(d_addr, a_lo + 4, hi, b_lo + 4, hi, idesc, 1);
+            umma_bf16_w(d_addr, a_lo + 6, hi, b_lo + 6, hi, idesc, 1);
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);      // accumulator complete -> epilogue
-        acc_phase[acc] ^= 1;
-        acc ^= 1;
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
+      if (elect_one()) umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+      __syncwarp();
     }
   } else {
     // ===================== epilogue (4 warps, 128 threads) =====================
     const int q = warp & 3;                  // TMEM lane quarter owned by this warp
     const int row = q * 32 + lane;           // accumulator row == pixel index inside the tile
     const int et = threadIdx.x - 64;         // 0..127
-    int acc = 0;
-    uint32_t acc_phase[2] = {0, 0};
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    const EpiSmem es = epi_carve(smem_epi, p.block_n, p.epi.out_cpitch);
+    epi_init(p.epi, es, et);
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const uint32_t acc = it & 1u;
       const int mt = t / p.n_tiles, nt = t - mt * p.n_tiles;
       const int twi = mt % p.tiles_w;
       const int thi = (mt / p.tiles_w) % p.tiles_h;
       const int tni = mt / (p.tiles_w * p.tiles_h);
-      const int co0 = nt * p.block_n;
       // my row's pixel
       const int pw = twi * p.tw + (row & (p.tw - 1));
       const int ph = thi * p.th + ((row >> p.tw_shift) & (p.th - 1));
       const int pn = tni * p.tn + (row >> (p.tw_shift + p.th_shift));
       const bool valid = (pw < p.out_w) && (ph < p.out_h) && (pn < p.n_img);
-      row_valid[row] = valid ? 1u : 0u;
-
-      mbar_wait(&tmem_full[acc], acc_phase[acc]);
+      const int my_pix = (valid && !(p.ko & 1)) ? (pn * p.out_h + ph) * p.out_w + pw : -1;
+      mbar_wait(&tmem_full[acc], (it >> 1) & 1u);
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.block_n);
-      uint8_t* my_row = smem_stage + (size_t)row * p.stage_pitch;
-      for (int c = 0; c < p.block_n; c += 16) {
-        float v[16];
-        tmem_ld16(t_addr + c, v);
-        if (p.bias != nullptr) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += (co0 + c + i < p.cout) ? __ldg(p.bias + co0 + c + i) : 0.f;
-        }
-        if (p.relu) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-        }
-        bf16x8 lo, hi;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          lo.v[i] = __float2bfloat16_rn(v[i]);
-          hi.v[i] = __float2bfloat16_rn(v[8 + i]);
-        }
-        *reinterpret_cast<bf16x8*>(my_row + c * 2) = lo;
-        *reinterpret_cast<bf16x8*>(my_row + c * 2 + 16) = hi;
-      }
-      // all TMEM reads of this warp are done -> hand the accumulator back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-      acc_phase[acc] ^= 1;
-      acc ^= 1;
-
-      named_bar_sync(1, 128);  // staging tile complete
-
-      // ---- coalesced stores: 16-byte chunks, consecutive threads -> consecutive chunks of a pixel row ----
-      const int n_store = min(p.block_n, p.out_cpitch - co0);      // channels this tile owns in memory
-      const int chunks = n_store >> 3;                             // out_cpitch, co0 multiples of 8
-      for (int id = et; id < kBlockM * chunks; id += 128) {
-        const int r = id / chunks, ch = id - r * chunks;
-        if (!row_valid[r]) continue;
-        const int rw = twi * p.tw + (r & (p.tw - 1));
-        const int rh = thi * p.th + ((r >> p.tw_shift) & (p.th - 1));
-        const int rn = tni * p.tn + (r >> (p.tw_shift + p.th_shift));
-        const size_t pix = ((size_t)rn * p.out_h + rh) * p.out_w + rw;
-        const bf16x8 val = *reinterpret_cast<const bf16x8*>(smem_stage + (size_t)r * p.stage_pitch + ch * 16);
-        *reinterpret_cast<bf16x8*>(p.out + pix * p.out_cpitch + co0 + ch * 8) = val;
-      }
-      // ---- BatchNorm statistics of the stored values (per-tile partials, reduced deterministically later) ----
-      if (p.stat_sum != nullptr) {
-        for (int col = et; col < n_store; col += 128) {
-          float s = 0.f, sq = 0.f;
-          for (int r = 0; r < kBlockM; ++r) {
-            if (row_valid[r]) {
-              const float x = __bfloat162float(*reinterpret_cast<const bf16*>(smem_stage + (size_t)r * p.stage_pitch + col * 2));
-              s += x;
-              sq += x * x;
-            }
-          }
-          p.stat_sum[(size_t)mt * p.out_cpitch + co0 + col] = s;
-          p.stat_sq[(size_t)mt * p.out_cpitch + co0 + col] = sq;
-        }
-      }
-      named_bar_sync(1, 128);  // staging buffer free for the next tile
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)p.block_n;
+      epi_tile(p.epi, es, t_addr, my_pix, nt * p.block_n, &tmem_empty[acc], q, lane, et);
     }
+    epi_finish(p.epi, es, et);
   }
 
   tc_fence_before();
@@ -275,11 +224,8 @@ int conv3x3_block_n(int cout) {
   return round_up(ceil_div(c16, parts), 16);
 }
 
-int conv3x3_m_tiles(int n, int out_h, int out_w) {
-  int tw, th, tn;
-  pick_tile(out_w, out_h, n, &tw, &th, &tn);
-  return ceil_div(out_w, tw) * ceil_div(out_h, th) * ceil_div(n, tn);
-}
+// rows of the BatchNorm partial-statistics buffers: one per persistent CTA
+int conv3x3_stat_rows() { return num_sms(); }
 
 // in      : activation view. mode 0 (fprop): pad == 1, output domain = in.H x in.W
 //                            mode 1 (dgrad): pad == 0, output domain = (in.H+2) x (in.W+2)
@@ -288,13 +234,15 @@ int conv3x3_m_tiles(int n, int out_h, int out_w) {
 int conv3x3_launch(const ActView& in, int mode, const bf16* wpacked, int cout, int cin_pitch, bf16* out, int out_cpitch,
                    float* stat_sum, float* stat_sq, const float* bias, int relu, cudaStream_t stream) {
   MIMO_CHECK(mode == 0 || mode == 1, MIMO_ERR_ARG, "conv3x3: bad mode %d", mode);
-  MIMO_CHECK(in.pad == (mode == 0 ? 1 : 0), MIMO_ERR_ARG, "conv3x3: mode %d needs pad=%d input", mode, mode == 0 ? 1 : 0);
+  MIMO_CHECK(mode == 0 ? in.pad == 1 : (in.pad == 0 || in.pad == 2), MIMO_ERR_ARG, "conv3x3: mode %d got a pad=%d input", mode, in.pad);
   MIMO_CHECK(in.cpitch % 8 == 0 && in.c_off % 8 == 0, MIMO_ERR_ALIGN, "conv3x3: input cpitch/c_off must be multiples of 8 (got %d/%d)", in.cpitch, in.c_off);
   MIMO_CHECK(cin_pitch % 8 == 0 && cin_pitch >= in.C, MIMO_ERR_ALIGN, "conv3x3: weight cin pitch %d invalid for C=%d", cin_pitch, in.C);
   MIMO_CHECK(out_cpitch % 8 == 0 && out_cpitch >= cout, MIMO_ERR_ALIGN, "conv3x3: out_cpitch %d invalid for cout=%d", out_cpitch, cout);
   MIMO_CHECK(((uintptr_t)in.base % 16) == 0 && ((uintptr_t)wpacked % 16) == 0 && ((uintptr_t)out % 16) == 0, MIMO_ERR_ALIGN,
              "conv3x3: pointers must be 16-byte aligned");
   MIMO_CHECK(in.H >= 2 && in.W >= 2, MIMO_ERR_ARG, "conv3x3: reflect padding needs H,W >= 2");
+  if (conv3x3_flat_ok(in, mode, cout))
+    return conv3x3_flat_launch(in, mode, wpacked, cout, cin_pitch, out, out_cpitch, stat_sum, stat_sq, bias, relu, stream);
 
   ConvParams p{};
   p.n_img = in.N;
@@ -311,20 +259,27 @@ int conv3x3_launch(const ActView& in, int mode, const bf16* wpacked, int cout, i
   p.n_tiles = ceil_div(round_up(cout, 16), p.block_n);
   p.cin_chunks = ceil_div(in.C, kBlockK);
   p.origin = (mode == 1) ? -2 : 0;
-  p.cout = cout;
-  p.out_cpitch = out_cpitch;
   p.b_stage_bytes = p.block_n * kBlockK * 2;
-  p.stage_pitch = p.block_n * 2 + 16;
-  p.out = out;
-  p.stat_sum = stat_sum;
-  p.stat_sq = stat_sq;
-  p.bias = bias;
-  p.relu = relu;
+  {
+    static const int ko = getenv("MIMO_KO") ? atoi(getenv("MIMO_KO")) : 0;
+    p.ko = ko;
+    if (ko & 8) { stat_sum = nullptr; stat_sq = nullptr; }
+  }
+  p.epi.block_n = p.block_n;
+  p.epi.cout = cout;
+  p.epi.out_cpitch = out_cpitch;
+  p.epi.stage_pitch = p.block_n * 2 + 16;
+  p.epi.stat_rows = conv3x3_stat_rows();
+  p.epi.out = out;
+  p.epi.stat_sum = stat_sum;
+  p.epi.stat_sq = stat_sq;
+  p.epi.bias = bias;
+  p.epi.relu = relu;
   // the last n-tile may own fewer than block_n channels in memory; it must still be a multiple of 8
   MIMO_CHECK((p.n_tiles - 1) * p.block_n < out_cpitch, MIMO_ERR_ARG, "conv3x3: n-tiling exceeds out_cpitch");
 
   const int smem_budget = 227 * 1024 - 1024 /*align slack*/;
-  const int fixed = kBlockM * p.stage_pitch + (2 * kMaxStages + 4) * 8 + 16 + kBlockM * 4 + 64;
+  const int fixed = (int)((epi_smem_bytes(p.block_n, out_cpitch) + 15) & ~size_t(15)) + (2 * kMaxStages + 4) * 8 + 16 + 64;
   int stages = (smem_budget - fixed) / (kABytes + p.b_stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   MIMO_CHECK(stages >= 2, MIMO_ERR_ARG, "conv3x3: not enough shared memory for block_n=%d", p.block_n);
@@ -334,8 +289,9 @@ int conv3x3_launch(const ActView& in, int mode, const bf16* wpacked, int cout, i
   // --- tensor maps ---
   CUtensorMap tm_in, tm_w;
   {
-    const int Hb = in.H + 2 * in.pad, Wb = in.W + 2 * in.pad;
-    uint64_t dims[4] = {(uint64_t)in.C, (uint64_t)Wb, (uint64_t)Hb, (uint64_t)in.N};
+    // fprop reads the whole haloed buffer; dgrad reads the H x W interior (zero fill outside) whatever the buffer pitch is
+    const int Hb = in.hb(), Wb = in.wb();
+    uint64_t dims[4] = {(uint64_t)in.C, (uint64_t)(mode == 0 ? Wb : in.W), (uint64_t)(mode == 0 ? Hb : in.H), (uint64_t)in.N};
     uint64_t strides[3] = {(uint64_t)in.cpitch * 2, (uint64_t)Wb * in.cpitch * 2, (uint64_t)Hb * Wb * in.cpitch * 2};
     uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)p.tw, (uint32_t)p.th, (uint32_t)p.tn};
     int rc = encode_tmap_bf16(&tm_in, in.base + in.c_off, 4, dims, strides, box, 1);

@@ -80,48 +80,53 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_c
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int pt = pt_begin; pt < pt_end; ++pt) {
-        const int twi = pt % p.tiles_w;
-        const int thi = (pt / p.tiles_w) % p.tiles_h;
-        const int tni = pt / (p.tiles_w * p.tiles_h);
-        const int w0 = twi * p.tw, h0 = thi * p.th, n0 = tni * p.tn;
-        uint8_t* st = smem + (size_t)stage * kStageBytes;
-        mbar_wait(&empty_bar[stage], phase ^ 1);
+    // TMA producer: warp-uniform loop, one elected lane issues
+    int stage = 0; uint32_t phase = 0;
+    for (int pt = pt_begin; pt < pt_end; ++pt) {
+      const int twi = pt % p.tiles_w;
+      const int thi = (pt / p.tiles_w) % p.tiles_h;
+      const int tni = pt / (p.tiles_w * p.tiles_h);
+      const int w0 = twi * p.tw, h0 = thi * p.th, n0 = tni * p.tn;
+      uint8_t* st = smem + (size_t)stage * kStageBytes;
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
         tma_load_4d(&tmap_dy, &full_bar[stage], st, cot * 128, w0, h0, n0);
         tma_load_4d(&tmap_dy, &full_bar[stage], st + kTileBytes, cot * 128 + 64, w0, h0, n0);
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw)  // X is the padded activation: pixel (h,w) + tap (kh,kw) -> (h+kh, w+kw)
           tma_load_4d(&tmap_x, &full_bar[stage], st + (2 + kw) * kTileBytes, cic * 64, w0 + kw, h0 + kh, n0);
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
+      __syncwarp();
+      if (++stage == kStages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);  // both operands MN-major
-      int stage = 0; uint32_t phase = 0;
-      for (int kb = 0; kb < n_kb; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        const uint32_t st = smem_u32(smem + (size_t)stage * kStageBytes);
+    // MMA issuer: warp-uniform loop, precomputed descriptor words (see common.cuh), tcgen05 under elect_one()
+    const uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);  // both operands MN-major
+    constexpr uint32_t hi = desc_hi(1024, kLayoutSW128);
+    // MN-major SW128: 64 channels contiguous (one 128 B row per pixel); next 64-channel block at LBO;
+    // 8-pixel groups at SBO = 1024 B; a 16-pixel k-step advances the start address by 2048 B.
+    const uint32_t lo0 = desc_lo(smem_u32(smem), kTileBytes);
+    int stage = 0; uint32_t phase = 0;
+    for (int kb = 0; kb < n_kb; ++kb) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      const uint32_t a_lo = lo0 + (uint32_t)stage * (kStageBytes >> 4);
+      if (elect_one()) {
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) {
 #pragma unroll
-          for (int k = 0; k < kPix / 16; ++k) {
-            // MN-major SW128: 64 channels contiguous (one 128 B row per pixel); next 64-channel block at LBO;
-            // 8-pixel groups at SBO = 1024 B; a 16-pixel k-step advances the start address by 2048 B.
-            const uint64_t ad = make_smem_desc(st + k * 2048, kTileBytes, 1024, kLayoutSW128);
-            const uint64_t bd = make_smem_desc(st + (2 + kw) * kTileBytes + k * 2048, kTileBytes, 1024, kLayoutSW128);
-            umma_bf16(tmem_base + kw * 64, ad, bd, idesc, (kb | k) != 0);
-          }
+          for (int k = 0; k < kPix / 16; ++k)
+            umma_bf16_w(tmem_base + kw * 64, a_lo + k * (2048 >> 4), hi, a_lo + (((2 + kw) * kTileBytes + k * 2048) >> 4), hi, idesc,
+                        (kb | k) != 0);
         }
         umma_commit(&empty_bar[stage]);
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
-      umma_commit(done_bar);
+      __syncwarp();
+      if (++stage == kStages) { stage = 0; phase ^= 1; }
     }
+    if (elect_one()) umma_commit(done_bar);
+    __syncwarp();
   } else {
     const int q = warp & 3;
     const int co = cot * 128 + q * 32 + lane;
@@ -190,11 +195,12 @@ __global__ void wgrad_unpack_kernel(const float* __restrict__ packed, float* __r
 // x      : padded activation view [N][H+2][W+2][cin]   (pad == 1, c_off % 8 == 0)
 // dw     : fp32 [9][cout][cin_pitch], cin_pitch % 4 == 0; zeroed here before accumulation
 int conv3x3_wgrad_launch(const ActView& dy, const ActView& x, float* dw, int cin_pitch, cudaStream_t stream) {
-  MIMO_CHECK(dy.pad == 0 && x.pad == 1, MIMO_ERR_ARG, "wgrad: dy must be unpadded and x padded");
+  MIMO_CHECK((dy.pad == 0 || dy.pad == 2) && x.pad == 1, MIMO_ERR_ARG, "wgrad: dy must be dense or zero-tailed and x haloed");
   MIMO_CHECK(dy.N == x.N && dy.H == x.H && dy.W == x.W, MIMO_ERR_ARG, "wgrad: dy/x shape mismatch");
   MIMO_CHECK(dy.cpitch % 8 == 0 && dy.c_off % 8 == 0 && x.cpitch % 8 == 0 && x.c_off % 8 == 0, MIMO_ERR_ALIGN,
              "wgrad: channel pitch/offset must be multiples of 8");
   MIMO_CHECK(cin_pitch % 4 == 0 && cin_pitch >= x.C, MIMO_ERR_ALIGN, "wgrad: cin_pitch %d invalid", cin_pitch);
+  if (conv3x3_wgrad_flat_ok(dy, x)) return conv3x3_wgrad_flat_launch(dy, x, dw, cin_pitch, stream);
   WgradParams p{};
   p.n_img = dy.N; p.H = dy.H; p.W = dy.W;
   pick_tile64(p.W, p.H, p.n_img, &p.tw, &p.th, &p.tn);
@@ -217,7 +223,7 @@ int conv3x3_wgrad_launch(const ActView& dy, const ActView& x, float* dw, int cin
   CUtensorMap tm_dy, tm_x;
   {
     uint64_t dims[4] = {(uint64_t)dy.C, (uint64_t)dy.W, (uint64_t)dy.H, (uint64_t)dy.N};
-    uint64_t strides[3] = {(uint64_t)dy.cpitch * 2, (uint64_t)dy.W * dy.cpitch * 2, (uint64_t)dy.H * dy.W * dy.cpitch * 2};
+    uint64_t strides[3] = {(uint64_t)dy.cpitch * 2, (uint64_t)dy.wb() * dy.cpitch * 2, (uint64_t)dy.hb() * dy.wb() * dy.cpitch * 2};
     uint32_t box[4] = {64, (uint32_t)p.tw, (uint32_t)p.th, (uint32_t)p.tn};
     int rc = encode_tmap_bf16(&tm_dy, dy.base + dy.c_off, 4, dims, strides, box, 1);
     if (rc) return rc;

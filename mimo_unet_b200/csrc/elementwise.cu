@@ -145,48 +145,58 @@ __global__ void bn_eval_affine_kernel(int C, const float* gamma, const float* be
 // BN apply + ReLU (+ Dropout2d keep-scale) (+ 2x2 max-pool) with reflect-halo writes.
 // One thread = one 2x2 pixel cell x 8 channels.
 // ------------------------------------------------------------------------------------------------
-__global__ void bn_relu_apply_kernel(const bf16* __restrict__ y, int ycp, const float* __restrict__ scale,
-                                     const float* __restrict__ shift, const float* __restrict__ drop /*[N][C] or null*/,
-                                     ActView o, ActView pool, int do_pool) {
+// One block per row of 2x2 cells (two image rows), grid-stride over cell rows: 32-bit index math only.
+__global__ void __launch_bounds__(256, 3)
+bn_relu_apply_kernel(const bf16* __restrict__ y, int ycp, const float* __restrict__ scale,
+                     const float* __restrict__ shift, const float* __restrict__ drop /*[N][C] or null*/,
+                     ActView o, ActView pool, int do_pool) {
   const int cells_h = (o.H + 1) >> 1, cells_w = (o.W + 1) >> 1;
   const int groups = (o.C + 7) >> 3;
-  const long long total = (long long)o.N * cells_h * cells_w * groups;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(i % groups);
-    long long r = i / groups;
-    const int cw = (int)(r % cells_w); r /= cells_w;
-    const int chh = (int)(r % cells_h);
-    const int n = (int)(r / cells_h);
-    const int c = g * 8, nv = min(8, o.C - c);
-    float sc[8], sh[8], dr[8];
+  const int cell_rows = o.N * cells_h;
+  const int items = cells_w * groups;
+  for (int cr = blockIdx.x; cr < cell_rows; cr += gridDim.x) {
+    const int n = cr / cells_h, chh = cr - n * cells_h;
+    const int h0 = chh * 2;
+    const bool row1 = h0 + 1 < o.H;
+    const bf16* y0 = y + (size_t)(n * o.H + h0) * o.W * ycp;
+    const bf16* y1 = y0 + (size_t)o.W * ycp;
+    for (int i = threadIdx.x; i < items; i += blockDim.x) {
+      const int cw = i / groups, g = i - cw * groups;
+      const int c = g * 8, nv = min(8, o.C - c);
+      const int w0 = cw * 2;
+      const bool col1 = w0 + 1 < o.W;
+      // issue all loads of the cell first (y is dense with ycp % 8 == 0: every 8-channel group is one aligned 16-byte load)
+      bf16x8 raw[4];
+      raw[0] = *reinterpret_cast<const bf16x8*>(y0 + (size_t)w0 * ycp + c);
+      if (col1) raw[1] = *reinterpret_cast<const bf16x8*>(y0 + (size_t)(w0 + 1) * ycp + c);
+      if (row1) raw[2] = *reinterpret_cast<const bf16x8*>(y1 + (size_t)w0 * ycp + c);
+      if (row1 && col1) raw[3] = *reinterpret_cast<const bf16x8*>(y1 + (size_t)(w0 + 1) * ycp + c);
+      float sc[8], sh[8], dr[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      sc[k] = (k < nv) ? scale[c + k] : 0.f;
-      sh[k] = (k < nv) ? shift[c + k] : 0.f;
-      dr[k] = (drop && k < nv) ? drop[(size_t)n * o.C + c + k] : 1.f;
-    }
-    float mx[8];
+      for (int k = 0; k < 8; ++k) {
+        sc[k] = (k < nv) ? scale[c + k] : 0.f;
+        sh[k] = (k < nv) ? shift[c + k] : 0.f;
+        dr[k] = (drop && k < nv) ? drop[(size_t)n * o.C + c + k] : 1.f;
+      }
+      float mx[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) mx[k] = -INFINITY;
-    bool full = true;
+      for (int k = 0; k < 8; ++k) mx[k] = -INFINITY;
 #pragma unroll
-    for (int dy = 0; dy < 2; ++dy) {
-#pragma unroll
-      for (int dx = 0; dx < 2; ++dx) {
-        const int h = chh * 2 + dy, w = cw * 2 + dx;
-        if (h >= o.H || w >= o.W) { full = false; continue; }
+      for (int j = 0; j < 4; ++j) {
+        const int dy = j >> 1, dx = j & 1;
+        if ((dy && !row1) || (dx && !col1)) continue;
         float v[8];
-        load8(y + ((size_t)(n * o.H + h) * o.W + w) * ycp + c, nv, v);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           // the activation is STORED in bf16: pool over the stored value so indices/values agree with it
-          v[k] = __bfloat162float(__float2bfloat16_rn(fmaxf(fmaf(v[k], sc[k], sh[k]), 0.f) * dr[k]));
-          mx[k] = (v[k] > mx[k] || v[k] != v[k]) ? v[k] : mx[k];
+          const float a = __bfloat162float(__float2bfloat16_rn(fmaxf(fmaf(__bfloat162float(raw[j].v[k]), sc[k], sh[k]), 0.f) * dr[k]));
+          v[k] = a;
+          mx[k] = (a > mx[k] || a != a) ? a : mx[k];
         }
-        store_with_halo(o, n, h, w, c, nv, v);
+        store_with_halo(o, n, h0 + dy, w0 + dx, c, nv, v);
       }
+      if (do_pool && row1 && col1 && chh < pool.H && cw < pool.W) store_with_halo(pool, n, chh, cw, c, nv, mx);
     }
-    if (do_pool && full && chh < pool.H && cw < pool.W) store_with_halo(pool, n, chh, cw, c, nv, mx);
   }
 }
 
@@ -399,61 +409,100 @@ __global__ void grad_gather_kernel(ActView dpad, int has_dpad, ActView gpool, Ac
 // ------------------------------------------------------------------------------------------------
 // BN + ReLU (+dropout) backward.
 //   dz = G * drop * [scale*y + shift > 0]
-//   pass 1 (reduce): s1 = sum dz, s2 = sum dz * x_hat with x_hat = (y - mean) * invstd   -> per-block partials
+//   pass 1 (reduce): per-block partials of sum dz and sum dz*y; the finalize kernel forms (in double)
+//                    s1 = sum dz, s2 = sum dz * x_hat = invstd * (sum dz*y - mean * s1), x_hat = (y - mean) * invstd
 //   pass 2 (apply) : dy = scale * (dz - (s1 + x_hat * s2) / count)     [training]
 //                    dy = scale * dz                                     [eval: running stats are constants]
 // ------------------------------------------------------------------------------------------------
-__global__ void bn_bwd_reduce_kernel(ActView G, const bf16* __restrict__ y, int ycp, const float* __restrict__ scale,
-                                     const float* __restrict__ shift, const float* __restrict__ mean,
-                                     const float* __restrict__ invstd, const float* __restrict__ drop, int C,
-                                     float* __restrict__ part /*[gridDim.x][2][C]*/) {
-  // block handles a contiguous pixel range; thread (tx = channel group lane, ty = pixel lane)
-  extern __shared__ float sh[];  // [2][C] accumulators
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
-  __syncthreads();
+// Block = 256 threads = (pixel lanes) x (8-channel groups); a block walks whole image rows (row = n*H + h), so
+// there is no per-element 64-bit index arithmetic; per-thread register accumulators are combined in shared memory
+// in a fixed order (deterministic), one partial row per block.
+__global__ void __launch_bounds__(256, 3)
+bn_bwd_reduce_kernel(ActView G, const bf16* __restrict__ y, int ycp, const float* __restrict__ scale,
+                     const float* __restrict__ shift, const float* __restrict__ drop, int C,
+                     float* __restrict__ part /*[gridDim.x][2][C]: sum dz, sum dz*y*/) {
+  extern __shared__ float sh[];  // [pix_lanes][groups*16]
   const int groups = (C + 7) >> 3;
-  const long long npix = (long long)G.N * G.H * G.W;
   const int pix_lanes = blockDim.x / groups;  // >= 1 (host guarantees groups <= blockDim.x)
   const int g = threadIdx.x % groups, pl = threadIdx.x / groups;
+  const int rows = G.N * G.H;
+  const int c = g * 8, nv = min(8, C - c);
+  float a1[8], a2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { a1[k] = 0.f; a2[k] = 0.f; }
   if (pl < pix_lanes) {
-    const int c = g * 8, nv = min(8, C - c);
-    float sc[8], sf[8], mu[8], is[8], a1[8], a2[8];
+    float sc[8], sf[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      sc[k] = k < nv ? scale[c + k] : 0.f; sf[k] = k < nv ? shift[c + k] : 0.f;
-      mu[k] = k < nv ? mean[c + k] : 0.f;  is[k] = k < nv ? invstd[c + k] : 0.f;
-      a1[k] = 0.f; a2[k] = 0.f;
-    }
-    for (long long pidx = (long long)blockIdx.x * pix_lanes + pl; pidx < npix; pidx += (long long)gridDim.x * pix_lanes) {
-      const int w = (int)(pidx % G.W), h = (int)((pidx / G.W) % G.H), n = (int)(pidx / ((long long)G.W * G.H));
-      float gv[8], yv[8];
-      load8(G.base + G.pix(n, h, w) + c, nv, gv);
-      load8(y + (size_t)pidx * ycp + c, nv, yv);
+    for (int k = 0; k < 8; ++k) { sc[k] = k < nv ? scale[c + k] : 0.f; sf[k] = k < nv ? shift[c + k] : 0.f; }
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+      const int n = row / G.H, h = row - n * G.H;
+      const bf16* gp = G.base + G.pix(n, h, 0) + c;
+      const bf16* yp = y + (size_t)row * G.W * ycp + c;
+      float dr[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float z = fmaf(yv[k], sc[k], sf[k]);
-        const float d = (drop && k < nv) ? drop[(size_t)n * C + c + k] : 1.f;
-        const float dz = (z > 0.f) ? gv[k] * d : 0.f;
-        a1[k] += dz;
-        a2[k] += dz * (yv[k] - mu[k]) * is[k];
+      for (int k = 0; k < 8; ++k) dr[k] = (drop && k < nv) ? drop[(size_t)n * C + c + k] : 1.f;
+      for (int w = pl; w < G.W; w += 2 * pix_lanes) {
+        const int w2 = w + pix_lanes;
+        float gv[8], yv[8], gv2[8], yv2[8];
+        load8(gp + (size_t)w * G.cpitch, nv, gv);
+        load8(yp + (size_t)w * ycp, nv, yv);
+        const bool has2 = w2 < G.W;
+        if (has2) {
+          load8(gp + (size_t)w2 * G.cpitch, nv, gv2);
+          load8(yp + (size_t)w2 * ycp, nv, yv2);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float z = fmaf(yv[k], sc[k], sf[k]);
+          const float dz = (z > 0.f) ? gv[k] * dr[k] : 0.f;
+          a1[k] += dz;
+          a2[k] = fmaf(dz, yv[k], a2[k]);
+        }
+        if (has2) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float z = fmaf(yv2[k], sc[k], sf[k]);
+            const float dz = (z > 0.f) ? gv2[k] * dr[k] : 0.f;
+            a1[k] += dz;
+            a2[k] = fmaf(dz, yv2[k], a2[k]);
+          }
+        }
       }
     }
+    float* mine = sh + (size_t)pl * groups * 16 + g * 16;
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
-      if (k < nv) { atomicAdd(&sh[c + k], a1[k]); atomicAdd(&sh[C + c + k], a2[k]); }
+    for (int k = 0; k < 8; ++k) { mine[k] = a1[k]; mine[8 + k] = a2[k]; }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) part[(size_t)blockIdx.x * 2 * C + i] = sh[i];
+  // fixed-order combine over the pixel lanes: thread i < 2*C owns (which = i / C, channel = i % C)
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    const int which = i / C, ch = i - which * C;
+    const float* src = sh + (ch >> 3) * 16 + which * 8 + (ch & 7);
+    float acc = 0.f;
+    for (int p = 0; p < pix_lanes; ++p) acc += src[(size_t)p * groups * 16];
+    part[(size_t)blockIdx.x * 2 * C + i] = acc;
+  }
 }
 
-// reduce partials -> s1,s2 ; write dgamma (= s2), dbeta (= s1), dbias_conv (eval only: scale * s1)
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int nparts, int C, float* __restrict__ s1s2 /*[2][C]*/,
-                                       float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias,
-                                       const float* __restrict__ scale, int training, float grad_scale, int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// reduce partials -> s1,s2 ; write dgamma (= s2), dbeta (= s1), dbias_conv (eval only: scale * s1).
+// Block = 8 channels x 32 partial lanes, combined in a fixed order.
+__global__ void __launch_bounds__(256)
+bn_bwd_finalize_kernel(const float* __restrict__ part, int nparts, int C, float* __restrict__ s1s2 /*[2][C]*/,
+                       float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias,
+                       const float* __restrict__ scale, const float* __restrict__ mean, const float* __restrict__ invstd,
+                       int training, float grad_scale, int accumulate) {
+  __shared__ double sa[32][8], sb[32][8];
+  const int cl = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  const int c = blockIdx.x * 8 + cl;
   double a = 0.0, b = 0.0;
-  for (int p = 0; p < nparts; ++p) { a += part[(size_t)p * 2 * C + c]; b += part[(size_t)p * 2 * C + C + c]; }
+  if (c < C)
+    for (int p = pl; p < nparts; p += 32) { a += part[(size_t)p * 2 * C + c]; b += part[(size_t)p * 2 * C + C + c]; }
+  sa[pl][cl] = a; sb[pl][cl] = b;
+  __syncthreads();
+  if (pl != 0 || c >= C) return;
+  a = 0.0; b = 0.0;
+  for (int p = 0; p < 32; ++p) { a += sa[p][cl]; b += sb[p][cl]; }
+  b = (double)invstd[c] * (b - (double)mean[c] * a);
   s1s2[c] = (float)a; s1s2[C + c] = (float)b;
   if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)b * grad_scale;
   if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)a * grad_scale;
@@ -461,42 +510,47 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int npart
   if (dbias) dbias[c] = (accumulate ? dbias[c] : 0.f) + (training ? 0.f : (float)a * scale[c] * grad_scale);
 }
 
-__global__ void bn_bwd_apply_kernel(ActView G, const bf16* __restrict__ y, int ycp, const float* __restrict__ scale,
-                                    const float* __restrict__ shift, const float* __restrict__ mean,
-                                    const float* __restrict__ invstd, const float* __restrict__ drop,
-                                    const float* __restrict__ s1s2, int C, float inv_count, int training, bf16* __restrict__ dy,
-                                    int dycp) {
+// One block per image row (grid-stride over rows); threads = (pixel, 8-channel group), groups fastest.
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(ActView G, const bf16* __restrict__ y, int ycp, const float* __restrict__ scale,
+                    const float* __restrict__ shift, const float* __restrict__ mean,
+                    const float* __restrict__ invstd, const float* __restrict__ drop,
+                    const float* __restrict__ s1s2, int C, float inv_count, int training, ActView dy) {
   const int groups = (C + 7) >> 3;
-  const long long npix = (long long)G.N * G.H * G.W;
-  const long long total = npix * groups;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(i % groups);
-    const long long pidx = i / groups;
-    const int w = (int)(pidx % G.W), h = (int)((pidx / G.W) % G.H), n = (int)(pidx / ((long long)G.W * G.H));
-    const int c = g * 8, nv = min(8, C - c);
-    float gv[8], yv[8], out[8];
-    load8(G.base + G.pix(n, h, w) + c, nv, gv);
-    load8(y + (size_t)pidx * ycp + c, nv, yv);
+  const int rows = G.N * G.H;
+  const int items = G.W * groups;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int n = row / G.H, h = row - n * G.H;
+    const bf16* gp = G.base + G.pix(n, h, 0);
+    const bf16* yp = y + (size_t)row * G.W * ycp;
+    bf16* dp = dy.base + dy.pix(n, h, 0);
+    for (int i = threadIdx.x; i < items; i += blockDim.x) {
+      const int w = i / groups, g = i - w * groups;
+      const int c = g * 8, nv = min(8, C - c);
+      float gv[8], yv[8], out[8];
+      load8(gp + (size_t)w * G.cpitch + c, nv, gv);
+      load8(yp + (size_t)w * ycp + c, nv, yv);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      if (k < nv) {
-        const float sc = scale[c + k];
-        const float z = fmaf(yv[k], sc, shift[c + k]);
-        const float d = drop ? drop[(size_t)n * C + c + k] : 1.f;
-        const float dz = (z > 0.f) ? gv[k] * d : 0.f;
-        if (training) {
-          const float xh = (yv[k] - mean[c + k]) * invstd[c + k];
-          out[k] = sc * (dz - (s1s2[c + k] + xh * s1s2[C + c + k]) * inv_count);
+      for (int k = 0; k < 8; ++k) {
+        if (k < nv) {
+          const float sc = scale[c + k];
+          const float z = fmaf(yv[k], sc, shift[c + k]);
+          const float d = drop ? drop[(size_t)n * C + c + k] : 1.f;
+          const float dz = (z > 0.f) ? gv[k] * d : 0.f;
+          if (training) {
+            const float xh = (yv[k] - mean[c + k]) * invstd[c + k];
+            out[k] = sc * (dz - (s1s2[c + k] + xh * s1s2[C + c + k]) * inv_count);
+          } else {
+            out[k] = sc * dz;
+          }
         } else {
-          out[k] = sc * dz;
+          out[k] = 0.f;
         }
-      } else {
-        out[k] = 0.f;
       }
+      // pad channels of dy are written as zeros so the tensor-core kernels never see garbage
+      const int nstore = min(8, dy.cpitch - c);
+      store8(dp + (size_t)w * dy.cpitch + c, nstore, out);
     }
-    // pad channels of dy are written as zeros so the tensor-core kernels never see garbage
-    const int nstore = min(8, dycp - c);
-    store8(dy + (size_t)pidx * dycp + c, nstore, out);
   }
 }
 
@@ -613,8 +667,9 @@ int bn_relu_apply_launch(const bf16* y, int ycp, const float* scale, const float
   MIMO_CHECK(o.H >= 2 && o.W >= 2, MIMO_ERR_ARG, "bn_relu_apply: H,W must be >= 2");
   ActView pv = pool ? *pool : o;
   if (pool) MIMO_CHECK(pool->H == o.H / 2 && pool->W == o.W / 2 && pool->C == o.C && pool->N == o.N, MIMO_ERR_ARG, "bn_relu_apply: pool view shape mismatch");
-  const long long total = (long long)o.N * ((o.H + 1) / 2) * ((o.W + 1) / 2) * ((o.C + 7) / 8);
-  bn_relu_apply_kernel<<<grid_for(total), kBlock, 0, st>>>(y, ycp, scale, shift, drop, o, pv, pool ? 1 : 0);
+  const int cell_rows = o.N * ((o.H + 1) / 2);
+  const int grid = cell_rows < 32 * num_sms() ? cell_rows : 32 * num_sms();
+  bn_relu_apply_kernel<<<grid, kBlock, 0, st>>>(y, ycp, scale, shift, drop, o, pv, pool ? 1 : 0);
   MIMO_LAUNCH_CHECK();
   return MIMO_OK;
 }
@@ -659,23 +714,28 @@ int grad_gather_launch(const ActView* dpad, const ActView* gpool, const ActView*
   return MIMO_OK;
 }
 
-int bn_bwd_parts(int C) { (void)C; return 2 * num_sms(); }
+int bn_bwd_parts(int C) { (void)C; return 4 * num_sms(); }
 
 int bn_bwd_launch(const ActView& G, const bf16* y, int ycp, const float* scale, const float* shift, const float* mean,
                   const float* invstd, const float* drop, int training, float* part, float* s1s2, float* dgamma, float* dbeta,
-                  float* dbias, float grad_scale, int accumulate, bf16* dy, int dycp, cudaStream_t st) {
+                  float* dbias, float grad_scale, int accumulate, const ActView& dy, cudaStream_t st) {
   const int C = G.C;
   MIMO_CHECK(G.pad == 0, MIMO_ERR_ARG, "bn_bwd: G must be unpadded");
-  MIMO_CHECK((C + 7) / 8 <= kBlock, MIMO_ERR_ARG, "bn_bwd: too many channels (%d)", C);
-  const int nparts = bn_bwd_parts(C);
-  bn_bwd_reduce_kernel<<<nparts, kBlock, 2 * C * sizeof(float), st>>>(G, y, ycp, scale, shift, mean, invstd, drop, C, part);
+  MIMO_CHECK(dy.pad != 1 && dy.c_off == 0 && dy.N == G.N && dy.H == G.H && dy.W == G.W && dy.cpitch >= C, MIMO_ERR_ARG,
+             "bn_bwd: dy must be a whole dense or zero-tail buffer of the same shape");
+  const int groups = (C + 7) / 8;
+  MIMO_CHECK(groups <= kBlock, MIMO_ERR_ARG, "bn_bwd: too many channels (%d)", C);
+  const int rows = G.N * G.H;
+  const int nparts = rows < bn_bwd_parts(C) ? rows : bn_bwd_parts(C);
+  const int pix_lanes = kBlock / groups;
+  const size_t sh_bytes = (size_t)pix_lanes * groups * 16 * sizeof(float);
+  bn_bwd_reduce_kernel<<<nparts, kBlock, sh_bytes, st>>>(G, y, ycp, scale, shift, drop, C, part);
   MIMO_LAUNCH_CHECK();
-  bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(part, nparts, C, s1s2, dgamma, dbeta, dbias, scale, training, grad_scale, accumulate);
+  bn_bwd_finalize_kernel<<<ceil_div(C, 8), 256, 0, st>>>(part, nparts, C, s1s2, dgamma, dbeta, dbias, scale, mean, invstd, training, grad_scale, accumulate);
   MIMO_LAUNCH_CHECK();
   const long long npix = (long long)G.N * G.H * G.W;
-  const long long total = npix * ((C + 7) / 8);
-  bn_bwd_apply_kernel<<<grid_for(total), kBlock, 0, st>>>(G, y, ycp, scale, shift, mean, invstd, drop, s1s2, C, 1.f / (float)npix,
-                                                          training, dy, dycp);
+  const int grid = rows < 32 * num_sms() ? rows : 32 * num_sms();
+  bn_bwd_apply_kernel<<<grid, kBlock, 0, st>>>(G, y, ycp, scale, shift, mean, invstd, drop, s1s2, C, 1.f / (float)npix, training, dy);
   MIMO_LAUNCH_CHECK();
   return MIMO_OK;
 }

@@ -30,7 +30,7 @@ struct Arena {
 struct Buf {  // activation-like buffer inside the workspace
   size_t off = 0;
   int N = 0, H = 0, W = 0, pad = 0, cpitch = 0;
-  size_t bytes() const { return (size_t)N * (H + 2 * pad) * (W + 2 * pad) * cpitch * sizeof(bf16); }
+  size_t bytes() const { return (size_t)N * (H + (pad ? 2 : 0)) * (W + (pad ? 2 : 0)) * cpitch * sizeof(bf16); }
 };
 
 struct View {  // channel slice of a Buf
@@ -88,6 +88,7 @@ struct mimo_unet_plan {
   bool bound = false;
   bool last_training = false;
   bool have_forward = false;
+  bool dy_tails_zeroed = false;  // the zero tails of the dy buffers are cleared once per binding
   const float* const* last_masks = nullptr;
   std::vector<const float*> masks_copy;
   int launches = 0;
@@ -126,7 +127,7 @@ void setup_conv(mimo_unet_plan* P, Arena& A, ConvL& c, int cin, int cout, int N,
   c.cin = cin; c.cout = cout; c.cin_p = p8(cin); c.cout_p = p8(cout); c.N = N; c.H = H; c.W = W;
   c.state0 = state_cursor;
   state_cursor += 7;
-  c.m_tiles = conv3x3_m_tiles(N, H, W);
+  c.m_tiles = conv3x3_stat_rows();
   c.wf = A.take((size_t)9 * cout * c.cin_p * sizeof(bf16));
   c.wd = A.take((size_t)9 * cin * c.cout_p * sizeof(bf16));
   c.psum = A.take((size_t)c.m_tiles * c.cout_p * sizeof(float));
@@ -135,7 +136,7 @@ void setup_conv(mimo_unet_plan* P, Arena& A, ConvL& c, int cin, int cout, int N,
   c.bnpart = A.take((size_t)bn_bwd_parts(cout) * 2 * cout * sizeof(float));
   c.dwp = A.take((size_t)9 * cout * c.cin_p * sizeof(float));
   c.y = add_buf(P, A, N, H, W, 0, cout);
-  c.dy = add_buf(P, A, N, H, W, 0, cout);
+  c.dy = add_buf(P, A, N, H, W, 2, cout);  // zero-tail layout: read by the flat dgrad / wgrad kernels
   c.dpad = add_buf(P, A, N, H + 2, W + 2, 0, cin);
 }
 
@@ -235,12 +236,11 @@ int conv_bn_backward(mimo_unet_plan* P, ConvL& c, const ActView& G, const ActVie
   float* vec = fptr(P, c.vec);
   float *scale = vec, *shift = vec + c.cout_p, *mean = vec + 2 * c.cout_p, *invstd = vec + 3 * c.cout_p, *s1s2 = vec + 4 * c.cout_p;
   const bf16* y = bptr(P, P->bufs[c.y].off);
-  bf16* dy = bptr(P, P->bufs[c.dy].off);
+  const ActView dyv = view_of(P, c.dy, 0, c.cout);
   RUN(kBnBwd, bn_bwd_launch(G, y, c.cout_p, scale, shift, mean, invstd, drop, training ? 1 : 0, fptr(P, c.bnpart), s1s2,
                     (float*)P->grads[c.state0 + 2], (float*)P->grads[c.state0 + 3], (float*)P->grads[c.state0 + 1], 1.f, accumulate,
-                    dy, c.cout_p, st));
+                    dyv, st));
   ++P->launches; ++P->launches;  // bn_bwd is three kernels
-  const ActView dyv = view_of(P, c.dy, 0, c.cout);
   if (P->grads[c.state0] != nullptr) {
     RUN(kConvWgrad, conv3x3_wgrad_launch(dyv, in, fptr(P, c.dwp), c.cin_p, st));
     RUN(kWgradUnpack, wgrad_unpack_launch(fptr(P, c.dwp), (float*)P->grads[c.state0], c.cout, c.cin, c.cin_p, 1.f, accumulate, st));
@@ -446,6 +446,7 @@ int mimo_unet_bind(mimo_unet_plan_t* P, void* workspace, size_t workspace_bytes,
   else P->grads.assign(n, nullptr);
   P->bound = true;
   P->have_forward = false;
+  P->dy_tails_zeroed = false;
   return MIMO_OK;
 }
 
@@ -512,6 +513,12 @@ int mimo_unet_backward(mimo_unet_plan_t* P, const float* dout, const float* grad
   auto mask = [&](int ni) { return P->masks_copy[ni]; };
   for (int s = 0; s < S; ++s) P->nodes[P->enc_in[s]].need_in_grad = (dx != nullptr);
   int rc;
+  if (!P->dy_tails_zeroed) {
+    // the interior of every dy buffer is rewritten each step; the 2-pixel zero tail only needs clearing once
+    for (auto& n : P->nodes)
+      for (ConvL* c : {&n.c1, &n.c2}) MIMO_CUDA(cudaMemsetAsync(P->ws + P->bufs[c->dy].off, 0, P->bufs[c->dy].bytes(), st));
+    P->dy_tails_zeroed = true;
+  }
 
   // ---- decoders ----
   for (int s = 0; s < S; ++s) {

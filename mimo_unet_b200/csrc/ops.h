@@ -7,10 +7,15 @@ namespace mimo {
 
 // ---- tensor-core convolutions (conv_igemm.cu / conv_wgrad.cu) ----
 int conv3x3_block_n(int cout);
-int conv3x3_m_tiles(int n, int out_h, int out_w);
+int conv3x3_stat_rows();
+bool conv3x3_flat_ok(const ActView& in, int mode, int cout);
+int conv3x3_flat_launch(const ActView& in, int mode, const bf16* wpacked, int cout, int cin_pitch, bf16* out, int out_cpitch,
+                        float* stat_sum, float* stat_sq, const float* bias, int relu, cudaStream_t stream);
 int conv3x3_launch(const ActView& in, int mode, const bf16* wpacked, int cout, int cin_pitch, bf16* out, int out_cpitch,
                    float* stat_sum, float* stat_sq, const float* bias, int relu, cudaStream_t stream);
 int conv3x3_wgrad_launch(const ActView& dy, const ActView& x, float* dw_packed, int cin_pitch, cudaStream_t stream);
+bool conv3x3_wgrad_flat_ok(const ActView& dy, const ActView& x);
+int conv3x3_wgrad_flat_launch(const ActView& dy, const ActView& x, float* dw_packed, int cin_pitch, cudaStream_t stream);
 int wgrad_unpack_launch(const float* packed, float* grad_oihw, int cout, int cin, int cin_pitch, float scale, int accumulate,
                         cudaStream_t stream);
 
@@ -35,7 +40,7 @@ int unpack_nchw_launch(const ActView& in, float* out, cudaStream_t st);
 int bn_bwd_parts(int C);
 int bn_bwd_launch(const ActView& G, const bf16* y, int ycp, const float* scale, const float* shift, const float* mean,
                   const float* invstd, const float* drop, int training, float* part, float* s1s2, float* dgamma, float* dbeta,
-                  float* dbias, float grad_scale, int accumulate, bf16* dy, int dycp, cudaStream_t st);
+                  float* dbias, float grad_scale, int accumulate, const ActView& dy, cudaStream_t st);
 
 // ---- heads, loss, loss buffer, aggregation (head_loss.cu) ----
 int head_fwd_launch(const ActView& f, const float* W, const float* bias, int K, float* out, long long out_bstride, cudaStream_t st);

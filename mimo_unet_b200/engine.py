@@ -98,10 +98,12 @@ class UNetPlan:
         off = a.ptr - base
         if kind.value == 1:
             return self.workspace[off: off + 4 * a.c].view(torch.float32).clone()
-        Hp, Wp = a.h + 2 * a.pad, a.w + 2 * a.pad
+        # pad 1: halo all around (interior at (1,1)); pad 2: zero tail (interior at (0,0)); both are (h+2) x (w+2) buffers
+        e, o = (2 if a.pad else 0), (1 if a.pad == 1 else 0)
+        Hp, Wp = a.h + e, a.w + e
         nbytes = a.n * Hp * Wp * a.cpitch * 2
         t = self.workspace[off: off + nbytes].view(torch.bfloat16).view(a.n, Hp, Wp, a.cpitch)
-        t = t[:, a.pad: a.pad + a.h, a.pad: a.pad + a.w, a.c_off: a.c_off + a.c]
+        t = t[:, o: o + a.h, o: o + a.w, a.c_off: a.c_off + a.c]
         return t.permute(0, 3, 1, 2).float().contiguous()
 
     def debug_tensor_padded(self, name: str) -> torch.Tensor:
@@ -110,6 +112,7 @@ class UNetPlan:
         kind = C.c_int()
         check(self.lib.mimo_unet_debug_view(self.handle, name.encode(), C.byref(a), C.byref(kind)), "mimo_unet_debug_view")
         off = a.ptr - self.workspace.data_ptr()
-        Hp, Wp = a.h + 2 * a.pad, a.w + 2 * a.pad
+        e = 2 if a.pad else 0
+        Hp, Wp = a.h + e, a.w + e
         t = self.workspace[off: off + a.n * Hp * Wp * a.cpitch * 2].view(torch.bfloat16).view(a.n, Hp, Wp, a.cpitch)
         return t[..., a.c_off: a.c_off + a.c].permute(0, 3, 1, 2).float().contiguous()

@@ -77,16 +77,25 @@ def test_weight_pack_and_conv_fprop(lib, N, Cin, Cout, H, W):
     assert rel_l2(q, (got * got).sum(dim=(0, 2, 3))) <= 1e-4
 
 
+def _dy_buffer(dy, dy_pad):
+    """dY in the dense (pad 0) or zero-tail (pad 2: buffer [N][H+2][W+2], data at the top-left) layout."""
+    N, Cout, H, W = dy.shape
+    e = 2 if dy_pad else 0
+    t = torch.zeros(N, H + e, W + e, p8(Cout), dtype=torch.bfloat16, device="cuda")
+    t[:, :H, :W, :Cout] = dy.permute(0, 2, 3, 1).to(torch.bfloat16)
+    return t, _lib.Act(t.data_ptr(), N, H, W, dy_pad, p8(Cout), 0, Cout)
+
+
+@pytest.mark.parametrize("dy_pad", [0, 2])
 @pytest.mark.parametrize("N,Cin,Cout,H,W", CONV_CASES)
-def test_conv_dgrad(lib, N, Cin, Cout, H, W):
+def test_conv_dgrad(lib, N, Cin, Cout, H, W, dy_pad):
     torch.manual_seed(2)
     dy = bf16r(torch.randn(N, Cout, H, W, device="cuda"))
     w = torch.randn(Cout, Cin, 3, 3, device="cuda") / math.sqrt(9 * Cin)
     wf, wd = _pack_weights(lib, w)
-    dyb = make_buffer(N, H, W, 0, p8(Cout), fill=0.0)
-    put_nchw(dyb, dy, 0)
+    dyb, dya = _dy_buffer(dy, dy_pad)
     dpad = make_buffer(N, H + 2, W + 2, 0, p8(Cin))
-    _lib.check(lib.mimo_conv3x3(act_of(dyb, 0, 0, Cout), 1, wd.data_ptr(), Cin, p8(Cout), dpad.data_ptr(), p8(Cin), None, None, None, 0,
+    _lib.check(lib.mimo_conv3x3(dya, 1, wd.data_ptr(), Cin, p8(Cout), dpad.data_ptr(), p8(Cin), None, None, None, 0,
                                 stream()), "dgrad")
     # gradient w.r.t. the PADDED input of a valid conv == full correlation with the flipped kernel
     ref_pad = F.conv_transpose2d(dy, bf16r(w))
@@ -105,24 +114,24 @@ def test_conv_dgrad(lib, N, Cin, Cout, H, W):
     assert rel_l2(get_nchw(g, 0, 0, Cin), xg.grad) <= 4e-3  # vs exact autograd: two bf16 roundings
 
 
+@pytest.mark.parametrize("dy_pad", [0, 2])
 @pytest.mark.parametrize("N,Cin,Cout,H,W", CONV_CASES)
-def test_conv_wgrad(lib, N, Cin, Cout, H, W):
+def test_conv_wgrad(lib, N, Cin, Cout, H, W, dy_pad):
     torch.manual_seed(3)
     x = bf16r(torch.randn(N, Cin, H, W, device="cuda"))
     dy = bf16r(torch.randn(N, Cout, H, W, device="cuda"))
     xb = make_buffer(N, H, W, 1, p8(Cin))
     put_nchw(xb, x, 1)
-    dyb = make_buffer(N, H, W, 0, p8(Cout), fill=0.0)
-    put_nchw(dyb, dy, 0)
+    dyb, dya = _dy_buffer(dy, dy_pad)
     scratch = torch.empty(9 * Cout * p8(Cin), device="cuda")
     grad = torch.full((Cout, Cin, 3, 3), float("nan"), device="cuda")
-    _lib.check(lib.mimo_conv3x3_wgrad(act_of(dyb, 0, 0, Cout), act_of(xb, 1, 0, Cin), scratch.data_ptr(), p8(Cin), grad.data_ptr(), 0,
+    _lib.check(lib.mimo_conv3x3_wgrad(dya, act_of(xb, 1, 0, Cin), scratch.data_ptr(), p8(Cin), grad.data_ptr(), 0,
                                       stream()), "wgrad")
     w = torch.zeros(Cout, Cin, 3, 3, device="cuda", requires_grad=True)
     O.conv3x3_reflect(x, w, None).backward(dy)
     assert rel_l2(grad, w.grad) <= TOL
     # accumulate mode adds onto the existing gradient
-    _lib.check(lib.mimo_conv3x3_wgrad(act_of(dyb, 0, 0, Cout), act_of(xb, 1, 0, Cin), scratch.data_ptr(), p8(Cin), grad.data_ptr(), 1,
+    _lib.check(lib.mimo_conv3x3_wgrad(dya, act_of(xb, 1, 0, Cin), scratch.data_ptr(), p8(Cin), grad.data_ptr(), 1,
                                       stream()), "wgrad")
     assert rel_l2(grad, 2 * w.grad) <= TOL
 
@@ -287,8 +296,9 @@ def test_grad_gather_fold_and_pool_bwd(lib, H, W):
 
 
 @pytest.mark.parametrize("training", [1, 0])
+@pytest.mark.parametrize("dy_pad", [0, 2])
 @pytest.mark.parametrize("C_,c_off,gcp", [(21, 0, 24), (42, 42, 88), (336, 0, 336)])
-def test_bn_relu_bwd(lib, training, C_, c_off, gcp):
+def test_bn_relu_bwd(lib, training, C_, c_off, gcp, dy_pad):
     torch.manual_seed(8)
     N, H, W = 3, 6, 7
     y = bf16r(torch.randn(N, C_, H, W, device="cuda") * 1.5 + 0.3)
@@ -311,13 +321,18 @@ def test_bn_relu_bwd(lib, training, C_, c_off, gcp):
     put_nchw(yb, y, 0)
     gb = make_buffer(N, H, W, 0, gcp, fill=0.0)
     put_nchw(gb, G, 0, c_off)
-    dyb = make_buffer(N, H, W, 0, p8(C_))
+    e = 2 if dy_pad else 0
+    dyb = torch.zeros(N, H + e, W + e, p8(C_), dtype=torch.bfloat16, device="cuda")
+    dyb[:, :H, :W] = float("nan")
+    dya = _lib.Act(dyb.data_ptr(), N, H, W, dy_pad, p8(C_), 0, C_)
     part = torch.empty(int(lib.mimo_bn_bwd_scratch_floats(C_)), device="cuda")
     s1s2 = torch.empty(2 * C_, device="cuda")
     dgamma, dbeta, dbias = (torch.full((C_,), float("nan"), device="cuda") for _ in range(3))
     _lib.check(lib.mimo_bn_relu_bwd(act_of(gb, 0, c_off, C_), yb.data_ptr(), p8(C_), scale.data_ptr(), shift.data_ptr(), mean.contiguous().data_ptr(),
                                     invstd.contiguous().data_ptr(), drop.data_ptr(), training, part.data_ptr(), s1s2.data_ptr(), dgamma.data_ptr(),
-                                    dbeta.data_ptr(), dbias.data_ptr(), 0, dyb.data_ptr(), p8(C_), stream()))
+                                    dbeta.data_ptr(), dbias.data_ptr(), 0, dya, stream()))
+    assert torch.all(dyb[:, H:] == 0) and torch.all(dyb[:, :, W:] == 0)  # the zero tail is never written
+    dyb = dyb[:, :H, :W].contiguous()
     assert rel_l2(get_nchw(dyb, 0, 0, C_), bf16r(yq.grad)) <= TOL
     assert rel_l2(dgamma, gq.grad) <= 1e-4 and rel_l2(dbeta, bq.grad) <= 1e-4
     if training:
