@@ -112,6 +112,43 @@ __device__ __forceinline__ void load8(const bf16* p, int nvalid, float out[8]) {
   }
 }
 
+// ---- register-level bf16 <-> fp32 helpers for the memory-bound kernels (they are instruction-issue bound, not HBM
+// bound, unless the per-element instruction count is kept to a handful) ----
+// 8 bf16 in a uint4 -> 8 floats: low half = x << 16, high half = x & 0xffff0000 (one ALU op per element)
+__device__ __forceinline__ void unpack8(const uint4& r, float f[8]) {
+  f[0] = __uint_as_float(r.x << 16); f[1] = __uint_as_float(r.x & 0xffff0000u);
+  f[2] = __uint_as_float(r.y << 16); f[3] = __uint_as_float(r.y & 0xffff0000u);
+  f[4] = __uint_as_float(r.z << 16); f[5] = __uint_as_float(r.z & 0xffff0000u);
+  f[6] = __uint_as_float(r.w << 16); f[7] = __uint_as_float(r.w & 0xffff0000u);
+}
+// two floats -> packed bf16x2 (round to nearest even), `lo` in the low half: one F2FP instruction
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ uint4 pack8(const float f[8]) {
+  return make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+}
+// word masks that zero the channels >= nvalid of an 8-channel group (loop-invariant per thread)
+__device__ __forceinline__ uint4 group_mask(int nvalid) {
+  uint32_t m[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) m[i] = (2 * i + 1 < nvalid) ? 0xffffffffu : ((2 * i < nvalid) ? 0x0000ffffu : 0u);
+  return make_uint4(m[0], m[1], m[2], m[3]);
+}
+__device__ __forceinline__ uint4 and4(const uint4& a, const uint4& m) { return make_uint4(a.x & m.x, a.y & m.y, a.z & m.z, a.w & m.w); }
+// 16-byte load of an 8-channel group when the view is 16-byte aligned (VEC), generic path otherwise; channels >= nvalid
+// come back as zero either way (the vector path may over-read pad channels inside the pixel's pitch and masks them)
+template <bool VEC>
+__device__ __forceinline__ uint4 load_group(const bf16* p, int nvalid, const uint4& mask) {
+  if (VEC) return and4(*reinterpret_cast<const uint4*>(p), mask);
+  bf16x8 t;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t.v[i] = (i < nvalid) ? p[i] : __float2bfloat16_rn(0.f);
+  return *reinterpret_cast<uint4*>(&t);
+}
+
 __device__ __forceinline__ void store8(bf16* p, int nvalid, const float in[8]) {
   if (nvalid >= 8 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
     bf16x8 t;

@@ -42,6 +42,51 @@ __device__ __forceinline__ void store_with_halo(const ActView& o, int n, int h, 
   }
 }
 
+// Packed variant for the hot kernels: `v` holds 8 bf16 (channels >= nvalid are zero). The halo logic only runs for
+// pixels on the two outermost rings (a rarely taken branch).
+// VEC: the address is 16-byte aligned. nvalid < 8 (last group of the view) is still written with one 16-byte store when
+// `tail_ok`: the view spans its whole buffer, so the channels past C are pad channels nobody else owns (they get zeros).
+template <bool VEC>
+__device__ __forceinline__ void store_group(bf16* p, int nvalid, const uint4& v, bool tail_ok = false) {
+  if (VEC && (nvalid == 8 || tail_ok)) {
+    *reinterpret_cast<uint4*>(p) = v;
+  } else {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < nvalid) reinterpret_cast<unsigned short*>(p)[i] = (unsigned short)(w[i >> 1] >> ((i & 1) * 16));
+  }
+}
+template <bool VEC>
+__device__ __forceinline__ void store_group_halo(const ActView& o, int n, int h, int w, int c, int nvalid, const uint4& v) {
+  const bool tail_ok = o.c_off == 0 && ((o.C + 7) & ~7) == o.cpitch;
+  store_group<VEC>(o.base + o.pix(n, h, w) + c, nvalid, v, tail_ok);
+  if (o.pad != 1) return;
+  if (h > 1 && h < o.H - 2 && w > 1 && w < o.W - 2) return;
+  const int hh = (h == 1) ? -1 : ((h == o.H - 2) ? o.H : -2);
+  const int ww = (w == 1) ? -1 : ((w == o.W - 2) ? o.W : -2);
+  const int hh2 = (o.H == 3 && h == 1) ? o.H : -2;
+  const int ww2 = (o.W == 3 && w == 1) ? o.W : -2;
+  const int hs[3] = {h, hh, hh2};
+  const int ws[3] = {w, ww, ww2};
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    if (hs[a] == -2) continue;
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      if (ws[b] == -2 || (a == 0 && b == 0)) continue;
+      store_group<VEC>(o.base + o.pix(n, hs[a], ws[b]) + c, nvalid, v, tail_ok);
+    }
+  }
+}
+__device__ __forceinline__ uint32_t bf162_max_nan(uint32_t a, uint32_t b) {
+  __nv_bfloat162 r = __hmax2_nan(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+__device__ __forceinline__ uint4 max4_nan(const uint4& a, const uint4& b) {
+  return make_uint4(bf162_max_nan(a.x, b.x), bf162_max_nan(a.y, b.y), bf162_max_nan(a.z, b.z), bf162_max_nan(a.w, b.w));
+}
+
 // ------------------------------------------------------------------------------------------------
 // input packing: fp32 NCHW (strided) -> bf16 NHWC with reflect halo; optional batch gather
 // (folds models/utils.py:38-41 index_select+stack of apply_input_transform into the load)
@@ -145,57 +190,63 @@ __global__ void bn_eval_affine_kernel(int C, const float* gamma, const float* be
 // BN apply + ReLU (+ Dropout2d keep-scale) (+ 2x2 max-pool) with reflect-halo writes.
 // One thread = one 2x2 pixel cell x 8 channels.
 // ------------------------------------------------------------------------------------------------
-// One block per row of 2x2 cells (two image rows), grid-stride over cell rows: 32-bit index math only.
+// Block = 256 threads = (cell lanes) x (8-channel groups): every thread keeps ONE channel group (scale/shift in
+// registers) and walks rows of 2x2 cells; 16-byte loads, packed bf16 stores, the 2x2 max is taken on the packed
+// (stored) values with the NaN-propagating bf16x2 max.
+template <bool VEC_O, bool VEC_P>
 __global__ void __launch_bounds__(256, 3)
 bn_relu_apply_kernel(const bf16* __restrict__ y, int ycp, const float* __restrict__ scale,
                      const float* __restrict__ shift, const float* __restrict__ drop /*[N][C] or null*/,
                      ActView o, ActView pool, int do_pool) {
   const int cells_h = (o.H + 1) >> 1, cells_w = (o.W + 1) >> 1;
   const int groups = (o.C + 7) >> 3;
+  const int lanes = blockDim.x / groups;
+  const int g = threadIdx.x % groups, pl = threadIdx.x / groups;
+  if (pl >= lanes) return;
+  const int c = g * 8, nv = min(8, o.C - c);
+  const uint4 mask = group_mask(nv);
+  float sc[8], sh[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { sc[k] = (k < nv) ? scale[c + k] : 0.f; sh[k] = (k < nv) ? shift[c + k] : 0.f; }
   const int cell_rows = o.N * cells_h;
-  const int items = cells_w * groups;
   for (int cr = blockIdx.x; cr < cell_rows; cr += gridDim.x) {
     const int n = cr / cells_h, chh = cr - n * cells_h;
     const int h0 = chh * 2;
     const bool row1 = h0 + 1 < o.H;
-    const bf16* y0 = y + (size_t)(n * o.H + h0) * o.W * ycp;
+    const bf16* y0 = y + (size_t)(n * o.H + h0) * o.W * ycp + c;
     const bf16* y1 = y0 + (size_t)o.W * ycp;
-    for (int i = threadIdx.x; i < items; i += blockDim.x) {
-      const int cw = i / groups, g = i - cw * groups;
-      const int c = g * 8, nv = min(8, o.C - c);
+    float dr[8];
+    if (drop) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) dr[k] = k < nv ? drop[(size_t)n * o.C + c + k] : 0.f;
+    }
+    for (int cw = pl; cw < cells_w; cw += lanes) {
       const int w0 = cw * 2;
       const bool col1 = w0 + 1 < o.W;
       // issue all loads of the cell first (y is dense with ycp % 8 == 0: every 8-channel group is one aligned 16-byte load)
-      bf16x8 raw[4];
-      raw[0] = *reinterpret_cast<const bf16x8*>(y0 + (size_t)w0 * ycp + c);
-      if (col1) raw[1] = *reinterpret_cast<const bf16x8*>(y0 + (size_t)(w0 + 1) * ycp + c);
-      if (row1) raw[2] = *reinterpret_cast<const bf16x8*>(y1 + (size_t)w0 * ycp + c);
-      if (row1 && col1) raw[3] = *reinterpret_cast<const bf16x8*>(y1 + (size_t)(w0 + 1) * ycp + c);
-      float sc[8], sh[8], dr[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        sc[k] = (k < nv) ? scale[c + k] : 0.f;
-        sh[k] = (k < nv) ? shift[c + k] : 0.f;
-        dr[k] = (drop && k < nv) ? drop[(size_t)n * o.C + c + k] : 1.f;
-      }
-      float mx[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) mx[k] = -INFINITY;
+      uint4 raw[4];
+      raw[0] = *reinterpret_cast<const uint4*>(y0 + (size_t)w0 * ycp);
+      if (col1) raw[1] = *reinterpret_cast<const uint4*>(y0 + (size_t)(w0 + 1) * ycp);
+      if (row1) raw[2] = *reinterpret_cast<const uint4*>(y1 + (size_t)w0 * ycp);
+      if (row1 && col1) raw[3] = *reinterpret_cast<const uint4*>(y1 + (size_t)(w0 + 1) * ycp);
+      uint4 mx = make_uint4(0, 0, 0, 0);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int dy = j >> 1, dx = j & 1;
         if ((dy && !row1) || (dx && !col1)) continue;
         float v[8];
+        unpack8(raw[j], v);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          // the activation is STORED in bf16: pool over the stored value so indices/values agree with it
-          const float a = __bfloat162float(__float2bfloat16_rn(fmaxf(fmaf(__bfloat162float(raw[j].v[k]), sc[k], sh[k]), 0.f) * dr[k]));
-          v[k] = a;
-          mx[k] = (a > mx[k] || a != a) ? a : mx[k];
+          v[k] = fmaxf(fmaf(v[k], sc[k], sh[k]), 0.f);
+          if (drop) v[k] *= dr[k];
         }
-        store_with_halo(o, n, h0 + dy, w0 + dx, c, nv, v);
+        // the activation is STORED in bf16: pool over the stored value so indices/values agree with it
+        const uint4 pk = and4(pack8(v), mask);
+        mx = (j == 0) ? pk : max4_nan(mx, pk);
+        store_group_halo<VEC_O>(o, n, h0 + dy, w0 + dx, c, nv, pk);
       }
-      if (do_pool && row1 && col1 && chh < pool.H && cw < pool.W) store_with_halo(pool, n, chh, cw, c, nv, mx);
+      if (do_pool && row1 && col1 && chh < pool.H && cw < pool.W) store_group_halo<VEC_P>(pool, n, chh, cw, c, nv, mx);
     }
   }
 }
@@ -351,58 +402,124 @@ __device__ __forceinline__ void fold_read(const ActView& dp /*H+2,W+2 unpadded*/
   }
 }
 
-__global__ void grad_gather_kernel(ActView dpad, int has_dpad, ActView gpool, ActView act, int has_pool, ActView gout,
-                                   int accumulate) {
+// fold of the padded-domain gradient at interior pixel (h,w): dpad(h+1,w+1) plus, on the second ring, the halo cells that
+// mirror it. `center` has already been loaded.
+template <bool VEC>
+__device__ __forceinline__ void fold_border(const ActView& dp, int n, int h, int w, int H, int W, int c, int nv, const uint4& mask,
+                                            float acc[8]) {
+  if (h != 1 && h != H - 2 && w != 1 && w != W - 2) return;
+  const int hs[3] = {h + 1, (h == 1) ? 0 : -1, (h == H - 2) ? H + 1 : -1};
+  const int ws[3] = {w + 1, (w == 1) ? 0 : -1, (w == W - 2) ? W + 1 : -1};
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    if (hs[a] < 0) continue;
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      if (ws[b] < 0 || (a == 0 && b == 0)) continue;
+      float v[8];
+      unpack8(load_group<VEC>(dp.base + dp.pix(n, hs[a], ws[b]) + c, nv, mask), v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += v[k];
+    }
+  }
+}
+
+// G = fold(dpad) (+ G when accumulating). Block = (pixel lanes) x (8-channel groups), one image row per block step.
+template <bool VEC_IN, bool VEC_OUT>
+__global__ void __launch_bounds__(256, 4)
+grad_fold_kernel(ActView dpad, ActView gout, int accumulate) {
   const int groups = (gout.C + 7) >> 3;
-  const long long total = (long long)gout.N * gout.H * gout.W * groups;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(i % groups);
-    long long r = i / groups;
-    const int w = (int)(r % gout.W); r /= gout.W;
-    const int h = (int)(r % gout.H);
-    const int n = (int)(r / gout.H);
-    const int c = g * 8, nv = min(8, gout.C - c);
-    float acc[8];
+  const int lanes = blockDim.x / groups;
+  const int g = threadIdx.x % groups, pl = threadIdx.x / groups;
+  if (pl >= lanes) return;
+  const int c = g * 8, nv = min(8, gout.C - c);
+  const uint4 mask = group_mask(nv);
+  const bool tail_ok = gout.c_off == 0 && ((gout.C + 7) & ~7) == gout.cpitch;
+  const int rows = gout.N * gout.H;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int n = row / gout.H, h = row - n * gout.H;
+    const bf16* src = dpad.base + dpad.pix(n, h + 1, 1) + c;
+    bf16* dst = gout.base + gout.pix(n, h, 0) + c;
+    for (int w = pl; w < gout.W; w += lanes) {
+      float acc[8];
+      unpack8(load_group<VEC_IN>(src + (size_t)w * dpad.cpitch, nv, mask), acc);
+      fold_border<VEC_IN>(dpad, n, h, w, gout.H, gout.W, c, nv, mask, acc);
+      if (accumulate) {
+        float old[8];
+        unpack8(load_group<VEC_OUT>(dst + (size_t)w * gout.cpitch, nv, mask), old);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-    if (has_dpad) fold_read(dpad, n, h, w, gout.H, gout.W, c, nv, acc);
-    if (has_pool) {
-      const int ph = h >> 1, pw = w >> 1;
-      if (ph < gpool.H && pw < gpool.W) {
-        float gp[8], mine[8];
-        load8(gpool.base + gpool.pix(n, ph, pw) + c, nv, gp);
-        load8(act.base + act.pix(n, h, w) + c, nv, mine);
-        bool win[8];
+        for (int k = 0; k < 8; ++k) acc[k] += old[k];
+      }
+      store_group<VEC_OUT>(dst + (size_t)w * gout.cpitch, nv, pack8(acc), tail_ok);
+    }
+  }
+}
+
+// G = [fold(dpad)] + max-pool backward of gpool through act, one thread per 2x2 cell x 8 channels: the winner of
+// every window is found once (first maximum in row-major window order, like nn.MaxPool2d) instead of once per pixel.
+template <bool VEC_D, bool VEC_A, bool VEC_P, bool VEC_OUT>
+__global__ void __launch_bounds__(256, 3)
+grad_gather_pool_kernel(ActView dpad, int has_dpad, ActView gpool, ActView act, ActView gout, int accumulate) {
+  const int cells_h = (gout.H + 1) >> 1, cells_w = (gout.W + 1) >> 1;
+  const int groups = (gout.C + 7) >> 3;
+  const int lanes = blockDim.x / groups;
+  const int g = threadIdx.x % groups, pl = threadIdx.x / groups;
+  if (pl >= lanes) return;
+  const int c = g * 8, nv = min(8, gout.C - c);
+  const uint4 mask = group_mask(nv);
+  const bool tail_ok = gout.c_off == 0 && ((gout.C + 7) & ~7) == gout.cpitch;
+  const int cell_rows = gout.N * cells_h;
+  for (int cr = blockIdx.x; cr < cell_rows; cr += gridDim.x) {
+    const int n = cr / cells_h, chh = cr - n * cells_h;
+    const int h0 = chh * 2;
+    const bool row1 = h0 + 1 < gout.H;
+    for (int cw = pl; cw < cells_w; cw += lanes) {
+      const int w0 = cw * 2;
+      const bool col1 = w0 + 1 < gout.W;
+      const bool pooled = row1 && col1 && chh < gpool.H && cw < gpool.W;
+      float out[4][8];
+      // fold part
 #pragma unroll
-        for (int k = 0; k < 8; ++k) win[k] = true;
-        const int my_rank = (h & 1) * 2 + (w & 1);
+      for (int j = 0; j < 4; ++j) {
+        const int dy = j >> 1, dx = j & 1;
 #pragma unroll
-        for (int dy = 0; dy < 2; ++dy)
+        for (int k = 0; k < 8; ++k) out[j][k] = 0.f;
+        if ((dy && !row1) || (dx && !col1)) continue;
+        if (has_dpad) {
+          unpack8(load_group<VEC_D>(dpad.base + dpad.pix(n, h0 + dy + 1, w0 + dx + 1) + c, nv, mask), out[j]);
+          fold_border<VEC_D>(dpad, n, h0 + dy, w0 + dx, gout.H, gout.W, c, nv, mask, out[j]);
+        }
+      }
+      if (pooled) {
+        float gp[8], a[4][8];
+        unpack8(load_group<VEC_P>(gpool.base + gpool.pix(n, chh, cw) + c, nv, mask), gp);
 #pragma unroll
-          for (int dx = 0; dx < 2; ++dx) {
-            const int rank = dy * 2 + dx;
-            if (rank == my_rank) continue;
-            float o[8];
-            load8(act.base + act.pix(n, ph * 2 + dy, pw * 2 + dx) + c, nv, o);
+        for (int j = 0; j < 4; ++j) unpack8(load_group<VEC_A>(act.base + act.pix(n, h0 + (j >> 1), w0 + (j & 1)) + c, nv, mask), a[j]);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              // the other element beats me if it is larger, or equal and earlier in window order
-              if (o[k] > mine[k] || (o[k] == mine[k] && rank < my_rank)) win[k] = false;
-            }
-          }
+        for (int k = 0; k < 8; ++k) {
+          int win = 0;
+          float m = a[0][k];
+          if (a[1][k] > m) { m = a[1][k]; win = 1; }
+          if (a[2][k] > m) { m = a[2][k]; win = 2; }
+          if (a[3][k] > m) { m = a[3][k]; win = 3; }
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          if (win[k]) acc[k] += gp[k];
+          for (int j = 0; j < 4; ++j) out[j][k] += (win == j) ? gp[k] : 0.f;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int dy = j >> 1, dx = j & 1;
+        if ((dy && !row1) || (dx && !col1)) continue;
+        bf16* dst = gout.base + gout.pix(n, h0 + dy, w0 + dx) + c;
+        if (accumulate) {
+          float old[8];
+          unpack8(load_group<VEC_OUT>(dst, nv, mask), old);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) out[j][k] += old[k];
+        }
+        store_group<VEC_OUT>(dst, nv, pack8(out[j]), tail_ok);
       }
     }
-    bf16* dst = gout.base + gout.pix(n, h, w) + c;
-    if (accumulate) {
-      float old[8];
-      load8(dst, nv, old);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) acc[k] += old[k];
-    }
-    store8(dst, nv, acc);
   }
 }
 
@@ -414,9 +531,11 @@ __global__ void grad_gather_kernel(ActView dpad, int has_dpad, ActView gpool, Ac
 //   pass 2 (apply) : dy = scale * (dz - (s1 + x_hat * s2) / count)     [training]
 //                    dy = scale * dz                                     [eval: running stats are constants]
 // ------------------------------------------------------------------------------------------------
-// Block = 256 threads = (pixel lanes) x (8-channel groups); a block walks whole image rows (row = n*H + h), so
-// there is no per-element 64-bit index arithmetic; per-thread register accumulators are combined in shared memory
-// in a fixed order (deterministic), one partial row per block.
+// Block = 256 threads = (pixel lanes) x (8-channel groups), every thread keeps ONE channel group for the whole kernel
+// (per-channel coefficients live in registers) and walks whole image rows (row = n*H + h): no per-element 64-bit index
+// arithmetic, 16-byte loads, ~9 instructions per element. Per-thread accumulators are combined in shared memory in a
+// fixed order (deterministic), one partial row per block.
+template <bool VEC>
 __global__ void __launch_bounds__(256, 3)
 bn_bwd_reduce_kernel(ActView G, const bf16* __restrict__ y, int ycp, const float* __restrict__ scale,
                      const float* __restrict__ shift, const float* __restrict__ drop, int C,
@@ -431,6 +550,7 @@ bn_bwd_reduce_kernel(ActView G, const bf16* __restrict__ y, int ycp, const float
 #pragma unroll
   for (int k = 0; k < 8; ++k) { a1[k] = 0.f; a2[k] = 0.f; }
   if (pl < pix_lanes) {
+    const uint4 mask = group_mask(nv);
     float sc[8], sf[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) { sc[k] = k < nv ? scale[c + k] : 0.f; sf[k] = k < nv ? shift[c + k] : 0.f; }
@@ -439,33 +559,43 @@ bn_bwd_reduce_kernel(ActView G, const bf16* __restrict__ y, int ycp, const float
       const bf16* gp = G.base + G.pix(n, h, 0) + c;
       const bf16* yp = y + (size_t)row * G.W * ycp + c;
       float dr[8];
+      if (drop) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) dr[k] = (drop && k < nv) ? drop[(size_t)n * C + c + k] : 1.f;
+        for (int k = 0; k < 8; ++k) dr[k] = k < nv ? drop[(size_t)n * C + c + k] : 0.f;
+      }
       for (int w = pl; w < G.W; w += 2 * pix_lanes) {
         const int w2 = w + pix_lanes;
-        float gv[8], yv[8], gv2[8], yv2[8];
-        load8(gp + (size_t)w * G.cpitch, nv, gv);
-        load8(yp + (size_t)w * ycp, nv, yv);
         const bool has2 = w2 < G.W;
+        // issue all loads first
+        const uint4 gr = load_group<VEC>(gp + (size_t)w * G.cpitch, nv, mask);
+        const uint4 yr = load_group<true>(yp + (size_t)w * ycp, nv, mask);
+        uint4 gr2 = make_uint4(0, 0, 0, 0), yr2 = make_uint4(0, 0, 0, 0);
         if (has2) {
-          load8(gp + (size_t)w2 * G.cpitch, nv, gv2);
-          load8(yp + (size_t)w2 * ycp, nv, yv2);
+          gr2 = load_group<VEC>(gp + (size_t)w2 * G.cpitch, nv, mask);
+          yr2 = load_group<true>(yp + (size_t)w2 * ycp, nv, mask);
         }
+        float gv[8], yv[8];
+        unpack8(gr, gv);
+        unpack8(yr, yv);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const float z = fmaf(yv[k], sc[k], sf[k]);
-          const float dz = (z > 0.f) ? gv[k] * dr[k] : 0.f;
+          float gg = gv[k];
+          if (drop) gg *= dr[k];
+          const float dz = (z > 0.f) ? gg : 0.f;
           a1[k] += dz;
           a2[k] = fmaf(dz, yv[k], a2[k]);
         }
-        if (has2) {
+        unpack8(gr2, gv);   // all-zero when !has2: contributes nothing
+        unpack8(yr2, yv);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const float z = fmaf(yv2[k], sc[k], sf[k]);
-            const float dz = (z > 0.f) ? gv2[k] * dr[k] : 0.f;
-            a1[k] += dz;
-            a2[k] = fmaf(dz, yv2[k], a2[k]);
-          }
+        for (int k = 0; k < 8; ++k) {
+          const float z = fmaf(yv[k], sc[k], sf[k]);
+          float gg = gv[k];
+          if (drop) gg *= dr[k];
+          const float dz = (z > 0.f) ? gg : 0.f;
+          a1[k] += dz;
+          a2[k] = fmaf(dz, yv[k], a2[k]);
         }
       }
     }
@@ -510,46 +640,61 @@ bn_bwd_finalize_kernel(const float* __restrict__ part, int nparts, int C, float*
   if (dbias) dbias[c] = (accumulate ? dbias[c] : 0.f) + (training ? 0.f : (float)a * scale[c] * grad_scale);
 }
 
-// One block per image row (grid-stride over rows); threads = (pixel, 8-channel group), groups fastest.
-__global__ void __launch_bounds__(256)
+// dy = scale * (dz - (s1 + x_hat * s2) / count) rewritten as  dy = scale * dz + A * y + B  with per-channel
+//   A = -scale * s2 * invstd / count,  B = -scale * (s1 - s2 * invstd * mean) / count   (A = B = 0 in eval mode),
+// so the per-element work is 3 FMAs + one select. Same thread layout as the reduce kernel.
+template <bool VEC>
+__global__ void __launch_bounds__(256, 4)
 bn_bwd_apply_kernel(ActView G, const bf16* __restrict__ y, int ycp, const float* __restrict__ scale,
                     const float* __restrict__ shift, const float* __restrict__ mean,
                     const float* __restrict__ invstd, const float* __restrict__ drop,
                     const float* __restrict__ s1s2, int C, float inv_count, int training, ActView dy) {
   const int groups = (C + 7) >> 3;
+  const int pix_lanes = blockDim.x / groups;
+  const int g = threadIdx.x % groups, pl = threadIdx.x / groups;
+  if (pl >= pix_lanes) return;
   const int rows = G.N * G.H;
-  const int items = G.W * groups;
+  const int c = g * 8, nv = min(8, C - c);
+  const uint4 mask = group_mask(nv);
+  float sc[8], sf[8], ca[8], cb[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    sc[k] = k < nv ? scale[c + k] : 0.f;
+    sf[k] = k < nv ? shift[c + k] : 0.f;
+    ca[k] = 0.f; cb[k] = 0.f;
+    if (training && k < nv) {
+      const float is = invstd[c + k], s1 = s1s2[c + k], s2 = s1s2[C + c + k];
+      ca[k] = -sc[k] * s2 * is * inv_count;
+      cb[k] = -sc[k] * (s1 - s2 * is * mean[c + k]) * inv_count;
+    }
+  }
+  const bool vec_store = c + 8 <= dy.cpitch;  // pad channels of dy are written as zeros (the tensor-core kernels read them)
   for (int row = blockIdx.x; row < rows; row += gridDim.x) {
     const int n = row / G.H, h = row - n * G.H;
-    const bf16* gp = G.base + G.pix(n, h, 0);
-    const bf16* yp = y + (size_t)row * G.W * ycp;
-    bf16* dp = dy.base + dy.pix(n, h, 0);
-    for (int i = threadIdx.x; i < items; i += blockDim.x) {
-      const int w = i / groups, g = i - w * groups;
-      const int c = g * 8, nv = min(8, C - c);
+    const bf16* gp = G.base + G.pix(n, h, 0) + c;
+    const bf16* yp = y + (size_t)row * G.W * ycp + c;
+    bf16* dp = dy.base + dy.pix(n, h, 0) + c;
+    float dr[8];
+    if (drop) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) dr[k] = k < nv ? drop[(size_t)n * C + c + k] : 0.f;
+    }
+    for (int w = pl; w < G.W; w += pix_lanes) {
+      const uint4 gr = load_group<VEC>(gp + (size_t)w * G.cpitch, nv, mask);
+      const uint4 yr = load_group<true>(yp + (size_t)w * ycp, nv, mask);
       float gv[8], yv[8], out[8];
-      load8(gp + (size_t)w * G.cpitch + c, nv, gv);
-      load8(yp + (size_t)w * ycp + c, nv, yv);
+      unpack8(gr, gv);
+      unpack8(yr, yv);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        if (k < nv) {
-          const float sc = scale[c + k];
-          const float z = fmaf(yv[k], sc, shift[c + k]);
-          const float d = drop ? drop[(size_t)n * C + c + k] : 1.f;
-          const float dz = (z > 0.f) ? gv[k] * d : 0.f;
-          if (training) {
-            const float xh = (yv[k] - mean[c + k]) * invstd[c + k];
-            out[k] = sc * (dz - (s1s2[c + k] + xh * s1s2[C + c + k]) * inv_count);
-          } else {
-            out[k] = sc * dz;
-          }
-        } else {
-          out[k] = 0.f;
-        }
+        const float z = fmaf(yv[k], sc[k], sf[k]);
+        float gg = gv[k];
+        if (drop) gg *= dr[k];
+        const float dz = (z > 0.f) ? gg : 0.f;
+        out[k] = fmaf(sc[k], dz, fmaf(ca[k], yv[k], cb[k]));
       }
-      // pad channels of dy are written as zeros so the tensor-core kernels never see garbage
-      const int nstore = min(8, dy.cpitch - c);
-      store8(dp + (size_t)w * dy.cpitch + c, nstore, out);
+      if (vec_store) *reinterpret_cast<uint4*>(dp + (size_t)w * dy.cpitch) = pack8(out);
+      else store8(dp + (size_t)w * dy.cpitch, min(8, dy.cpitch - c), out);
     }
   }
 }
@@ -631,6 +776,15 @@ __global__ void unpack_nchw_kernel(ActView in, float* __restrict__ out) {
 }  // namespace
 
 // ===================================== launchers =====================================
+// true when every 8-channel group of the view starts 16-byte aligned and may be over-READ up to 8 channels
+static bool view_vec_ok(const ActView& v) {
+  return ((uintptr_t)v.base % 16) == 0 && v.cpitch % 8 == 0 && v.c_off % 8 == 0 && v.c_off + round_up(v.C, 8) <= v.cpitch;
+}
+// true when full 8-channel groups of the view can be written with 16-byte stores (partial groups stay scalar)
+static bool view_store_vec_ok(const ActView& v) {
+  return ((uintptr_t)v.base % 16) == 0 && v.cpitch % 8 == 0 && v.c_off % 8 == 0;
+}
+
 int pack_input_launch(const float* x, long long sb, long long sc, const long long* gather, const ActView& o, cudaStream_t st) {
   MIMO_CHECK(o.H >= 2 && o.W >= 2, MIMO_ERR_ARG, "pack_input: H,W must be >= 2");
   const long long total = (long long)o.N * (o.H + 2 * o.pad) * (o.W + 2 * o.pad);
@@ -667,9 +821,15 @@ int bn_relu_apply_launch(const bf16* y, int ycp, const float* scale, const float
   MIMO_CHECK(o.H >= 2 && o.W >= 2, MIMO_ERR_ARG, "bn_relu_apply: H,W must be >= 2");
   ActView pv = pool ? *pool : o;
   if (pool) MIMO_CHECK(pool->H == o.H / 2 && pool->W == o.W / 2 && pool->C == o.C && pool->N == o.N, MIMO_ERR_ARG, "bn_relu_apply: pool view shape mismatch");
+  MIMO_CHECK(ycp % 8 == 0 && ycp >= round_up(o.C, 8) && ((uintptr_t)y % 16) == 0, MIMO_ERR_ALIGN, "bn_relu_apply: y must be 16-byte aligned with a pitch >= round_up(C, 8)");
+  MIMO_CHECK((o.C + 7) / 8 <= kBlock, MIMO_ERR_ARG, "bn_relu_apply: too many channels (%d)", o.C);
   const int cell_rows = o.N * ((o.H + 1) / 2);
-  const int grid = cell_rows < 32 * num_sms() ? cell_rows : 32 * num_sms();
-  bn_relu_apply_kernel<<<grid, kBlock, 0, st>>>(y, ycp, scale, shift, drop, o, pv, pool ? 1 : 0);
+  const int grid = cell_rows < 8 * num_sms() ? cell_rows : 8 * num_sms();
+  const bool vo = view_store_vec_ok(o), vp = view_store_vec_ok(pv);
+  if (vo && vp) bn_relu_apply_kernel<true, true><<<grid, kBlock, 0, st>>>(y, ycp, scale, shift, drop, o, pv, pool ? 1 : 0);
+  else if (vo) bn_relu_apply_kernel<true, false><<<grid, kBlock, 0, st>>>(y, ycp, scale, shift, drop, o, pv, pool ? 1 : 0);
+  else if (vp) bn_relu_apply_kernel<false, true><<<grid, kBlock, 0, st>>>(y, ycp, scale, shift, drop, o, pv, pool ? 1 : 0);
+  else bn_relu_apply_kernel<false, false><<<grid, kBlock, 0, st>>>(y, ycp, scale, shift, drop, o, pv, pool ? 1 : 0);
   MIMO_LAUNCH_CHECK();
   return MIMO_OK;
 }
@@ -707,9 +867,23 @@ int grad_gather_launch(const ActView* dpad, const ActView* gpool, const ActView*
   MIMO_CHECK(gout.pad == 0, MIMO_ERR_ARG, "grad_gather: output must be unpadded");
   if (dpad) MIMO_CHECK(dpad->pad == 0 && dpad->H == gout.H + 2 && dpad->W == gout.W + 2 && dpad->C == gout.C, MIMO_ERR_ARG, "grad_gather: dpad shape mismatch");
   if (gpool) MIMO_CHECK(act && gpool->pad == 0 && gpool->H == gout.H / 2 && gpool->W == gout.W / 2 && gpool->C == gout.C && act->C == gout.C && act->H == gout.H, MIMO_ERR_ARG, "grad_gather: pool shape mismatch");
-  const long long total = (long long)gout.N * gout.H * gout.W * ((gout.C + 7) / 8);
-  grad_gather_kernel<<<grid_for(total), kBlock, 0, st>>>(dpad ? *dpad : gout, dpad ? 1 : 0, gpool ? *gpool : gout, act ? *act : gout,
-                                                        gpool ? 1 : 0, gout, accumulate);
+  MIMO_CHECK((gout.C + 7) / 8 <= kBlock, MIMO_ERR_ARG, "grad_gather: too many channels (%d)", gout.C);
+  const bool vo = view_vec_ok(gout);
+  if (!gpool) {
+    const bool vi = view_vec_ok(*dpad);
+    const int rows = gout.N * gout.H;
+    const int grid = rows < 8 * num_sms() ? rows : 8 * num_sms();
+    if (vi && vo) grad_fold_kernel<true, true><<<grid, kBlock, 0, st>>>(*dpad, gout, accumulate);
+    else if (vi) grad_fold_kernel<true, false><<<grid, kBlock, 0, st>>>(*dpad, gout, accumulate);
+    else if (vo) grad_fold_kernel<false, true><<<grid, kBlock, 0, st>>>(*dpad, gout, accumulate);
+    else grad_fold_kernel<false, false><<<grid, kBlock, 0, st>>>(*dpad, gout, accumulate);
+  } else {
+    const bool vec = vo && (!dpad || view_vec_ok(*dpad)) && view_vec_ok(*gpool) && view_vec_ok(*act);
+    const int cell_rows = gout.N * ((gout.H + 1) / 2);
+    const int grid = cell_rows < 8 * num_sms() ? cell_rows : 8 * num_sms();
+    if (vec) grad_gather_pool_kernel<true, true, true, true><<<grid, kBlock, 0, st>>>(dpad ? *dpad : gout, dpad ? 1 : 0, *gpool, *act, gout, accumulate);
+    else grad_gather_pool_kernel<false, false, false, false><<<grid, kBlock, 0, st>>>(dpad ? *dpad : gout, dpad ? 1 : 0, *gpool, *act, gout, accumulate);
+  }
   MIMO_LAUNCH_CHECK();
   return MIMO_OK;
 }
@@ -721,21 +895,26 @@ int bn_bwd_launch(const ActView& G, const bf16* y, int ycp, const float* scale, 
                   float* dbias, float grad_scale, int accumulate, const ActView& dy, cudaStream_t st) {
   const int C = G.C;
   MIMO_CHECK(G.pad == 0, MIMO_ERR_ARG, "bn_bwd: G must be unpadded");
-  MIMO_CHECK(dy.pad != 1 && dy.c_off == 0 && dy.N == G.N && dy.H == G.H && dy.W == G.W && dy.cpitch >= C, MIMO_ERR_ARG,
-             "bn_bwd: dy must be a whole dense or zero-tail buffer of the same shape");
+  MIMO_CHECK(dy.pad != 1 && dy.c_off == 0 && dy.N == G.N && dy.H == G.H && dy.W == G.W && dy.cpitch >= C && dy.cpitch % 8 == 0 &&
+                 ((uintptr_t)dy.base % 16) == 0,
+             MIMO_ERR_ARG, "bn_bwd: dy must be a whole dense or zero-tail buffer of the same shape");
+  MIMO_CHECK(ycp % 8 == 0 && ycp >= round_up(C, 8) && ((uintptr_t)y % 16) == 0, MIMO_ERR_ALIGN, "bn_bwd: y must be 16-byte aligned with a pitch >= round_up(C, 8)");
   const int groups = (C + 7) / 8;
   MIMO_CHECK(groups <= kBlock, MIMO_ERR_ARG, "bn_bwd: too many channels (%d)", C);
   const int rows = G.N * G.H;
   const int nparts = rows < bn_bwd_parts(C) ? rows : bn_bwd_parts(C);
   const int pix_lanes = kBlock / groups;
   const size_t sh_bytes = (size_t)pix_lanes * groups * 16 * sizeof(float);
-  bn_bwd_reduce_kernel<<<nparts, kBlock, sh_bytes, st>>>(G, y, ycp, scale, shift, drop, C, part);
+  const bool vec = view_vec_ok(G);
+  if (vec) bn_bwd_reduce_kernel<true><<<nparts, kBlock, sh_bytes, st>>>(G, y, ycp, scale, shift, drop, C, part);
+  else bn_bwd_reduce_kernel<false><<<nparts, kBlock, sh_bytes, st>>>(G, y, ycp, scale, shift, drop, C, part);
   MIMO_LAUNCH_CHECK();
   bn_bwd_finalize_kernel<<<ceil_div(C, 8), 256, 0, st>>>(part, nparts, C, s1s2, dgamma, dbeta, dbias, scale, mean, invstd, training, grad_scale, accumulate);
   MIMO_LAUNCH_CHECK();
   const long long npix = (long long)G.N * G.H * G.W;
-  const int grid = rows < 32 * num_sms() ? rows : 32 * num_sms();
-  bn_bwd_apply_kernel<<<grid, kBlock, 0, st>>>(G, y, ycp, scale, shift, mean, invstd, drop, s1s2, C, 1.f / (float)npix, training, dy);
+  const int grid = rows < 8 * num_sms() ? rows : 8 * num_sms();
+  if (vec) bn_bwd_apply_kernel<true><<<grid, kBlock, 0, st>>>(G, y, ycp, scale, shift, mean, invstd, drop, s1s2, C, 1.f / (float)npix, training, dy);
+  else bn_bwd_apply_kernel<false><<<grid, kBlock, 0, st>>>(G, y, ycp, scale, shift, mean, invstd, drop, s1s2, C, 1.f / (float)npix, training, dy);
   MIMO_LAUNCH_CHECK();
   return MIMO_OK;
 }
