@@ -182,14 +182,17 @@ def run_gpu_arm(args):
     # L2 hygiene: the step touches several GB of activations (>> 126 MB L2), so the L2 is flushed by the step itself
     loss_host = torch.zeros(1).pin_memory()
 
+    # data parallel: the flat gradient buffer is all-reduced (mean) in 4 buckets, each launched on a side stream as soon
+    # as the executor's backward has finalised it (mimo_unet_set_backward_events), overlapped with the rest of backward
+    sync = model.model.runtime().enable_overlapped_allreduce() if world > 1 else None
+
     def step(image, label):
         out = model.training_step({"image": image, "label": label}, 0)
         loss = out["loss"]
         opt.zero_grad(set_to_none=True)
         loss.backward()
-        if world > 1:
-            rt = model.model._runtime
-            dist.all_reduce(rt.flat_grads, op=dist.ReduceOp.AVG)
+        if sync is not None:
+            sync.wait()
         opt.step()
         return loss
 

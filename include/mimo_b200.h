@@ -190,6 +190,13 @@ int mimo_unet_forward(mimo_unet_plan_t* plan, const float* x, const long long* g
  * not supported together with gather). Parameter gradients are WRITTEN (accumulate==0) or ADDED to grads[]. */
 int mimo_unet_backward(mimo_unet_plan_t* plan, const float* dout, const float* grad_scale, float* dx, int accumulate,
                        void* stream);
+/* Overlap hook for the data-parallel gradient all-reduce: events[4] are caller-owned cudaEvent_t (or NULL
+ * to disable). mimo_unet_backward records events[k] on its stream as soon as the parameter gradients of stage k are
+ * final: 0 = decoders + heads, 1 = core up path, 2 = core down path, 3 = encoders (end of backward). The state entries
+ * of stage k are the contiguous range [mimo_unet_backward_stage_first_state(plan, k), first state of stage k-1) (stage 0
+ * runs to the end), i.e. stages are contiguous slices of a flat gradient buffer laid out in state order. */
+int mimo_unet_set_backward_events(mimo_unet_plan_t* plan, void* const* events);
+int mimo_unet_backward_stage_first_state(const mimo_unet_plan_t* plan, int stage);
 /* test hook: geometry of a named intermediate ("<node>.<buf>", e.g. "core.down2.c1.y") inside the workspace.
  * kind: 0 = bf16 activation view, 1 = fp32 vector of view->c floats. */
 int mimo_unet_debug_view(const mimo_unet_plan_t* plan, const char* name, mimo_act_t* view, int* kind);

@@ -98,12 +98,16 @@ class MimoUNet(nn.Module):
                 [self.core.down2.conv, self.core.down3.conv, self.core.down4.conv, self.core.up1.conv, self.core.up2.conv,
                  self.core.up3.conv] + [self.decoder.up4s[i].conv for i in range(S)])
 
+    def runtime(self):
+        """The CUDA executor glue of this module (created on first use)."""
+        from mimo_unet_b200.network import NetworkRuntime
+        if self._runtime is None:
+            self._runtime = NetworkRuntime(self)
+        return self._runtime
+
     def forward(self, x: torch.Tensor, gather: torch.Tensor = None):
         """x: [B, S, C_in, H, W] -> [B, S, C_out, H, W].
 
         gather (optional, int64 [S, B]): x is then the un-shuffled batch [B, C_in, H, W] and subnetwork s reads
         x[gather[s]] -- apply_input_transform folded into the first convolution's loader."""
-        from mimo_unet_b200.network import NetworkRuntime
-        if self._runtime is None:
-            self._runtime = NetworkRuntime(self)
-        return self._runtime(x, gather)
+        return self.runtime()(x, gather)

@@ -89,6 +89,9 @@ struct mimo_unet_plan {
   bool last_training = false;
   bool have_forward = false;
   bool dy_tails_zeroed = false;  // the zero tails of the dy buffers are cleared once per binding
+  // optional caller-owned events recorded during backward when a group of parameter gradients is final:
+  // 0 decoders + heads, 1 core up path, 2 core down path, 3 encoders (= end of backward)
+  cudaEvent_t stage_ev[4] = {nullptr, nullptr, nullptr, nullptr};
   const float* const* last_masks = nullptr;
   std::vector<const float*> masks_copy;
   int launches = 0;
@@ -536,6 +539,7 @@ int mimo_unet_backward(mimo_unet_plan_t* P, const float* dout, const float* grad
     RUN(kGradGather, grad_gather_launch(&dp, nullptr, nullptr, t0, 0, st));
     RUN(kUpsampleBwd, upsample_bwd_launch(t0, view_of(P, P->g_u3, 0, c / 2), s > 0 ? 1 : 0, st));
   }
+  if (P->stage_ev[0]) MIMO_CUDA(cudaEventRecord(P->stage_ev[0], st));
   // ---- core up path ----
   if ((rc = node_backward(P, P->up3, tr, mask(P->up3), accumulate, st))) return rc;
   {
@@ -558,6 +562,7 @@ int mimo_unet_backward(mimo_unet_plan_t* P, const float* dout, const float* grad
     RUN(kGradGather, grad_gather_launch(&dp, nullptr, nullptr, t, 0, st));
     RUN(kUpsampleBwd, upsample_bwd_launch(t, view_of(P, P->g_x5, 0, 4 * c), 0, st));
   }
+  if (P->stage_ev[1]) MIMO_CUDA(cudaEventRecord(P->stage_ev[1], st));
   // ---- core down path: skip gradient (fold of the concat slice) + max-pool backward ----
   if ((rc = node_backward(P, P->down4, tr, mask(P->down4), accumulate, st))) return rc;
   {
@@ -586,6 +591,7 @@ int mimo_unet_backward(mimo_unet_plan_t* P, const float* dout, const float* grad
     const ActView act = view_of(P, P->cat3, 0, c);
     RUN(kGradGather, grad_gather_launch(&dskip, &gp, &act, view_of(P, P->g_xc, 0, c), 0, st));
   }
+  if (P->stage_ev[2]) MIMO_CUDA(cudaEventRecord(P->stage_ev[2], st));
   // ---- encoders ----
   for (int s = 0; s < S; ++s) {
     if ((rc = node_backward(P, P->enc_down[s], tr, mask(P->enc_down[s]), accumulate, st))) return rc;
@@ -608,7 +614,23 @@ int mimo_unet_backward(mimo_unet_plan_t* P, const float* dout, const float* grad
       ++P->launches;
     }
   }
+  if (P->stage_ev[3]) MIMO_CUDA(cudaEventRecord(P->stage_ev[3], st));
   return MIMO_OK;
+}
+
+int mimo_unet_set_backward_events(mimo_unet_plan_t* P, void* const* events) {
+  MIMO_CHECK(P, MIMO_ERR_ARG, "set_backward_events: null plan");
+  for (int i = 0; i < 4; ++i) P->stage_ev[i] = events ? (cudaEvent_t)events[i] : nullptr;
+  return MIMO_OK;
+}
+
+int mimo_unet_backward_stage_first_state(const mimo_unet_plan_t* P, int stage) {
+  if (!P || stage < 0 || stage > 3) return -1;
+  // state order == flat order: encoders | core.down2..4 | core.up1..3 | decoders + heads
+  if (stage == 3) return 0;
+  if (stage == 2) return P->nodes[P->down2].c1.state0;
+  if (stage == 1) return P->nodes[P->up1].c1.state0;
+  return P->nodes[P->dec[0]].c1.state0;
 }
 
 int mimo_unet_debug_view(const mimo_unet_plan_t* P, const char* name, mimo_act_t* view, int* kind) {

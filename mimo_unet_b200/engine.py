@@ -36,7 +36,9 @@ class UNetPlan:
         self.handle = h
         self.device = device
         self.ws_bytes = int(self.lib.mimo_unet_workspace_bytes(h))
-        self.workspace = torch.empty(self.ws_bytes, dtype=torch.uint8, device=device)
+        # zero-initialised once: pad channels (C..cpitch) of the NHWC buffers are never written by the elementwise kernels
+        # and are over-read by their 16-byte vector loads, so they must not hold NaN bit patterns
+        self.workspace = torch.zeros(self.ws_bytes, dtype=torch.uint8, device=device)
         self.n_state = int(self.lib.mimo_unet_num_state(h))
         self.n_dconv = int(self.lib.mimo_unet_num_double_convs(h))
         self.drop_channels = [int(self.lib.mimo_unet_dropout_channels(h, i)) for i in range(self.n_dconv)]
@@ -83,6 +85,18 @@ class UNetPlan:
         assert dout.is_contiguous() and dout.dtype == torch.float32
         check(self.lib.mimo_unet_backward(self.handle, dout.data_ptr(), _ptr(grad_scale), _ptr(dx), int(accumulate), stream_ptr()),
               "mimo_unet_backward")
+
+    def set_backward_events(self, events: Optional[Sequence["torch.cuda.Event"]]):
+        """events: 4 torch.cuda.Event objects (already recorded once so their handles exist) or None; see
+        mimo_unet_set_backward_events."""
+        if events is None:
+            check(self.lib.mimo_unet_set_backward_events(self.handle, None), "mimo_unet_set_backward_events")
+        else:
+            arr = (C.c_void_p * 4)(*[e.cuda_event for e in events])
+            check(self.lib.mimo_unet_set_backward_events(self.handle, arr), "mimo_unet_set_backward_events")
+
+    def stage_first_state(self, stage: int) -> int:
+        return int(self.lib.mimo_unet_backward_stage_first_state(self.handle, stage))
 
     @property
     def last_launches(self) -> int:

@@ -57,6 +57,30 @@ class NetworkRuntime:
         self._grad_views: List[Optional[torch.Tensor]] = []
         self._learnable_idx: List[int] = []
         self.last_launches = (0, 0)
+        self.grad_sync = None  # OverlappedGradientSynchronizer when data-parallel training is enabled
+
+    def enable_overlapped_allreduce(self, group=None):
+        """Data-parallel training: average the flat gradient buffer over ranks, bucket by bucket, overlapped with
+        backward. Call `grad_sync.wait()` before the optimizer step."""
+        from .parallel import OverlappedGradientSynchronizer
+        self.grad_sync = OverlappedGradientSynchronizer(group)
+        return self.grad_sync
+
+    def _stage_bounds(self, plan: UNetPlan, state):
+        """Element ranges of the four backward stages inside the flat gradient buffer (state order)."""
+        offs, off = {}, 0
+        for i in self._learnable_idx:
+            offs[i] = off
+            off += state[i].numel()
+        total = off
+
+        def flat_off(state_index):
+            for i in self._learnable_idx:
+                if i >= state_index:
+                    return offs[i]
+            return total
+        first = [flat_off(plan.stage_first_state(k)) for k in range(4)]   # stage 0 starts last
+        return [(first[0], total), (first[1], first[0]), (first[2], first[1]), (first[3], first[2])]
 
     def __deepcopy__(self, memo):  # plans hold device workspaces and C handles: never copied with the module
         return None
@@ -189,7 +213,11 @@ class NetworkRuntime:
                 self._ensure_grad_buffer(state)
                 plan._bound_sig = None
                 plan.bind([t.detach() for t in state], self._grad_views)
+            sync = self.grad_sync
+            plan.set_backward_events(sync.events if sync is not None else None)
             plan.backward(dout, dx=dx, accumulate=False)
+            if sync is not None:
+                sync.launch(self._flat_grads, self._stage_bounds(plan, state))
             # fresh view objects so autograd can adopt them as .grad without a copy
             grads, off = [None] * len(state), 0
             for i in self._learnable_idx:

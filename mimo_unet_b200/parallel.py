@@ -58,6 +58,43 @@ class GradientSynchronizer:
         self._work = []
 
 
+class OverlappedGradientSynchronizer:
+    """Gradient all-reduce overlapped with backward (NCCL over NVLink, one process per GPU).
+
+    The C executor records one CUDA event per backward stage as soon as that stage's parameter gradients are final
+    (decoders + heads, core up path, core down path, encoders). Stages are contiguous slices of the flat gradient
+    buffer, so each stage is one bucket: right after the (asynchronous) enqueue of backward returns, the buckets are
+    all-reduced (mean) on a side stream that waits only for the bucket's event, i.e. the first buckets travel while the
+    GPU is still computing the rest of backward. wait() joins them before the optimizer step."""
+
+    NUM_STAGES = 4
+
+    def __init__(self, group=None):
+        self.group = group
+        self.events = [torch.cuda.Event() for _ in range(self.NUM_STAGES)]
+        for e in self.events:
+            e.record()  # torch creates the cudaEvent_t lazily on the first record
+        self.side = torch.cuda.Stream()
+        self._work: List = []
+
+    def launch(self, flat: torch.Tensor, bounds):
+        """bounds[k] = (start, end) element range of stage k inside `flat`."""
+        if world_size() == 1:
+            return
+        for k in range(self.NUM_STAGES):
+            a, b = bounds[k]
+            if b <= a:
+                continue
+            with torch.cuda.stream(self.side):
+                self.side.wait_event(self.events[k])
+                self._work.append(dist.all_reduce(flat[a:b], op=dist.ReduceOp.AVG, group=self.group, async_op=True))
+
+    def wait(self):
+        for w in self._work:
+            w.wait()
+        self._work = []
+
+
 def allreduce_mean_(t: torch.Tensor, group=None) -> torch.Tensor:
     """In-place mean over ranks (used for the [S] loss vector that feeds the loss buffer)."""
     w = world_size()
