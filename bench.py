@@ -234,14 +234,16 @@ def run_gpu_arm(args):
     launches_per_step = rt.last_launches[0] + rt.last_launches[1] + 3  # + fused loss (2) + gradient-seed scale (1)
 
     # ---- roofline of the dominant kernel (tcgen05 implicit-GEMM conv), timed live with CUDA events on its stream
+    # (every rank runs the 3 extra steps -- they contain the gradient all-reduce -- but only rank 0 records events)
     roof = None
+    lib = _lib.lib()
+    plan = next(iter(rt.plans.values()))
     if rank == 0:
-        lib = _lib.lib()
-        plan = next(iter(rt.plans.values()))
         lib.mimo_unet_profile_enable(plan.handle, 1)
-        for i in range(3):
-            step(*dev_batches[i % n_host])
-        torch.cuda.synchronize()
+    for i in range(3):
+        step(*dev_batches[i % n_host])
+    torch.cuda.synchronize()
+    if rank == 0:
         import ctypes as C
         ncls = lib.mimo_unet_profile_classes()
         msb = (C.c_float * ncls)()
@@ -254,7 +256,7 @@ def run_gpu_arm(args):
         t_conv = (per_step["conv_fprop"][0] + per_step["conv_dgrad"][0]) * 1e-3
         sustained, burst, hbm, src = load_peaks()
         achieved = (fprop_fl + dgrad_fl) / t_conv / 1e12
-        roof = {"bound": "tensor", "kernel": "conv3x3_igemm_kernel (fprop+dgrad launches)", "achieved": achieved, "peak": sustained,
+        roof = {"bound": "tensor", "kernel": "conv3x3_flat_kernel + conv3x3_igemm_kernel (all fprop+dgrad launches of a step)", "achieved": achieved, "peak": sustained,
                 "unit": "TFLOP/s", "frac": achieved / sustained, "traffic": None,
                 "peak_source": f"bf16_tflops_sustained of {src} MEASURED_PEAKS.json (kernel timed inside a long step)",
                 "launches_per_step": per_step["conv_fprop"][1] + per_step["conv_dgrad"][1],

@@ -139,8 +139,14 @@ class MimoUnetModel(LightningModule):
             from mimo_unet_b200 import functional as Fn
             out = _out if _out is not None else torch.cat([p1, p2], dim=2)
             dev_buf = self.loss_buffer.device_state(p1.device)
-            total, loss, weights = Fn.laplace_train_loss(out, y_true, mask=mask, loss_buffer=dev_buf, update_buffer=True,
+            from mimo_unet_b200 import parallel as Par
+            dp = Par.world_size() > 1
+            # data parallel: every rank's loss buffer receives the MEAN per-subnetwork loss over ranks, so the softmax
+            # weights stay identical everywhere (the reference defines no multi-GPU behaviour)
+            total, loss, weights = Fn.laplace_train_loss(out, y_true, mask=mask, loss_buffer=dev_buf, update_buffer=not dp,
                                                          eps_min=self.loss_fn.eps_min, eps_max=self.loss_fn.eps_max)
+            if dp:
+                dev_buf.add(Par.allreduce_mean_(loss.detach().clone()))
             # `total` (= mean_s w_s loss_s) carries the autograd graph; expose it through the reference's
             # (loss, loss*weights, weights) triple so that loss_weighted.mean() == total, value and gradient
             loss_weighted = loss * weights + (total - (loss * weights).mean())

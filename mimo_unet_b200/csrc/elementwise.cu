@@ -625,8 +625,18 @@ bn_bwd_finalize_kernel(const float* __restrict__ part, int nparts, int C, float*
   const int cl = threadIdx.x & 7, pl = threadIdx.x >> 3;
   const int c = blockIdx.x * 8 + cl;
   double a = 0.0, b = 0.0;
-  if (c < C)
-    for (int p = pl; p < nparts; p += 32) { a += part[(size_t)p * 2 * C + c]; b += part[(size_t)p * 2 * C + C + c]; }
+  if (c < C) {
+    // independent loads, unrolled so their latencies overlap (the grid is only C/8 blocks)
+    int p = pl;
+    for (; p + 96 < nparts; p += 128) {
+      float va[4], vb[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { va[u] = part[(size_t)(p + 32 * u) * 2 * C + c]; vb[u] = part[(size_t)(p + 32 * u) * 2 * C + C + c]; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { a += va[u]; b += vb[u]; }
+    }
+    for (; p < nparts; p += 32) { a += part[(size_t)p * 2 * C + c]; b += part[(size_t)p * 2 * C + C + c]; }
+  }
   sa[pl][cl] = a; sb[pl][cl] = b;
   __syncthreads();
   if (pl != 0 || c >= C) return;

@@ -533,12 +533,13 @@ int mimo_unet_backward(mimo_unet_plan_t* P, const float* dout, const float* grad
                         (float*)P->grads[P->head_state0 + 2 * s + 1], accumulate, st));
     ++P->launches;
     if ((rc = node_backward(P, P->dec[s], tr, mask(P->dec[s]), accumulate, st))) return rc;
-    // gradient of the shared up-sampled core output: fold the [f, f + c/2) slice, then bilinear backward
+    // gradient of the shared up-sampled core output: fold the [f, f + c/2) slice of every decoder into ONE buffer
+    // (the bilinear backward is linear, so it runs once on the sum instead of once per subnetwork)
     const ActView dp = view_of(P, n.c1.dpad, f, c / 2);
     const ActView t0 = view_of(P, P->tmp0, 0, c / 2);
-    RUN(kGradGather, grad_gather_launch(&dp, nullptr, nullptr, t0, 0, st));
-    RUN(kUpsampleBwd, upsample_bwd_launch(t0, view_of(P, P->g_u3, 0, c / 2), s > 0 ? 1 : 0, st));
+    RUN(kGradGather, grad_gather_launch(&dp, nullptr, nullptr, t0, s > 0 ? 1 : 0, st));
   }
+  RUN(kUpsampleBwd, upsample_bwd_launch(view_of(P, P->tmp0, 0, c / 2), view_of(P, P->g_u3, 0, c / 2), 0, st));
   if (P->stage_ev[0]) MIMO_CUDA(cudaEventRecord(P->stage_ev[0], st));
   // ---- core up path ----
   if ((rc = node_backward(P, P->up3, tr, mask(P->up3), accumulate, st))) return rc;
