@@ -322,6 +322,117 @@ __global__ void upsample_kernel(ActView in, ActView o, int off_h, int off_w) {
   }
 }
 
+// own = view channels [c, c+8), next = [c+8, c+16) (packed bf16): returns the 8 channels starting at c + e, 0 < e < 8
+__device__ __forceinline__ uint4 funnel8(const uint4& own, const uint4& next, int e) {
+  const uint32_t w[8] = {own.x, own.y, own.z, own.w, next.x, next.y, next.z, next.w};
+  uint4 r = own;
+  switch (e) {
+#define MIMO_F8(E)                                                                                                       \
+  case E:                                                                                                                \
+    r.x = __funnelshift_r(w[(E >> 1) + 0], w[(E >> 1) + 1], (E & 1) * 16);                                               \
+    r.y = __funnelshift_r(w[(E >> 1) + 1], w[(E >> 1) + 2], (E & 1) * 16);                                               \
+    r.z = __funnelshift_r(w[(E >> 1) + 2], w[(E >> 1) + 3], (E & 1) * 16);                                               \
+    r.w = __funnelshift_r(w[(E >> 1) + 3], w[(E >> 1) + 4 > 7 ? 7 : (E >> 1) + 4], (E & 1) * 16);                        \
+    break;
+    MIMO_F8(1) MIMO_F8(2) MIMO_F8(3) MIMO_F8(4) MIMO_F8(5) MIMO_F8(6) MIMO_F8(7)
+#undef MIMO_F8
+    default: break;
+  }
+  return r;
+}
+
+// Fast path of the up-sampling: block = (pixel lanes) x GPP lanes per pixel (GPP = power of two >= #channel groups, so
+// the groups of a pixel never straddle a warp), row-based 32-bit indexing, 16-byte loads of the four taps. Destination
+// slices whose channel offset is NOT a multiple of 8 (decoder concat: 21 + 42 channels) are still written with 16-byte
+// stores: each thread takes the missing leading channels of the next group from its neighbour lane (shuffle) and funnel-
+// shifts the pair onto the buffer's 16-byte grid; only the first e = 8 - c_off % 8 channels of a pixel are scalar.
+template <int GPP>
+__global__ void __launch_bounds__(256, 3)
+upsample_fast_kernel(ActView in, ActView o, int off_h, int off_w) {
+  const int uh = 2 * in.H, uw = 2 * in.W;
+  const float rh = uh > 1 ? (float)(in.H - 1) / (float)(uh - 1) : 0.f;
+  const float rw = uw > 1 ? (float)(in.W - 1) / (float)(uw - 1) : 0.f;
+  const int groups = (o.C + 7) >> 3;
+  constexpr int lanes = 256 / GPP;
+  const int g = threadIdx.x % GPP, pl = threadIdx.x / GPP;
+  const int c = g * 8, nv = max(0, min(8, o.C - c));
+  const uint4 mask = group_mask(nv);
+  const int e = (8 - (o.c_off & 7)) & 7;                       // element shift onto the buffer's 16-byte grid
+  const bool last_slice = o.c_off + o.C > o.cpitch - 8;         // the overhang of the last word falls on pad channels
+  const bool tail_ok = e == 0 && o.c_off + ((o.C + 7) & ~7) <= o.cpitch && last_slice;
+  const int rows = o.N * o.H;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int n = row / o.H, h = row - n * o.H;
+    const int y = h - off_h;
+    const bool yin = y >= 0 && y < uh;
+    const float sy = rh * y;
+    const int y0 = yin ? (int)sy : 0;
+    const int y1 = min(y0 + 1, in.H - 1);
+    const float ly = sy - y0;
+    const bf16* r0 = in.base + in.pix(n, y0, 0) + c;
+    const bf16* r1 = in.base + in.pix(n, y1, 0) + c;
+    for (int w0 = 0; w0 < o.W; w0 += lanes) {   // uniform trip count: the shuffles below need converged warps
+      const int w = w0 + pl;
+      const bool active = w < o.W && g < groups;
+      uint4 own = make_uint4(0, 0, 0, 0);
+      const int x = w - off_w;
+      if (active && yin && x >= 0 && x < uw) {
+        const float sx = rw * x;
+        const int x0 = (int)sx, x1 = min(x0 + 1, in.W - 1);
+        const float lx = sx - x0;
+        float a[8], b[8], cc[8], d[8], out[8];
+        unpack8(load_group<true>(r0 + (size_t)x0 * in.cpitch, nv, mask), a);
+        unpack8(load_group<true>(r0 + (size_t)x1 * in.cpitch, nv, mask), b);
+        unpack8(load_group<true>(r1 + (size_t)x0 * in.cpitch, nv, mask), cc);
+        unpack8(load_group<true>(r1 + (size_t)x1 * in.cpitch, nv, mask), d);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          out[k] = (1.f - ly) * ((1.f - lx) * a[k] + lx * b[k]) + ly * ((1.f - lx) * cc[k] + lx * d[k]);
+        own = pack8(out);
+      }
+      uint4 word = own;
+      if (e != 0) {
+        uint4 next;
+        next.x = __shfl_down_sync(0xffffffffu, own.x, 1);
+        next.y = __shfl_down_sync(0xffffffffu, own.y, 1);
+        next.z = __shfl_down_sync(0xffffffffu, own.z, 1);
+        next.w = __shfl_down_sync(0xffffffffu, own.w, 1);
+        if (g == GPP - 1) next = make_uint4(0, 0, 0, 0);  // the next lane belongs to another pixel
+        word = funnel8(own, next, e);
+      }
+      if (!active) continue;
+      // targets: the pixel itself + the halo cells that mirror it (outer two rings only)
+      const int hh = (h == 1) ? -1 : ((h == o.H - 2) ? o.H : -2);
+      const int ww = (w == 1) ? -1 : ((w == o.W - 2) ? o.W : -2);
+      const int hh2 = (o.H == 3 && h == 1) ? o.H : -2;
+      const int ww2 = (o.W == 3 && w == 1) ? o.W : -2;
+      const int hs[3] = {h, hh, hh2};
+      const int ws[3] = {w, ww, ww2};
+      const bool border = o.pad == 1 && !(h > 1 && h < o.H - 2 && w > 1 && w < o.W - 2);
+#pragma unroll
+      for (int ai = 0; ai < 3; ++ai) {
+        if (hs[ai] == -2 || (ai > 0 && !border)) continue;
+#pragma unroll
+        for (int bi = 0; bi < 3; ++bi) {
+          if (ws[bi] == -2 || ((ai | bi) != 0 && !border)) continue;
+          bf16* px = o.base + o.pix(n, hs[ai], ws[bi]);
+          if (e == 0) {
+            store_group<true>(px + c, nv, own, tail_ok);
+          } else {
+            const int valid = min(8, o.C - (c + e));  // view channels [c+e, c+e+8) carried by `word`
+            if (valid == 8 || (valid > 0 && last_slice && o.c_off + c + e + 8 <= o.cpitch)) {
+              *reinterpret_cast<uint4*>(px + c + e) = word;
+            } else if (valid > 0) {
+              store_group<false>(px + c + e, valid, word);
+            }
+            if (g == 0) store_group<false>(px, min(e, o.C), own);  // leading channels [0, e) of the pixel
+          }
+        }
+      }
+    }
+  }
+}
+
 // backward of the above as a gather: every source pixel sums the destination pixels that sampled it
 __global__ void upsample_bwd_kernel(ActView gdst /*unpadded, skip-sized*/, ActView gsrc /*unpadded*/, int off_h, int off_w,
                                     int accumulate) {
@@ -856,7 +967,24 @@ int upsample_launch(const ActView& in, const ActView& o, cudaStream_t st) {
   MIMO_CHECK(o.N == in.N && o.C == in.C, MIMO_ERR_ARG, "upsample: N/C mismatch");
   const int dY = o.H - 2 * in.H, dX = o.W - 2 * in.W;
   MIMO_CHECK(dY >= 0 && dX >= 0, MIMO_ERR_ARG, "upsample: skip smaller than the up-sampled map");
-  const long long total = (long long)o.N * o.H * o.W * ((o.C + 7) / 8);
+  const int groups = (o.C + 7) / 8;
+  if (groups <= 32 && view_vec_ok(in) && ((uintptr_t)o.base % 16) == 0 && o.cpitch % 8 == 0 && o.pad <= 1) {
+    const int rows = o.N * o.H;
+    const int grid = rows < 8 * num_sms() ? rows : 8 * num_sms();
+    int gpp = 1;
+    while (gpp < groups) gpp <<= 1;
+    switch (gpp) {
+      case 1: upsample_fast_kernel<1><<<grid, kBlock, 0, st>>>(in, o, dY / 2, dX / 2); break;
+      case 2: upsample_fast_kernel<2><<<grid, kBlock, 0, st>>>(in, o, dY / 2, dX / 2); break;
+      case 4: upsample_fast_kernel<4><<<grid, kBlock, 0, st>>>(in, o, dY / 2, dX / 2); break;
+      case 8: upsample_fast_kernel<8><<<grid, kBlock, 0, st>>>(in, o, dY / 2, dX / 2); break;
+      case 16: upsample_fast_kernel<16><<<grid, kBlock, 0, st>>>(in, o, dY / 2, dX / 2); break;
+      default: upsample_fast_kernel<32><<<grid, kBlock, 0, st>>>(in, o, dY / 2, dX / 2); break;
+    }
+    MIMO_LAUNCH_CHECK();
+    return MIMO_OK;
+  }
+  const long long total = (long long)o.N * o.H * o.W * groups;
   upsample_kernel<<<grid_for(total), kBlock, 0, st>>>(in, o, dY / 2, dX / 2);
   MIMO_LAUNCH_CHECK();
   return MIMO_OK;

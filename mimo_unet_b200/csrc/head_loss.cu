@@ -131,6 +131,84 @@ __global__ void head_bwd_kernel(ActView f, const float* __restrict__ W, int K, c
   if ((int)threadIdx.x + kBlock < pairs) part[(size_t)blockIdx.x * pairs + threadIdx.x + kBlock] = acc1;
 }
 
+// Fast path of the head backward (K <= 4, 16-byte aligned views): block = (pixel lanes) x (8-channel groups), every
+// thread keeps ONE channel group: W[k][c..c+8) and its dW / db accumulators live in registers (K*8 FMAs per pixel, no
+// shared-memory tiles), G is written with one 16-byte store. The per-thread accumulators are combined through shared
+// memory in a fixed order; the partial layout [block][K*C + K] is the one head_bwd_finalize_kernel reduces.
+template <int K>
+__global__ void __launch_bounds__(256, 3)
+head_bwd_fast_kernel(ActView f, const float* __restrict__ W, const float* __restrict__ dout, long long out_bstride,
+                     const float* __restrict__ grad_scale, ActView G, float* __restrict__ part) {
+  extern __shared__ float sh[];  // [lanes][groups][K*8 + K]
+  const int C = f.C;
+  const int groups = (C + 7) >> 3;
+  const int lanes = blockDim.x / groups;
+  const int g = threadIdx.x % groups, pl = threadIdx.x / groups;
+  const int c = g * 8, nv = min(8, C - c);
+  const float gs = grad_scale ? *grad_scale : 1.f;
+  const long long HW = (long long)f.H * f.W;
+  float w[K][8], aw[K][8], ab[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    ab[k] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { w[k][j] = (j < nv) ? W[k * C + c + j] : 0.f; aw[k][j] = 0.f; }
+  }
+  if (pl < lanes) {
+    const uint4 mask = group_mask(nv);
+    const int rows = f.N * f.H;
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+      const int n = row / f.H, h = row - n * f.H;
+      const bf16* src = f.base + f.pix(n, h, 0) + c;
+      bf16* gdst = G.base + G.pix(n, h, 0) + c;
+      const float* dp = dout + (long long)n * out_bstride + (long long)h * f.W;
+      for (int x = pl; x < f.W; x += lanes) {
+        const uint4 raw = and4(*reinterpret_cast<const uint4*>(src + (size_t)x * f.cpitch), mask);
+        float d[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) d[k] = gs * dp[k * HW + x];
+        float v[8], o[8];
+        unpack8(raw, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float a = 0.f;
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            a = fmaf(d[k], w[k][j], a);
+            aw[k][j] = fmaf(d[k], v[j], aw[k][j]);
+          }
+          o[j] = a;
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) ab[k] += d[k];
+        *reinterpret_cast<uint4*>(gdst + (size_t)x * G.cpitch) = pack8(o);  // pad channels get zeros (w == 0 there)
+      }
+    }
+    float* mine = sh + ((size_t)pl * groups + g) * (K * 8 + K);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) mine[k * 8 + j] = aw[k][j];
+      mine[K * 8 + k] = ab[k];
+    }
+  }
+  __syncthreads();
+  const int pairs = K * C + K;
+  for (int i = threadIdx.x; i < pairs; i += blockDim.x) {
+    float acc = 0.f;
+    if (i < K * C) {
+      const int k = i / C, ch = i - k * C;
+      const float* srcp = sh + (size_t)(ch >> 3) * (K * 8 + K) + k * 8 + (ch & 7);
+      for (int p = 0; p < lanes; ++p) acc += srcp[(size_t)p * groups * (K * 8 + K)];
+    } else {
+      const int k = i - K * C;
+      const float* srcp = sh + K * 8 + k;  // group 0 of every pixel lane saw every pixel exactly once
+      for (int p = 0; p < lanes; ++p) acc += srcp[(size_t)p * groups * (K * 8 + K)];
+    }
+    part[(size_t)blockIdx.x * pairs + i] = acc;
+  }
+}
+
 __global__ void head_bwd_finalize_kernel(const float* __restrict__ part, int nparts, int K, int C, float* __restrict__ dW,
                                          float* __restrict__ db, int accumulate) {
   const int pairs = K * C + K;
@@ -409,7 +487,7 @@ int head_fwd_launch(const ActView& f, const float* W, const float* bias, int K, 
   return MIMO_OK;
 }
 
-int head_bwd_parts() { return 2 * num_sms(); }
+int head_bwd_parts() { return 3 * num_sms(); }
 
 int head_bwd_launch(const ActView& f, const float* W, int K, const float* dout, long long out_bstride, const float* grad_scale,
                     const ActView& G, float* part, float* dW, float* db, int accumulate, cudaStream_t st) {
@@ -417,6 +495,27 @@ int head_bwd_launch(const ActView& f, const float* W, int K, const float* dout, 
   MIMO_CHECK(K * f.C + K <= 2 * kBlock, MIMO_ERR_ARG, "head: K*C too large");
   MIMO_CHECK(G.pad == 0 && G.c_off == 0 && G.C == f.C, MIMO_ERR_ARG, "head_bwd: G view mismatch");
   const int nparts = head_bwd_parts();
+  {
+    // fast path: register accumulators, 16-byte loads / stores
+    const int groups = (f.C + 7) / 8;
+    const bool aligned = ((uintptr_t)f.base % 16) == 0 && f.cpitch % 8 == 0 && f.c_off % 8 == 0 && f.c_off + groups * 8 <= f.cpitch &&
+                         ((uintptr_t)G.base % 16) == 0 && G.cpitch % 8 == 0 && groups * 8 <= G.cpitch;
+    if (aligned && (K == 1 || K == 2 || K == 4) && groups <= kBlock) {
+      const int rows = f.N * f.H;
+      const int grid = rows < nparts ? rows : nparts;
+      const int lanes = kBlock / groups;
+      const size_t shb = (size_t)lanes * groups * (K * 8 + K) * sizeof(float);
+      if (shb <= 48 * 1024) {
+        if (K == 1) head_bwd_fast_kernel<1><<<grid, kBlock, shb, st>>>(f, W, dout, out_bstride, grad_scale, G, part);
+        else if (K == 2) head_bwd_fast_kernel<2><<<grid, kBlock, shb, st>>>(f, W, dout, out_bstride, grad_scale, G, part);
+        else head_bwd_fast_kernel<4><<<grid, kBlock, shb, st>>>(f, W, dout, out_bstride, grad_scale, G, part);
+        MIMO_LAUNCH_CHECK();
+        head_bwd_finalize_kernel<<<ceil_div(K * f.C + K, 128), 128, 0, st>>>(part, grid, K, f.C, dW, db, accumulate);
+        MIMO_LAUNCH_CHECK();
+        return MIMO_OK;
+      }
+    }
+  }
   const size_t smem = ((size_t)K * f.C + (size_t)K * kBlock + (size_t)kBlock * (f.C + 1)) * sizeof(float);
   static bool attr = false;
   if (!attr) { MIMO_CUDA(cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr = true; }

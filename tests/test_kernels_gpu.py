@@ -136,6 +136,49 @@ def test_conv_wgrad(lib, N, Cin, Cout, H, W, dy_pad):
     assert rel_l2(grad, 2 * w.grad) <= TOL
 
 
+FLATK_CASES = [
+    # N, Cin, Cout, H, W   (65..256 input channels, <= 192 output channels: the K-chunked flat kernel)
+    (2, 84, 42, 16, 20),
+    (2, 168, 84, 12, 18),
+    (3, 84, 168, 9, 13),
+    (1, 200, 100, 7, 9),
+    (2, 70, 192, 6, 6),
+]
+
+
+@pytest.mark.parametrize("N,Cin,Cout,H,W", FLATK_CASES)
+def test_conv_flatk_fprop_dgrad(lib, monkeypatch, N, Cin, Cout, H, W):
+    """Forces the K-chunked flat kernel (it is normally reserved for large feature maps) and checks fprop + BatchNorm
+    statistics and dgrad against the oracle, like test_weight_pack_and_conv_fprop / test_conv_dgrad."""
+    monkeypatch.setenv("MIMO_FLATK_MIN_ITEMS", "1")
+    torch.manual_seed(5)
+    x = bf16r(torch.randn(N, Cin, H, W, device="cuda"))
+    w = torch.randn(Cout, Cin, 3, 3, device="cuda") / math.sqrt(9 * Cin)
+    wf, wd = _pack_weights(lib, w)
+    wq = bf16r(w)
+    xb = make_buffer(N, H, W, 1, p8(Cin))
+    put_nchw(xb, x, 1)
+    yb = make_buffer(N, H, W, 0, p8(Cout))
+    rows = lib.mimo_conv3x3_m_tiles(N, H, W)
+    ssum = torch.full((rows, p8(Cout)), float("nan"), device="cuda")
+    ssq = torch.full((rows, p8(Cout)), float("nan"), device="cuda")
+    _lib.check(lib.mimo_conv3x3(act_of(xb, 1, 0, Cin), 0, wf.data_ptr(), Cout, p8(Cin), yb.data_ptr(), p8(Cout), ssum.data_ptr(),
+                                ssq.data_ptr(), None, 0, stream()), "conv3x3")
+    got = get_nchw(yb, 0, 0, Cout)
+    assert rel_l2(got, bf16r(O.conv3x3_reflect(x, wq, None))) <= TOL
+    if p8(Cout) > Cout:
+        assert torch.all(yb[..., Cout:] == 0)
+    s, q = ssum.sum(0)[:Cout], ssq.sum(0)[:Cout]
+    assert rel_l2(s, got.sum(dim=(0, 2, 3))) <= 1e-4 or float((s - got.sum(dim=(0, 2, 3))).abs().max()) < 1e-2
+    assert rel_l2(q, (got * got).sum(dim=(0, 2, 3))) <= 1e-4
+    # dgrad over the zero-tail dY layout
+    dy = bf16r(torch.randn(N, Cout, H, W, device="cuda"))
+    dyb, dya = _dy_buffer(dy, 2)
+    dpad = make_buffer(N, H + 2, W + 2, 0, p8(Cin))
+    _lib.check(lib.mimo_conv3x3(dya, 1, wd.data_ptr(), Cin, p8(Cout), dpad.data_ptr(), p8(Cin), None, None, None, 0, stream()), "dgrad")
+    assert rel_l2(get_nchw(dpad, 0, 0, Cin), bf16r(F.conv_transpose2d(dy, wq))) <= TOL
+
+
 def test_conv_eval_epilogue_bias_relu(lib):
     torch.manual_seed(4)
     N, Cin, Cout, H, W = 2, 16, 24, 12, 20
@@ -267,6 +310,33 @@ def test_upsample_fwd_bwd(lib, golden_dir):
     ob = make_buffer(N, 2 * H, 2 * W, 1, p8(Cc))
     _lib.check(lib.mimo_upsample_bilinear2x(act_of(xb, 1, 0, Cc), act_of(ob, 1, 0, Cc), stream()))
     assert rel_l2(get_nchw(ob, 1, 0, Cc), g["y"].cuda()) <= 6e-3
+
+
+@pytest.mark.parametrize("C_,c_off,cpitch", [(42, 21, 64), (42, 0, 48), (84, 84, 168), (5, 10, 24), (21, 3, 24), (168, 168, 336)])
+def test_upsample_into_concat_slice(lib, C_, c_off, cpitch):
+    """Decoder / core concat geometry: the up-sampled map lands in a channel slice whose offset need not be a multiple
+    of 8 (21 + 42 channels in the decoder); neighbouring slices and the halo must stay intact."""
+    torch.manual_seed(11)
+    N, H, W = 2, 5, 7
+    x = bf16r(torch.randn(N, C_, H, W, device="cuda"))
+    xb = make_buffer(N, H, W, 1, p8(C_))
+    put_nchw(xb, x, 1)
+    OH, OW = 2 * H, 2 * W + 1
+    ob = make_buffer(N, OH, OW, 1, cpitch, fill=0.0)
+    sentinel = 7.0
+    ob[...] = sentinel
+    _lib.check(lib.mimo_upsample_bilinear2x(act_of(xb, 1, 0, C_), act_of(ob, 1, c_off, C_), stream()))
+    ref = O.pad_to(O.upsample_bilinear2x_ac(x), OH, OW)
+    got = get_nchw(ob, 1, c_off, C_, with_halo=True)
+    assert rel_l2(got[:, :, 1:-1, 1:-1], bf16r(ref)) <= TOL
+    assert torch.equal(got, F.pad(got[:, :, 1:-1, 1:-1], (1, 1, 1, 1), mode="reflect"))
+    # channels before the slice are untouched; channels after it are untouched unless they are pad channels of the
+    # buffer's last 16-byte group (those may be zeroed)
+    assert torch.all(ob[..., :c_off] == sentinel)
+    rest = ob[..., c_off + C_:]
+    assert torch.all((rest == sentinel) | (rest == 0))
+    if c_off + C_ <= cpitch - 8:
+        assert torch.all(rest == sentinel)
 
 
 @pytest.mark.parametrize("H,W", [(8, 10), (9, 11), (3, 3)])
