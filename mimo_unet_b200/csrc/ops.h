@@ -19,6 +19,8 @@ int conv3x3_flatk_launch(const ActView& in, int mode, const bf16* wpacked, int c
 int conv3x3_wgrad_launch(const ActView& dy, const ActView& x, float* dw_packed, int cin_pitch, cudaStream_t stream);
 bool conv3x3_wgrad_flat_ok(const ActView& dy, const ActView& x);
 int conv3x3_wgrad_flat_launch(const ActView& dy, const ActView& x, float* dw_packed, int cin_pitch, cudaStream_t stream);
+bool conv3x3_wgrad_flatk_ok(const ActView& dy, const ActView& x);
+int conv3x3_wgrad_flatk_launch(const ActView& dy, const ActView& x, float* dw_packed, int cin_pitch, cudaStream_t stream);
 int wgrad_unpack_launch(const float* packed, float* grad_oihw, int cout, int cin, int cin_pitch, float scale, int accumulate,
                         cudaStream_t stream);
 

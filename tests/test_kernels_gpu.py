@@ -136,6 +136,36 @@ def test_conv_wgrad(lib, N, Cin, Cout, H, W, dy_pad):
     assert rel_l2(grad, 2 * w.grad) <= TOL
 
 
+WGRAD_FLATK_CASES = [
+    # N, Cin, Cout, H, W   (more than 64 input or output channels: the stream-K flat wgrad kernel, conv_wgrad_flatk.cu)
+    (2, 100, 70, 7, 9),       # one ci pair, one co tile, ragged channels
+    (1, 200, 150, 5, 6),      # pair + single ci chunk, two co tiles (second one 22 channels)
+    (2, 130, 40, 9, 11),      # pair + single chunk with 2 channels
+    (3, 40, 130, 6, 10),      # single ci chunk only (no two-chunk items), two co tiles
+    (1, 336, 336, 8, 10),     # three pairs, three co tiles
+    (2, 64, 65, 16, 20),      # the smallest shapes that leave the <= 64-channel kernel
+]
+
+
+@pytest.mark.parametrize("N,Cin,Cout,H,W", WGRAD_FLATK_CASES)
+def test_conv_wgrad_flatk(lib, N, Cin, Cout, H, W):
+    """Stream-K flat wgrad (zero-tail dY layout) against autograd of the oracle convolution, incl. accumulate mode."""
+    torch.manual_seed(7)
+    x = bf16r(torch.randn(N, Cin, H, W, device="cuda"))
+    dy = bf16r(torch.randn(N, Cout, H, W, device="cuda"))
+    xb = make_buffer(N, H, W, 1, p8(Cin))
+    put_nchw(xb, x, 1)
+    dyb, dya = _dy_buffer(dy, 2)
+    scratch = torch.empty(9 * Cout * p8(Cin), device="cuda")
+    grad = torch.full((Cout, Cin, 3, 3), float("nan"), device="cuda")
+    _lib.check(lib.mimo_conv3x3_wgrad(dya, act_of(xb, 1, 0, Cin), scratch.data_ptr(), p8(Cin), grad.data_ptr(), 0, stream()), "wgrad")
+    w = torch.zeros(Cout, Cin, 3, 3, device="cuda", requires_grad=True)
+    O.conv3x3_reflect(x, w, None).backward(dy)
+    assert rel_l2(grad, w.grad) <= TOL
+    _lib.check(lib.mimo_conv3x3_wgrad(dya, act_of(xb, 1, 0, Cin), scratch.data_ptr(), p8(Cin), grad.data_ptr(), 1, stream()), "wgrad")
+    assert rel_l2(grad, 2 * w.grad) <= TOL
+
+
 FLATK_CASES = [
     # N, Cin, Cout, H, W   (65..256 input channels, <= 192 output channels: the K-chunked flat kernel)
     (2, 84, 42, 16, 20),
