@@ -48,6 +48,7 @@ struct WgFlatKParams {
   long long W2, Wtot;  // weight (k-block x ci chunks) of the two-chunk items / of everything
   int cout, cin_pitch;
   float* dw;           // [9][cout][cin_pitch], zeroed by the launcher
+  int ko;              // diagnostic knock-outs (env MIMO_WGK_KO): 1 no reductions, 2 no memset, 4 no MMAs
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -181,6 +182,7 @@ conv3x3_wgrad_flatk_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __
         const uint32_t b_lo = b_lo0 + (uint32_t)stage * (kStageBytes >> 4);
         const uint32_t acc = kb != sw.kb0;   // the first k-step of a segment overwrites the accumulator
         if (elect_one()) {
+          if (!(p.ko & 4)) {
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k)
             umma_bf16_w(tmem_base, a_lo + k * (2048 >> 4), hi, b_lo + k * (2048 >> 4), hi, idesc, acc | (uint32_t)k);
@@ -189,6 +191,7 @@ conv3x3_wgrad_flatk_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __
             for (int k = 0; k < kBlockK / 16; ++k)
               umma_bf16_w(tmem_base + kAccCols, a_lo + k * (2048 >> 4), hi, b_lo + (kXSlot >> 4) + k * (2048 >> 4), hi, idesc,
                           acc | (uint32_t)k);
+          }
           }
           umma_commit(&empty_bar[stage]);
         }
@@ -218,7 +221,7 @@ conv3x3_wgrad_flatk_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __
           for (int c = 0; c < 64; c += 16) {
             float v[16];
             tmem_ld16(t_addr + j * kAccCols + kw * 64 + c, v);
-            if (co < p.cout) {
+            if (co < p.cout && !(p.ko & 1)) {
 #pragma unroll
               for (int i = 0; i < 16; i += 4)
                 if (ci0 + c + i + 3 < p.cin_pitch) red_add_v4(dst_row + c + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
@@ -283,7 +286,8 @@ int conv3x3_wgrad_flatk_launch(const ActView& dy, const ActView& x, float* dw, i
     rc = encode_tmap_bf16(&tm_x2, x.base + x.c_off, 2, dims, strides, box2, 1);
     if (rc) return rc;
   }
-  MIMO_CUDA(cudaMemsetAsync(dw, 0, (size_t)9 * p.cout * cin_pitch * sizeof(float), stream));
+  p.ko = getenv("MIMO_WGK_KO") ? atoi(getenv("MIMO_WGK_KO")) : 0;
+  if (!(p.ko & 2)) MIMO_CUDA(cudaMemsetAsync(dw, 0, (size_t)9 * p.cout * cin_pitch * sizeof(float), stream));
   const size_t smem_bytes = (size_t)kStages * kStageBytes + (2 * kStages + 2) * 8 + 16 + 1024;
   static bool attr_set = false;
   if (!attr_set) {

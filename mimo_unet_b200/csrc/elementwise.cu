@@ -7,6 +7,8 @@
 #include "common.cuh"
 #include "ops.h"
 
+#include <stdlib.h>
+
 namespace mimo {
 namespace {
 
@@ -821,6 +823,141 @@ bn_bwd_apply_kernel(ActView G, const bf16* __restrict__ y, int ycp, const float*
 }
 
 // ------------------------------------------------------------------------------------------------
+// Bulk-copy pipelined variants of the two BN-backward passes for dense operands (G and y are whole [N][H][W][cp]
+// buffers with the same pitch: every full-resolution layer). The register-prefetch kernels above keep only ~48 KB per
+// SM in flight and spill (ncu: 2.9 TB/s, 50 % "no eligible warp"); here one thread streams contiguous row chunks of G
+// and y into a 3-stage shared-memory ring with cp.async.bulk (mbarrier complete_tx), so ~130 KB per SM are in
+// flight without holding registers, and the 256 threads read 16-byte groups conflict-free out of shared memory.
+//   MODE 0: per-block partials of sum dz, sum dz*y      MODE 1: dy = scale*dz + A*y + B  (see bn_bwd_apply_kernel)
+// A chunk is `rows_per_chunk` whole image rows, or one of `segs` segments of a row when a row exceeds the stage.
+// ------------------------------------------------------------------------------------------------
+constexpr int kBulkStages = 3;
+constexpr int kBulkStageCap = 16 * 1024;   // bytes per tensor per stage
+
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+struct BulkArgs {
+  const bf16* G; const bf16* y;   // dense [rows][W][cp]
+  int cp, C, W, H, rows;          // rows = N*H
+  int rows_per_chunk, segs, seg_w, n_chunks;
+  const float *scale, *shift, *mean, *invstd, *drop, *s1s2;
+  float inv_count; int training;
+  float* part;                    // MODE 0: [gridDim.x][2][C]
+  ActView dy;                     // MODE 1
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(256, 2)
+bn_bwd_bulk_kernel(const BulkArgs a) {
+  extern __shared__ __align__(128) uint8_t bsm[];
+  uint8_t* sG = bsm;
+  uint8_t* sY = bsm + kBulkStages * kBulkStageCap;
+  uint64_t* full = reinterpret_cast<uint64_t*>(bsm + 2 * kBulkStages * kBulkStageCap);
+  float* red = reinterpret_cast<float*>(sG);   // MODE 0 epilogue: [pix_lanes][groups*16], aliases the (drained) ring
+  const int C = a.C, cp = a.cp, W = a.W;
+  const int groups = cp >> 3;                 // whole pixels are streamed: pad channels are zero in G (dz = 0)
+  const int pix_lanes = blockDim.x / groups;
+  const int g = threadIdx.x % groups, pl = threadIdx.x / groups;
+  const int c = g * 8, nv = max(0, min(8, C - c));
+  const bool lane_on = pl < pix_lanes;
+  const size_t row_elems = (size_t)W * cp;
+
+  auto issue = [&](int chunk, int stage) {   // one thread
+    int row0, w0, npx_rows, npx_w;
+    if (a.segs > 1) { row0 = chunk / a.segs; const int sg = chunk - row0 * a.segs; w0 = sg * a.seg_w; npx_w = min(a.seg_w, W - w0); npx_rows = 1; }
+    else { row0 = chunk * a.rows_per_chunk; w0 = 0; npx_w = W; npx_rows = min(a.rows_per_chunk, a.rows - row0); }
+    const uint32_t bytes = (uint32_t)((size_t)npx_rows * npx_w * cp * 2);
+    const size_t off = (size_t)row0 * row_elems + (size_t)w0 * cp;
+    mbar_arrive_expect_tx(&full[stage], 2 * bytes);
+    bulk_load(sG + (size_t)stage * kBulkStageCap, a.G + off, bytes, &full[stage]);
+    bulk_load(sY + (size_t)stage * kBulkStageCap, a.y + off, bytes, &full[stage]);
+  };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kBulkStages; ++s) mbar_init(&full[s], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  const int my_n = (a.n_chunks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  if (threadIdx.x == 0)
+    for (int i = 0; i < kBulkStages && i < my_n; ++i) issue(blockIdx.x + i * gridDim.x, i);
+
+  float sc[8], sf[8], ca[8], cb[8], a1[8], a2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    sc[k] = (lane_on && k < nv) ? a.scale[c + k] : 0.f;
+    sf[k] = (lane_on && k < nv) ? a.shift[c + k] : 0.f;
+    ca[k] = 0.f; cb[k] = 0.f; a1[k] = 0.f; a2[k] = 0.f;
+    if (MODE == 1 && a.training && lane_on && k < nv) {
+      const float is = a.invstd[c + k], s1 = a.s1s2[c + k], s2 = a.s1s2[C + c + k];
+      ca[k] = -sc[k] * s2 * is * a.inv_count;
+      cb[k] = -sc[k] * (s1 - s2 * is * a.mean[c + k]) * a.inv_count;
+    }
+  }
+
+  int stage = 0; uint32_t phase = 0;
+  for (int i = 0; i < my_n; ++i) {
+    const int chunk = blockIdx.x + i * gridDim.x;
+    int row0, w0, npx_rows, npx_w;
+    if (a.segs > 1) { row0 = chunk / a.segs; const int sg = chunk - row0 * a.segs; w0 = sg * a.seg_w; npx_w = min(a.seg_w, W - w0); npx_rows = 1; }
+    else { row0 = chunk * a.rows_per_chunk; w0 = 0; npx_w = W; npx_rows = min(a.rows_per_chunk, a.rows - row0); }
+    mbar_wait(&full[stage], phase);
+    if (lane_on) {
+      const uint4* gs = reinterpret_cast<const uint4*>(sG + (size_t)stage * kBulkStageCap);
+      const uint4* ys = reinterpret_cast<const uint4*>(sY + (size_t)stage * kBulkStageCap);
+      for (int rr = 0; rr < npx_rows; ++rr) {
+        const int row = row0 + rr;
+        const int n = row / a.H, h = row - n * a.H;
+        float dr[8];
+        if (a.drop) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) dr[k] = k < nv ? a.drop[(size_t)n * C + c + k] : 0.f;
+        }
+        bf16* dp = nullptr;
+        if (MODE == 1) dp = a.dy.base + a.dy.pix(n, h, w0) + c;
+        const int base = rr * npx_w * groups + g;
+        for (int w = pl; w < npx_w; w += pix_lanes) {
+          float gv[8], yv[8], out[8];
+          unpack8(gs[base + w * groups], gv);
+          unpack8(ys[base + w * groups], yv);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float z = fmaf(yv[k], sc[k], sf[k]);
+            float gg = gv[k];
+            if (a.drop) gg *= dr[k];
+            const float dz = (z > 0.f) ? gg : 0.f;
+            if (MODE == 0) { a1[k] += dz; a2[k] = fmaf(dz, yv[k], a2[k]); }
+            else out[k] = fmaf(sc[k], dz, fmaf(ca[k], yv[k], cb[k]));
+          }
+          if (MODE == 1) *reinterpret_cast<uint4*>(dp + (size_t)w * a.dy.cpitch) = pack8(out);
+        }
+      }
+    }
+    __syncthreads();   // every thread is done with this stage: refill it
+    if (threadIdx.x == 0 && i + kBulkStages < my_n) issue(blockIdx.x + (i + kBulkStages) * gridDim.x, stage);
+    if (++stage == kBulkStages) { stage = 0; phase ^= 1; }
+  }
+  if (MODE == 0) {
+    if (lane_on) {
+      float* mine = red + (size_t)pl * groups * 16 + g * 16;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { mine[k] = a1[k]; mine[8 + k] = a2[k]; }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {   // fixed-order combine over the pixel lanes
+      const int which = i / C, ch = i - which * C;
+      const float* src = red + (ch >> 3) * 16 + which * 8 + (ch & 7);
+      float acc = 0.f;
+      for (int p = 0; p < pix_lanes; ++p) acc += src[(size_t)p * groups * 16];
+      a.part[(size_t)blockIdx.x * 2 * C + i] = acc;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Component-level up-sampling alternatives of `Up` (components.py:86-98). The reference cannot run them at
 // whole-model level, so they are plain CUDA-core kernels, not tensor-core paths.
 // ------------------------------------------------------------------------------------------------
@@ -1040,6 +1177,48 @@ int bn_bwd_launch(const ActView& G, const bf16* y, int ycp, const float* scale, 
   const int groups = (C + 7) / 8;
   MIMO_CHECK(groups <= kBlock, MIMO_ERR_ARG, "bn_bwd: too many channels (%d)", C);
   const int rows = G.N * G.H;
+  {
+    // dense operands with one pitch: bulk-copy pipelined kernels (every full-resolution layer)
+    static const int bulk_on = getenv("MIMO_BN_BULK") ? atoi(getenv("MIMO_BN_BULK")) : 1;
+    const int cp = G.cpitch;
+    const size_t row_bytes = (size_t)G.W * cp * 2;
+    const bool dense = G.c_off == 0 && round_up(C, 8) == cp && ycp == cp && dy.cpitch == cp && ((uintptr_t)G.base % 16) == 0 &&
+                       (cp >> 3) <= kBlock && (size_t)G.N * G.H * G.W * cp < (1ull << 31);
+    if (bulk_on && dense) {
+      BulkArgs a{};
+      a.G = G.base; a.y = y; a.cp = cp; a.C = C; a.W = G.W; a.H = G.H; a.rows = rows;
+      if (row_bytes <= (size_t)kBulkStageCap) {
+        a.rows_per_chunk = (int)(kBulkStageCap / row_bytes); a.segs = 1; a.seg_w = G.W;
+        a.n_chunks = ceil_div(rows, a.rows_per_chunk);
+      } else {
+        a.rows_per_chunk = 1; a.segs = (int)ceil_div_ll((long long)row_bytes, kBulkStageCap);
+        a.seg_w = ceil_div(G.W, a.segs); a.segs = ceil_div(G.W, a.seg_w);
+        a.n_chunks = rows * a.segs;
+      }
+      a.scale = scale; a.shift = shift; a.mean = mean; a.invstd = invstd; a.drop = drop; a.s1s2 = s1s2;
+      a.inv_count = 1.f / (float)((long long)G.N * G.H * G.W); a.training = training;
+      a.part = part; a.dy = dy;
+      const int pl = kBlock / (cp >> 3);
+      const size_t smem = (size_t)2 * kBulkStages * kBulkStageCap + kBulkStages * 8 + 64;
+      (void)pl;
+      static bool attr = false;
+      if (!attr) {
+        MIMO_CUDA(cudaFuncSetAttribute(bn_bwd_bulk_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        MIMO_CUDA(cudaFuncSetAttribute(bn_bwd_bulk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        attr = true;
+      }
+      int grid = 2 * num_sms();
+      if (grid > a.n_chunks) grid = a.n_chunks;
+      if (grid > bn_bwd_parts(C)) grid = bn_bwd_parts(C);
+      bn_bwd_bulk_kernel<0><<<grid, kBlock, smem, st>>>(a);
+      MIMO_LAUNCH_CHECK();
+      bn_bwd_finalize_kernel<<<ceil_div(C, 8), 256, 0, st>>>(part, grid, C, s1s2, dgamma, dbeta, dbias, scale, mean, invstd, training, grad_scale, accumulate);
+      MIMO_LAUNCH_CHECK();
+      bn_bwd_bulk_kernel<1><<<grid, kBlock, smem, st>>>(a);
+      MIMO_LAUNCH_CHECK();
+      return MIMO_OK;
+    }
+  }
   const int nparts = rows < bn_bwd_parts(C) ? rows : bn_bwd_parts(C);
   const int pix_lanes = kBlock / groups;
   const size_t sh_bytes = (size_t)pix_lanes * groups * 16 * sizeof(float);

@@ -63,6 +63,49 @@ __global__ void head_fwd_kernel(ActView f, const float* __restrict__ W, const fl
   }
 }
 
+// Fast path (K in {1, 2, 4}, 16-byte aligned feature view): one thread per pixel, the pixel's channels are read with
+// 16-byte loads, the weights sit in shared memory as [channel][K] so one LDS feeds K FMAs (the generic kernel above is
+// instruction-issue bound: scalar loads of the partial channel group, one LDS per FMA, 64-bit index math; ncu IPC 3.1).
+template <int K>
+__global__ void __launch_bounds__(256)
+head_fwd_fast_kernel(ActView f, const float* __restrict__ W, const float* __restrict__ bias, float* __restrict__ out,
+                     long long out_bstride) {
+  extern __shared__ float shw[];  // [groups*8][K], zero past C
+  const int C = f.C, groups = (C + 7) >> 3;
+  for (int i = threadIdx.x; i < groups * 8 * K; i += blockDim.x) {
+    const int c = i / K, k = i - c * K;
+    shw[i] = c < C ? W[k * C + c] : 0.f;
+  }
+  float b[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) b[k] = bias[k];
+  __syncthreads();
+  const uint4 tail_mask = group_mask(C - (groups - 1) * 8);
+  const unsigned HW = (unsigned)f.H * (unsigned)f.W, total = (unsigned)f.N * HW;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned n = i / HW, r = i - n * HW;
+    const unsigned h = r / (unsigned)f.W, w = r - h * (unsigned)f.W;
+    const uint4* src = reinterpret_cast<const uint4*>(f.base + f.pix((int)n, (int)h, (int)w));
+    float acc[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] = b[k];
+    for (int g = 0; g < groups; ++g) {
+      float v[8];
+      uint4 r = src[g];
+      if (g == groups - 1) r = and4(r, tail_mask);   // pad channels of the buffer may hold anything (0 * NaN)
+      unpack8(r, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[k] = fmaf(v[j], shw[(g * 8 + j) * K + k], acc[k]);
+      }
+    }
+    float* dst = out + (long long)n * out_bstride + r;
+#pragma unroll
+    for (int k = 0; k < K; ++k) dst[(size_t)k * HW] = acc[k];
+  }
+}
+
 // backward of the head: G[n,h,w,c] = gs * sum_k dOut[n,k,h,w] * W[k][c]  (bf16, unpadded NHWC)
 //                       dW[k][c]  (+)= gs * sum_pix dOut * feat ;  db[k] (+)= gs * sum_pix dOut
 // gs = *grad_scale (device scalar, e.g. the AMP loss scale) or 1.
@@ -211,13 +254,19 @@ head_bwd_fast_kernel(ActView f, const float* __restrict__ W, const float* __rest
 
 __global__ void head_bwd_finalize_kernel(const float* __restrict__ part, int nparts, int K, int C, float* __restrict__ dW,
                                          float* __restrict__ db, int accumulate) {
+  // one warp per entry: lanes stride over the partial rows (independent loads in flight), fixed-order butterfly
   const int pairs = K * C + K;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= pairs) return;
+  const int lane = threadIdx.x & 31;
   double a = 0.0;
-  for (int p = 0; p < nparts; ++p) a += part[(size_t)p * pairs + i];
-  float* dst = (i < K * C) ? dW + i : db + (i - K * C);
-  *dst = (accumulate ? *dst : 0.f) + (float)a;
+  for (int p = lane; p < nparts; p += 32) a += part[(size_t)p * pairs + i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if (lane == 0) {
+    float* dst = (i < K * C) ? dW + i : db + (i - K * C);
+    *dst = (accumulate ? *dst : 0.f) + (float)a;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -468,6 +517,79 @@ __global__ void aggregate_kernel(const float* __restrict__ p1, long long p1_bs, 
   }
 }
 
+// 16-byte variant: four consecutive output elements per thread. The epistemic variance uses the exact two-pass form
+// (sum of squared deviations from the mean); the second pass re-reads the members from L1/L2 when S exceeds the
+// register-resident limit, otherwise they stay in registers.
+template <int SREG>
+__global__ void __launch_bounds__(256)
+aggregate_vec4_kernel(const float* __restrict__ p1, long long p1_bs, long long p1_ss, const float* __restrict__ p2,
+                      long long p2_bs, long long p2_ss, int B, int S, long long inner4, float* __restrict__ mean,
+                      float* __restrict__ alea, float* __restrict__ epi) {
+  const long long total = (long long)B * inner4;
+  const float invS = 1.f / (float)S;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / inner4, j = (i - b * inner4) * 4;
+    const float* a = p1 + b * p1_bs + j;
+    const float* l = p2 + b * p2_bs + j;
+    float4 m = make_float4(0.f, 0.f, 0.f, 0.f), al = m, e = m;
+    if (SREG > 0) {
+      float4 va[SREG > 0 ? SREG : 1], vl[SREG > 0 ? SREG : 1];
+#pragma unroll
+      for (int s = 0; s < SREG; ++s) {
+        va[s] = __ldcs(reinterpret_cast<const float4*>(a + s * p1_ss));
+        vl[s] = __ldcs(reinterpret_cast<const float4*>(l + s * p2_ss));
+      }
+#pragma unroll
+      for (int s = 0; s < SREG; ++s) {
+        m.x += va[s].x; m.y += va[s].y; m.z += va[s].z; m.w += va[s].w;
+        // (exp(l) * sqrt2)^2 = 2 exp(l)^2, evaluated like the reference: std first, then squared
+        float sd;
+        sd = expf(vl[s].x) * 1.41421356237309515f; al.x += sd * sd;
+        sd = expf(vl[s].y) * 1.41421356237309515f; al.y += sd * sd;
+        sd = expf(vl[s].z) * 1.41421356237309515f; al.z += sd * sd;
+        sd = expf(vl[s].w) * 1.41421356237309515f; al.w += sd * sd;
+      }
+      m.x *= invS; m.y *= invS; m.z *= invS; m.w *= invS;
+      if (SREG > 1) {
+#pragma unroll
+        for (int s = 0; s < SREG; ++s) {
+          float d;
+          d = va[s].x - m.x; e.x += d * d; d = va[s].y - m.y; e.y += d * d;
+          d = va[s].z - m.z; e.z += d * d; d = va[s].w - m.w; e.w += d * d;
+        }
+        const float r = 1.f / (float)(SREG - 1);
+        e.x *= r; e.y *= r; e.z *= r; e.w *= r;
+      }
+    } else {
+      for (int s = 0; s < S; ++s) {
+        const float4 va = *reinterpret_cast<const float4*>(a + s * p1_ss);
+        const float4 vl = __ldcs(reinterpret_cast<const float4*>(l + s * p2_ss));
+        m.x += va.x; m.y += va.y; m.z += va.z; m.w += va.w;
+        float sd;
+        sd = expf(vl.x) * 1.41421356237309515f; al.x += sd * sd;
+        sd = expf(vl.y) * 1.41421356237309515f; al.y += sd * sd;
+        sd = expf(vl.z) * 1.41421356237309515f; al.z += sd * sd;
+        sd = expf(vl.w) * 1.41421356237309515f; al.w += sd * sd;
+      }
+      m.x *= invS; m.y *= invS; m.z *= invS; m.w *= invS;
+      if (S > 1) {
+        for (int s = 0; s < S; ++s) {
+          const float4 va = *reinterpret_cast<const float4*>(a + s * p1_ss);
+          float d;
+          d = va.x - m.x; e.x += d * d; d = va.y - m.y; e.y += d * d;
+          d = va.z - m.z; e.z += d * d; d = va.w - m.w; e.w += d * d;
+        }
+        const float r = 1.f / (float)(S - 1);
+        e.x *= r; e.y *= r; e.z *= r; e.w *= r;
+      }
+    }
+    al.x *= invS; al.y *= invS; al.z *= invS; al.w *= invS;
+    __stcs(reinterpret_cast<float4*>(mean + i * 4), m);
+    __stcs(reinterpret_cast<float4*>(alea + i * 4), al);
+    __stcs(reinterpret_cast<float4*>(epi + i * 4), e);
+  }
+}
+
 inline int grid_for(long long work, int per_thread = 1) {
   long long g = ceil_div_ll(work, (long long)kBlock * per_thread);
   const long long cap = (long long)num_sms() * 8;
@@ -482,6 +604,19 @@ inline int grid_for(long long work, int per_thread = 1) {
 int head_fwd_launch(const ActView& f, const float* W, const float* bias, int K, float* out, long long out_bstride, cudaStream_t st) {
   MIMO_CHECK(K >= 1 && K <= 8, MIMO_ERR_ARG, "head: out_channels must be in [1,8] (got %d)", K);
   const long long total = (long long)f.N * f.H * f.W;
+  {
+    const int groups = (f.C + 7) / 8;
+    const bool aligned = ((uintptr_t)f.base % 16) == 0 && f.cpitch % 8 == 0 && f.c_off % 8 == 0 && f.c_off + groups * 8 <= f.cpitch;
+    if (aligned && (K == 1 || K == 2 || K == 4) && total < (1ll << 31) && groups * 8 * K * sizeof(float) <= 40 * 1024) {
+      const size_t shb = (size_t)groups * 8 * K * sizeof(float);
+      const int grid = grid_for(total);
+      if (K == 1) head_fwd_fast_kernel<1><<<grid, kBlock, shb, st>>>(f, W, bias, out, out_bstride);
+      else if (K == 2) head_fwd_fast_kernel<2><<<grid, kBlock, shb, st>>>(f, W, bias, out, out_bstride);
+      else head_fwd_fast_kernel<4><<<grid, kBlock, shb, st>>>(f, W, bias, out, out_bstride);
+      MIMO_LAUNCH_CHECK();
+      return MIMO_OK;
+    }
+  }
   head_fwd_kernel<<<grid_for(total), kBlock, (K * f.C + K) * sizeof(float), st>>>(f, W, bias, K, out, out_bstride);
   MIMO_LAUNCH_CHECK();
   return MIMO_OK;
@@ -510,7 +645,7 @@ int head_bwd_launch(const ActView& f, const float* W, int K, const float* dout, 
         else if (K == 2) head_bwd_fast_kernel<2><<<grid, kBlock, shb, st>>>(f, W, dout, out_bstride, grad_scale, G, part);
         else head_bwd_fast_kernel<4><<<grid, kBlock, shb, st>>>(f, W, dout, out_bstride, grad_scale, G, part);
         MIMO_LAUNCH_CHECK();
-        head_bwd_finalize_kernel<<<ceil_div(K * f.C + K, 128), 128, 0, st>>>(part, grid, K, f.C, dW, db, accumulate);
+        head_bwd_finalize_kernel<<<ceil_div(K * f.C + K, 8), 256, 0, st>>>(part, grid, K, f.C, dW, db, accumulate);
         MIMO_LAUNCH_CHECK();
         return MIMO_OK;
       }
@@ -522,7 +657,7 @@ int head_bwd_launch(const ActView& f, const float* W, int K, const float* dout, 
   MIMO_CHECK(smem <= 160 * 1024, MIMO_ERR_ARG, "head_bwd: feature count too large for shared memory");
   head_bwd_kernel<<<nparts, kBlock, smem, st>>>(f, W, K, dout, out_bstride, grad_scale, G, part);
   MIMO_LAUNCH_CHECK();
-  head_bwd_finalize_kernel<<<ceil_div(K * f.C + K, 128), 128, 0, st>>>(part, nparts, K, f.C, dW, db, accumulate);
+  head_bwd_finalize_kernel<<<ceil_div(K * f.C + K, 8), 256, 0, st>>>(part, nparts, K, f.C, dW, db, accumulate);
   MIMO_LAUNCH_CHECK();
   return MIMO_OK;
 }
@@ -606,6 +741,24 @@ int scale_by_scalar_launch(float* x, long long n, const float* s, cudaStream_t s
 int aggregate_launch(const float* p1, long long p1_bs, long long p1_ss, const float* p2, long long p2_bs, long long p2_ss, int B,
                      int S, long long inner, float* mean, float* alea, float* epi, cudaStream_t st) {
   MIMO_CHECK(S >= 1, MIMO_ERR_ARG, "aggregate: S must be >= 1");
+  const bool vec = (inner % 4) == 0 && (p1_bs % 4) == 0 && (p1_ss % 4) == 0 && (p2_bs % 4) == 0 && (p2_ss % 4) == 0 &&
+                   (((uintptr_t)p1 | (uintptr_t)p2 | (uintptr_t)mean | (uintptr_t)alea | (uintptr_t)epi) % 16) == 0;
+  if (vec) {
+    const long long inner4 = inner / 4;
+    const int grid = grid_for((long long)B * inner4, 1);
+#define MIMO_AGG(SR) aggregate_vec4_kernel<SR><<<grid, kBlock, 0, st>>>(p1, p1_bs, p1_ss, p2, p2_bs, p2_ss, B, S, inner4, mean, alea, epi)
+    switch (S) {
+      case 1: MIMO_AGG(1); break;
+      case 2: MIMO_AGG(2); break;
+      case 3: MIMO_AGG(3); break;
+      case 4: MIMO_AGG(4); break;
+      case 8: MIMO_AGG(8); break;
+      default: MIMO_AGG(0); break;
+    }
+#undef MIMO_AGG
+    MIMO_LAUNCH_CHECK();
+    return MIMO_OK;
+  }
   aggregate_kernel<<<grid_for((long long)B * inner, 2), kBlock, 0, st>>>(p1, p1_bs, p1_ss, p2, p2_bs, p2_ss, B, S, inner, mean, alea, epi);
   MIMO_LAUNCH_CHECK();
   return MIMO_OK;

@@ -399,8 +399,19 @@ def test_grad_gather_fold_and_pool_bwd(lib, H, W):
 @pytest.mark.parametrize("dy_pad", [0, 2])
 @pytest.mark.parametrize("C_,c_off,gcp", [(21, 0, 24), (42, 42, 88), (336, 0, 336)])
 def test_bn_relu_bwd(lib, training, C_, c_off, gcp, dy_pad):
+    _bn_relu_bwd_case(lib, training, C_, c_off, gcp, dy_pad, 3, 6, 7)
+
+
+@pytest.mark.parametrize("training", [1, 0])
+@pytest.mark.parametrize("N,H,W,C_", [(4, 96, 160, 21), (2, 8, 400, 21), (2, 33, 70, 168), (5, 10, 12, 336), (1, 300, 37, 31)])
+def test_bn_relu_bwd_bulk_shapes(lib, training, N, H, W, C_):
+    """Dense operands take the cp.async.bulk pipelined kernels: many chunks per block, several rows per chunk, rows split into
+    segments (W = 400), ragged last chunks."""
+    _bn_relu_bwd_case(lib, training, C_, 0, p8(C_), 2, N, H, W)
+
+
+def _bn_relu_bwd_case(lib, training, C_, c_off, gcp, dy_pad, N, H, W):
     torch.manual_seed(8)
-    N, H, W = 3, 6, 7
     y = bf16r(torch.randn(N, C_, H, W, device="cuda") * 1.5 + 0.3)
     G = bf16r(torch.randn(N, C_, H, W, device="cuda"))
     gamma, beta = torch.rand(C_, device="cuda") + 0.5, torch.randn(C_, device="cuda") * 0.3
