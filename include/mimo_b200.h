@@ -117,6 +117,14 @@ int mimo_bn_relu_bwd(mimo_act_t g, const void* y, int y_cpitch, const float* sca
                      const float* save_mean, const float* save_invstd, const float* drop, int training, float* part,
                      float* s1s2, float* dgamma, float* dbeta, float* dbias, int accumulate, mimo_act_t dy, void* stream);
 
+/* Same, with the upstream gradient given as the padded-domain gradient `dpad` [N][H+2][W+2] of the following reflect-padded
+ * convolution (autograd of F.pad(mode="reflect") feeding conv2 of DoubleConv, components.py:23-27): G = fold_reflect(dpad) is
+ * formed inside the two passes when the operands are dense; otherwise it is materialised in `g_scratch` first. */
+int mimo_bn_relu_bwd_folded(mimo_act_t dpad, mimo_act_t g_scratch, const void* y, int y_cpitch, const float* scale,
+                            const float* shift, const float* save_mean, const float* save_invstd, const float* drop,
+                            int training, float* part, float* s1s2, float* dgamma, float* dbeta, float* dbias,
+                            int accumulate, mimo_act_t dy, void* stream);
+
 /* ------------------------------------------------------------------ heads / loss / aggregation ------------ */
 /* OutConv 1x1 (components.py:123-129): out fp32 planes, element (n,k,h,w) at out[n*out_bstride + k*h*w + ...] */
 int mimo_head1x1(mimo_act_t feat, const float* w, const float* bias, int k, float* out, long long out_bstride, void* stream);

@@ -12,7 +12,16 @@ def shuffle_indices(batch: int, num_subnetworks: int, input_repetition_probabili
     for every subnetwork with the CPU generator, the tail stays aligned across subnetworks."""
     main = torch.randperm(batch, device=device).repeat(batch_repetitions)
     k = int(main.shape[0] * (1.0 - input_repetition_probability))
-    return [torch.cat((main[:k][torch.randperm(k)], main[k:]), dim=0) for _ in range(num_subnetworks)]
+    out = []
+    for _ in range(num_subnetworks):
+        perm = torch.randperm(k)  # CPU generator, like the reference
+        if main.is_cuda:
+            # indexing a CUDA tensor with a pageable CPU index makes PyTorch copy it with a blocking cudaStreamSynchronize
+            # (twice per training step: the GPU drains while the host enqueues the next forward). Pinned + non_blocking
+            # keeps the step asynchronous; the values are identical.
+            perm = perm.pin_memory().to(main.device, non_blocking=True)
+        out.append(torch.cat((main[:k][perm], main[k:]), dim=0))
+    return out
 
 
 def apply_input_transform(image: torch.Tensor, label: torch.Tensor, mask: Optional[torch.Tensor], num_subnetworks: int,

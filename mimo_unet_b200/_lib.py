@@ -68,6 +68,7 @@ SIGNATURES = {
     "mimo_grad_gather": (i32, [ActP, ActP, ActP, Act, i32, vp]),
     "mimo_bn_bwd_scratch_floats": (sz, [i32]),
     "mimo_bn_relu_bwd": (i32, [Act, vp, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, i32, Act, vp]),
+    "mimo_bn_relu_bwd_folded": (i32, [Act, Act, vp, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, i32, Act, vp]),
     "mimo_head1x1": (i32, [Act, vp, vp, i32, vp, i64, vp]),
     "mimo_head1x1_bwd_scratch_floats": (sz, [i32, i32]),
     "mimo_head1x1_bwd": (i32, [Act, vp, i32, vp, i64, vp, Act, vp, vp, vp, i32, vp]),

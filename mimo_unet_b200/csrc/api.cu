@@ -125,6 +125,16 @@ int mimo_bn_relu_bwd(mimo_act_t g, const void* y, int y_cpitch, const float* sca
                        dbeta, dbias, 1.f, accumulate, make_view(dy), (cudaStream_t)stream);
 }
 
+int mimo_bn_relu_bwd_folded(mimo_act_t dpad, mimo_act_t g_scratch, const void* y, int y_cpitch, const float* scale, const float* shift,
+                            const float* save_mean, const float* save_invstd, const float* drop, int training, float* part, float* s1s2,
+                            float* dgamma, float* dbeta, float* dbias, int accumulate, mimo_act_t dy, void* stream) {
+  MIMO_CHECK(dpad.ptr && g_scratch.ptr && y && scale && shift && save_mean && save_invstd && part && s1s2 && dy.ptr, MIMO_ERR_ARG,
+             "bn_relu_bwd_folded: null pointer");
+  const ActView d = make_view(dpad);
+  return bn_bwd_launch(make_view(g_scratch), (const bf16*)y, y_cpitch, scale, shift, save_mean, save_invstd, drop, training, part, s1s2,
+                       dgamma, dbeta, dbias, 1.f, accumulate, make_view(dy), (cudaStream_t)stream, &d);
+}
+
 int mimo_head1x1(mimo_act_t feat, const float* w, const float* bias, int k, float* out, long long out_bstride, void* stream) {
   MIMO_CHECK(feat.ptr && w && bias && out, MIMO_ERR_ARG, "head1x1: null pointer");
   return head_fwd_launch(make_view(feat), w, bias, k, out, out_bstride, (cudaStream_t)stream);

@@ -373,12 +373,11 @@ upsample_fast_kernel(ActView in, ActView o, int off_h, int off_w) {
     const float ly = sy - y0;
     const bf16* r0 = in.base + in.pix(n, y0, 0) + c;
     const bf16* r1 = in.base + in.pix(n, y1, 0) + c;
-    for (int w0 = 0; w0 < o.W; w0 += lanes) {   // uniform trip count: the shuffles below need converged warps
-      const int w = w0 + pl;
-      const bool active = w < o.W && g < groups;
+    // bilinear sample of this thread's channel group at output column w (zero outside the up-sampled area / inactive lanes)
+    auto sample = [&](int w) -> uint4 {
       uint4 own = make_uint4(0, 0, 0, 0);
       const int x = w - off_w;
-      if (active && yin && x >= 0 && x < uw) {
+      if (w < o.W && g < groups && yin && x >= 0 && x < uw) {
         const float sx = rw * x;
         const int x0 = (int)sx, x1 = min(x0 + 1, in.W - 1);
         const float lx = sx - x0;
@@ -392,6 +391,10 @@ upsample_fast_kernel(ActView in, ActView o, int off_h, int off_w) {
           out[k] = (1.f - ly) * ((1.f - lx) * a[k] + lx * b[k]) + ly * ((1.f - lx) * cc[k] + lx * d[k]);
         own = pack8(out);
       }
+      return own;
+    };
+    // shuffle + funnel onto the buffer's 16-byte grid, then store the pixel and the halo cells that mirror it
+    auto emit = [&](int w, const uint4& own) {
       uint4 word = own;
       if (e != 0) {
         uint4 next;
@@ -402,7 +405,7 @@ upsample_fast_kernel(ActView in, ActView o, int off_h, int off_w) {
         if (g == GPP - 1) next = make_uint4(0, 0, 0, 0);  // the next lane belongs to another pixel
         word = funnel8(own, next, e);
       }
-      if (!active) continue;
+      if (!(w < o.W && g < groups)) return;
       // targets: the pixel itself + the halo cells that mirror it (outer two rings only)
       const int hh = (h == 1) ? -1 : ((h == o.H - 2) ? o.H : -2);
       const int ww = (w == 1) ? -1 : ((w == o.W - 2) ? o.W : -2);
@@ -431,6 +434,15 @@ upsample_fast_kernel(ActView in, ActView o, int off_h, int off_w) {
           }
         }
       }
+    };
+    // two pixels per thread and trip: eight independent 16-byte loads in flight (the kernel is load-latency bound otherwise);
+    // uniform trip count: the shuffles need converged warps
+    for (int w0 = 0; w0 < o.W; w0 += 2 * lanes) {
+      const int wa = w0 + pl, wb = wa + lanes;
+      const uint4 oa = sample(wa);
+      const uint4 ob = sample(wb);
+      emit(wa, oa);
+      emit(wb, ob);
     }
   }
 }
@@ -840,7 +852,9 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint
 }
 
 struct BulkArgs {
-  const bf16* G; const bf16* y;   // dense [rows][W][cp]
+  const bf16* G; const bf16* y;   // dense [rows][W][cp]; fold mode: G = padded-domain gradient [N][H+2][W+2][cp]
+  int fold;                       // 1: the upstream gradient is fold_reflect(G) (adjoint of the reflect halo), formed on the fly
+  int capG;                       // bytes of the G part of a stage
   int cp, C, W, H, rows;          // rows = N*H
   int rows_per_chunk, segs, seg_w, n_chunks;
   const float *scale, *shift, *mean, *invstd, *drop, *s1s2;
@@ -853,10 +867,10 @@ template <int MODE>
 __global__ void __launch_bounds__(256, 2)
 bn_bwd_bulk_kernel(const BulkArgs a) {
   extern __shared__ __align__(128) uint8_t bsm[];
-  uint8_t* sG = bsm;
-  uint8_t* sY = bsm + kBulkStages * kBulkStageCap;
-  uint64_t* full = reinterpret_cast<uint64_t*>(bsm + 2 * kBulkStages * kBulkStageCap);
-  float* red = reinterpret_cast<float*>(sG);   // MODE 0 epilogue: [pix_lanes][groups*16], aliases the (drained) ring
+  uint8_t* sY = bsm;
+  uint8_t* sG = bsm + kBulkStages * kBulkStageCap;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sG + (size_t)kBulkStages * a.capG);
+  float* red = reinterpret_cast<float*>(bsm);   // MODE 0 epilogue: [pix_lanes][groups*16], aliases the (drained) ring
   const int C = a.C, cp = a.cp, W = a.W;
   const int groups = cp >> 3;                 // whole pixels are streamed: pad channels are zero in G (dz = 0)
   const int pix_lanes = blockDim.x / groups;
@@ -865,14 +879,27 @@ bn_bwd_bulk_kernel(const BulkArgs a) {
   const bool lane_on = pl < pix_lanes;
   const size_t row_elems = (size_t)W * cp;
 
+  const uint32_t prow_bytes = (uint32_t)((W + 2) * cp * 2);   // fold mode: one padded-domain row
   auto issue = [&](int chunk, int stage) {   // one thread
+    if (a.fold) {
+      // chunk = image row (n, h): padded row h+1 (W+2 pixels) and, for h == 1 / h == H-2, the halo row 0 / H+1 that folds onto it
+      const int n = chunk / a.H, h = chunk - n * a.H;
+      const bf16* img = a.G + (size_t)n * (a.H + 2) * (W + 2) * cp;
+      const int extra = (h == 1) ? 0 : ((h == a.H - 2) ? a.H + 1 : -1);
+      const uint32_t ybytes = (uint32_t)(row_elems * 2);
+      mbar_arrive_expect_tx(&full[stage], prow_bytes * (extra >= 0 ? 2u : 1u) + ybytes);
+      bulk_load(sG + (size_t)stage * a.capG, img + (size_t)(h + 1) * (W + 2) * cp, prow_bytes, &full[stage]);
+      if (extra >= 0) bulk_load(sG + (size_t)stage * a.capG + prow_bytes, img + (size_t)extra * (W + 2) * cp, prow_bytes, &full[stage]);
+      bulk_load(sY + (size_t)stage * kBulkStageCap, a.y + (size_t)chunk * row_elems, ybytes, &full[stage]);
+      return;
+    }
     int row0, w0, npx_rows, npx_w;
     if (a.segs > 1) { row0 = chunk / a.segs; const int sg = chunk - row0 * a.segs; w0 = sg * a.seg_w; npx_w = min(a.seg_w, W - w0); npx_rows = 1; }
     else { row0 = chunk * a.rows_per_chunk; w0 = 0; npx_w = W; npx_rows = min(a.rows_per_chunk, a.rows - row0); }
     const uint32_t bytes = (uint32_t)((size_t)npx_rows * npx_w * cp * 2);
     const size_t off = (size_t)row0 * row_elems + (size_t)w0 * cp;
     mbar_arrive_expect_tx(&full[stage], 2 * bytes);
-    bulk_load(sG + (size_t)stage * kBulkStageCap, a.G + off, bytes, &full[stage]);
+    bulk_load(sG + (size_t)stage * a.capG, a.G + off, bytes, &full[stage]);
     bulk_load(sY + (size_t)stage * kBulkStageCap, a.y + off, bytes, &full[stage]);
   };
 
@@ -902,11 +929,12 @@ bn_bwd_bulk_kernel(const BulkArgs a) {
   for (int i = 0; i < my_n; ++i) {
     const int chunk = blockIdx.x + i * gridDim.x;
     int row0, w0, npx_rows, npx_w;
-    if (a.segs > 1) { row0 = chunk / a.segs; const int sg = chunk - row0 * a.segs; w0 = sg * a.seg_w; npx_w = min(a.seg_w, W - w0); npx_rows = 1; }
+    if (a.fold) { row0 = chunk; w0 = 0; npx_w = W; npx_rows = 1; }
+    else if (a.segs > 1) { row0 = chunk / a.segs; const int sg = chunk - row0 * a.segs; w0 = sg * a.seg_w; npx_w = min(a.seg_w, W - w0); npx_rows = 1; }
     else { row0 = chunk * a.rows_per_chunk; w0 = 0; npx_w = W; npx_rows = min(a.rows_per_chunk, a.rows - row0); }
     mbar_wait(&full[stage], phase);
     if (lane_on) {
-      const uint4* gs = reinterpret_cast<const uint4*>(sG + (size_t)stage * kBulkStageCap);
+      const uint4* gs = reinterpret_cast<const uint4*>(sG + (size_t)stage * a.capG);
       const uint4* ys = reinterpret_cast<const uint4*>(sY + (size_t)stage * kBulkStageCap);
       for (int rr = 0; rr < npx_rows; ++rr) {
         const int row = row0 + rr;
@@ -921,7 +949,36 @@ bn_bwd_bulk_kernel(const BulkArgs a) {
         const int base = rr * npx_w * groups + g;
         for (int w = pl; w < npx_w; w += pix_lanes) {
           float gv[8], yv[8], out[8];
-          unpack8(gs[base + w * groups], gv);
+          if (a.fold) {
+            // G(h, w) = dpad(h+1, w+1) + the halo cells that mirror onto (h, w): columns 0 / W+1 for w == 1 / W-2, and the
+            // whole extra row (with its own two corner columns) for h == 1 / H-2
+            unpack8(gs[(w + 1) * groups + g], gv);
+            const bool has_extra = (h == 1) || (h == a.H - 2);
+            const int wm = (w == 1) ? 0 : ((w == W - 2) ? W + 1 : -1);
+            const int wm2 = (W == 3 && w == 1) ? W + 1 : -1;
+            const int nrow = has_extra ? 2 : 1;
+            for (int r = 0; r < nrow; ++r) {
+              const uint4* rowp = gs + (size_t)r * (W + 2) * groups + g;
+              float t[8];
+              if (r == 1) {
+                unpack8(rowp[(w + 1) * groups], t);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) gv[k] += t[k];
+              }
+              if (wm >= 0) {
+                unpack8(rowp[wm * groups], t);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) gv[k] += t[k];
+              }
+              if (wm2 >= 0) {
+                unpack8(rowp[wm2 * groups], t);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) gv[k] += t[k];
+              }
+            }
+          } else {
+            unpack8(gs[base + w * groups], gv);
+          }
           unpack8(ys[base + w * groups], yv);
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
@@ -1167,7 +1224,7 @@ int bn_bwd_parts(int C) { (void)C; return 4 * num_sms(); }
 
 int bn_bwd_launch(const ActView& G, const bf16* y, int ycp, const float* scale, const float* shift, const float* mean,
                   const float* invstd, const float* drop, int training, float* part, float* s1s2, float* dgamma, float* dbeta,
-                  float* dbias, float grad_scale, int accumulate, const ActView& dy, cudaStream_t st) {
+                  float* dbias, float grad_scale, int accumulate, const ActView& dy, cudaStream_t st, const ActView* fold_src) {
   const int C = G.C;
   MIMO_CHECK(G.pad == 0, MIMO_ERR_ARG, "bn_bwd: G must be unpadded");
   MIMO_CHECK(dy.pad != 1 && dy.c_off == 0 && dy.N == G.N && dy.H == G.H && dy.W == G.W && dy.cpitch >= C && dy.cpitch % 8 == 0 &&
@@ -1178,36 +1235,52 @@ int bn_bwd_launch(const ActView& G, const bf16* y, int ycp, const float* scale, 
   MIMO_CHECK(groups <= kBlock, MIMO_ERR_ARG, "bn_bwd: too many channels (%d)", C);
   const int rows = G.N * G.H;
   {
-    // dense operands with one pitch: bulk-copy pipelined kernels (every full-resolution layer)
+    // dense operands with one pitch: bulk-copy pipelined kernels (every full-resolution layer). With `fold_src` the
+    // upstream gradient is fold_reflect(*fold_src) and is formed inside the two passes (no grad_fold launch, no G buffer).
     static const int bulk_on = getenv("MIMO_BN_BULK") ? atoi(getenv("MIMO_BN_BULK")) : 1;
-    const int cp = G.cpitch;
+    const int cp = round_up(C, 8);
     const size_t row_bytes = (size_t)G.W * cp * 2;
-    const bool dense = G.c_off == 0 && round_up(C, 8) == cp && ycp == cp && dy.cpitch == cp && ((uintptr_t)G.base % 16) == 0 &&
-                       (cp >> 3) <= kBlock && (size_t)G.N * G.H * G.W * cp < (1ull << 31);
-    if (bulk_on && dense) {
+    const size_t prow_bytes = (size_t)(G.W + 2) * cp * 2;
+    const bool common = bulk_on && ycp == cp && dy.cpitch == cp && (cp >> 3) <= kBlock && (size_t)G.N * (G.H + 2) * (G.W + 2) * cp < (1ull << 31);
+    bool fold = false;
+    if (fold_src) {
+      const ActView& d = *fold_src;
+      fold = common && d.pad == 0 && d.c_off == 0 && d.cpitch == cp && d.C == C && d.N == G.N && d.H == G.H + 2 && d.W == G.W + 2 &&
+             ((uintptr_t)d.base % 16) == 0 && G.H >= 4 && G.W >= 3 && row_bytes <= (size_t)kBulkStageCap && 2 * prow_bytes <= 50 * 1024;
+      if (!fold) {
+        int rc = grad_gather_launch(fold_src, nullptr, nullptr, G, 0, st);
+        if (rc) return rc;
+      }
+    }
+    const bool dense = common && G.c_off == 0 && G.cpitch == cp && ((uintptr_t)G.base % 16) == 0;
+    if (fold || dense) {
       BulkArgs a{};
-      a.G = G.base; a.y = y; a.cp = cp; a.C = C; a.W = G.W; a.H = G.H; a.rows = rows;
-      if (row_bytes <= (size_t)kBulkStageCap) {
+      a.fold = fold ? 1 : 0;
+      a.G = fold ? fold_src->base : G.base; a.y = y; a.cp = cp; a.C = C; a.W = G.W; a.H = G.H; a.rows = rows;
+      if (fold) {
+        a.rows_per_chunk = 1; a.segs = 1; a.seg_w = G.W; a.n_chunks = rows;
+        a.capG = round_up((int)(2 * prow_bytes), 128);
+      } else if (row_bytes <= (size_t)kBulkStageCap) {
         a.rows_per_chunk = (int)(kBulkStageCap / row_bytes); a.segs = 1; a.seg_w = G.W;
         a.n_chunks = ceil_div(rows, a.rows_per_chunk);
+        a.capG = kBulkStageCap;
       } else {
         a.rows_per_chunk = 1; a.segs = (int)ceil_div_ll((long long)row_bytes, kBulkStageCap);
         a.seg_w = ceil_div(G.W, a.segs); a.segs = ceil_div(G.W, a.seg_w);
         a.n_chunks = rows * a.segs;
+        a.capG = kBulkStageCap;
       }
       a.scale = scale; a.shift = shift; a.mean = mean; a.invstd = invstd; a.drop = drop; a.s1s2 = s1s2;
       a.inv_count = 1.f / (float)((long long)G.N * G.H * G.W); a.training = training;
       a.part = part; a.dy = dy;
-      const int pl = kBlock / (cp >> 3);
-      const size_t smem = (size_t)2 * kBulkStages * kBulkStageCap + kBulkStages * 8 + 64;
-      (void)pl;
+      const size_t smem = (size_t)kBulkStages * (kBulkStageCap + a.capG) + kBulkStages * 8 + 64;
       static bool attr = false;
       if (!attr) {
-        MIMO_CUDA(cudaFuncSetAttribute(bn_bwd_bulk_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        MIMO_CUDA(cudaFuncSetAttribute(bn_bwd_bulk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        MIMO_CUDA(cudaFuncSetAttribute(bn_bwd_bulk_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        MIMO_CUDA(cudaFuncSetAttribute(bn_bwd_bulk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr = true;
       }
-      int grid = 2 * num_sms();
+      int grid = (smem <= 112 * 1024 ? 2 : 1) * num_sms();
       if (grid > a.n_chunks) grid = a.n_chunks;
       if (grid > bn_bwd_parts(C)) grid = bn_bwd_parts(C);
       bn_bwd_bulk_kernel<0><<<grid, kBlock, smem, st>>>(a);

@@ -235,14 +235,14 @@ int node_forward(mimo_unet_plan* P, int ni, bool training, const float* drop, cu
 }
 
 int conv_bn_backward(mimo_unet_plan* P, ConvL& c, const ActView& G, const ActView& in, const float* drop, bool training,
-                     bool need_in_grad, int accumulate, cudaStream_t st) {
+                     bool need_in_grad, int accumulate, cudaStream_t st, const ActView* fold_src = nullptr) {
   float* vec = fptr(P, c.vec);
   float *scale = vec, *shift = vec + c.cout_p, *mean = vec + 2 * c.cout_p, *invstd = vec + 3 * c.cout_p, *s1s2 = vec + 4 * c.cout_p;
   const bf16* y = bptr(P, P->bufs[c.y].off);
   const ActView dyv = view_of(P, c.dy, 0, c.cout);
   RUN(kBnBwd, bn_bwd_launch(G, y, c.cout_p, scale, shift, mean, invstd, drop, training ? 1 : 0, fptr(P, c.bnpart), s1s2,
                     (float*)P->grads[c.state0 + 2], (float*)P->grads[c.state0 + 3], (float*)P->grads[c.state0 + 1], 1.f, accumulate,
-                    dyv, st));
+                    dyv, st, fold_src));
   ++P->launches; ++P->launches;  // bn_bwd is three kernels
   if (P->grads[c.state0] != nullptr) {
     RUN(kConvWgrad, conv3x3_wgrad_launch(dyv, in, fptr(P, c.dwp), c.cin_p, st));
@@ -265,9 +265,10 @@ int node_backward(mimo_unet_plan* P, int ni, bool training, const float* drop, i
   const ActView dpad2 = view_of(P, n.c2.dpad, 0, n.c2.cin);
   const ActView G1 = view_of(P, n.g1, 0, n.c1.cout);
   P->cur_tag = 2 * ni;
-  RUN(kGradGather, grad_gather_launch(&dpad2, nullptr, nullptr, G1, 0, st));
+  // G1 = fold_reflect(dpad2) is formed inside the BN-backward passes of c1 (bn_bwd_launch falls back to a grad_gather
+  // launch into G1 when the operands are not dense)
   const ActView in = view_of(P, n.in);
-  rc = conv_bn_backward(P, n.c1, G1, in, nullptr, training, n.need_in_grad, accumulate, st);
+  rc = conv_bn_backward(P, n.c1, G1, in, nullptr, training, n.need_in_grad, accumulate, st, &dpad2);
   P->cur_tag = -1;
   return rc;
 }

@@ -45,7 +45,9 @@ int unpack_nchw_launch(const ActView& in, float* out, cudaStream_t st);
 int bn_bwd_parts(int C);
 int bn_bwd_launch(const ActView& G, const bf16* y, int ycp, const float* scale, const float* shift, const float* mean,
                   const float* invstd, const float* drop, int training, float* part, float* s1s2, float* dgamma, float* dbeta,
-                  float* dbias, float grad_scale, int accumulate, const ActView& dy, cudaStream_t st);
+                  float* dbias, float grad_scale, int accumulate, const ActView& dy, cudaStream_t st, const ActView* fold_src = nullptr);
+// fold_src != nullptr: the upstream gradient is fold_reflect(*fold_src) (padded-domain gradient of the next conv); it is fused
+// into the two passes when the operands are dense, otherwise G is filled by grad_gather first (G is scratch in both cases).
 
 // ---- heads, loss, loss buffer, aggregation (head_loss.cu) ----
 int head_fwd_launch(const ActView& f, const float* W, const float* bias, int K, float* out, long long out_bstride, cudaStream_t st);
