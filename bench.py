@@ -154,6 +154,43 @@ def conv_flops_per_step(batch):
     return fprop, dgrad
 
 
+def infer_throughput(dev, batch=64, mc_steps=1, steps=10, warmup=3, M=4, f=21, H=128, W=160, from_host=False):
+    """C4 (BASELINE.json configs[3]): M=4 subnetworks with MC dropout 0.1, EnsembleModule.forward = forward of all members +
+    fused ensemble aggregation (mean, aleatoric, epistemic). Returns (MPix/s, ms per batch): MPix = B*H*W input pixels, not
+    multiplied by S or the MC steps."""
+    from mimo.models.ensemble import EnsembleModule
+    from mimo.models.mimo_unet import MimoUnetModel
+    torch.manual_seed(1)
+    m = MimoUnetModel(in_channels=3, out_channels=2, num_subnetworks=M, filter_base_count=f, center_dropout_rate=0.0,
+                      final_dropout_rate=0.0, encoder_dropout_rate=0.1, core_dropout_rate=0.1, decoder_dropout_rate=0.1,
+                      loss="laplace_nll", weight_decay=0.0, learning_rate=1e-3, seed=1, loss_buffer_size=10,
+                      loss_buffer_temperature=0.3).to(dev)
+    ens = EnsembleModule([], monte_carlo_steps=mc_steps, models=[m])
+    host = [torch.rand(batch, 3, H, W).pin_memory() for _ in range(2)]
+    xs = [h.to(dev) for h in host]
+    outs_host = [torch.empty(batch, 1, H, W).pin_memory() for _ in range(3)]
+
+    def run(n):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        with torch.no_grad():
+            for i in range(n):
+                x = host[i % 2].to(dev, non_blocking=True) if from_host else xs[i % 2]
+                mean, alea, epi = ens(x)
+                if from_host:
+                    for o, t in zip(outs_host, (mean, alea, epi)):
+                        o.copy_(t, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    run(warmup)
+    ms = run(steps) / steps
+    del ens, m
+    return batch * H * W / (ms * 1e-3) / 1e6, ms
+
+
 def run_gpu_arm(args):
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -273,6 +310,17 @@ def run_gpu_arm(args):
         cpu = {"value": sb / t, "unit": "images/s", "cores": threads, "kind": "port",
                "sample": f"oracle port (fp32, train step incl. Adam) on batch {sb} x 3x128x160, 1 warm-up + 2 timed steps, median"}
 
+    infer = None
+    if rank == 0 and world == 1 and not args.no_infer:
+        del dev_batches
+        torch.cuda.empty_cache()
+        infer = {"metric": "infer_mpix_per_sec", "unit": "MPix/s", "config": "C4 M=4 fbc=21 dropout 0.1 (MC dropout active), 3x128x160, EnsembleModule.forward incl. fused aggregation",
+                 "cases": []}
+        for (b, mc) in ((64, 1), (256, 1), (64, 8)):
+            v, t = infer_throughput(dev, batch=b, mc_steps=mc)
+            ve, te = infer_throughput(dev, batch=b, mc_steps=mc, from_host=True)
+            infer["cases"].append({"batch": b, "mc_steps": mc, "members": 4 * mc, "value": v, "ms_per_batch": t, "e2e_value": ve, "e2e_ms_per_batch": te})
+
     if rank == 0:
         total_images = B * world * args.steps
         h2d = (3 + 1) * B * H * W * 4
@@ -288,6 +336,7 @@ def run_gpu_arm(args):
             "clocks": clocks,
             "roofline": roof,
             "cpu_baseline": cpu,
+            "infer": infer,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -301,6 +350,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-infer", action="store_true", help="skip the secondary inference (MPix/s) measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
