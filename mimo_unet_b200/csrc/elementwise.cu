@@ -406,32 +406,35 @@ upsample_fast_kernel(ActView in, ActView o, int off_h, int off_w) {
         word = funnel8(own, next, e);
       }
       if (!(w < o.W && g < groups)) return;
-      // targets: the pixel itself + the halo cells that mirror it (outer two rings only)
+      const int valid = min(8, o.C - (c + e));  // view channels [c+e, c+e+8) carried by `word`
+      const bool word_vec = valid == 8 || (valid > 0 && last_slice && o.c_off + c + e + 8 <= o.cpitch);
+      auto put = [&](bf16* px) {
+        if (e == 0) {
+          store_group<true>(px + c, nv, own, tail_ok);
+        } else {
+          if (word_vec) *reinterpret_cast<uint4*>(px + c + e) = word;
+          else if (valid > 0) store_group<false>(px + c + e, valid, word);
+          if (g == 0) store_group<false>(px, min(e, o.C), own);  // leading channels [0, e) of the pixel
+        }
+      };
+      if (o.pad != 1 || (h > 1 && h < o.H - 2 && w > 1 && w < o.W - 2)) {   // interior: one target (the common case)
+        put(o.base + o.pix(n, h, w));
+        return;
+      }
+      // border: the pixel itself + the halo cells that mirror it (outer two rings only)
       const int hh = (h == 1) ? -1 : ((h == o.H - 2) ? o.H : -2);
       const int ww = (w == 1) ? -1 : ((w == o.W - 2) ? o.W : -2);
       const int hh2 = (o.H == 3 && h == 1) ? o.H : -2;
       const int ww2 = (o.W == 3 && w == 1) ? o.W : -2;
       const int hs[3] = {h, hh, hh2};
       const int ws[3] = {w, ww, ww2};
-      const bool border = o.pad == 1 && !(h > 1 && h < o.H - 2 && w > 1 && w < o.W - 2);
-#pragma unroll
+#pragma unroll 1
       for (int ai = 0; ai < 3; ++ai) {
-        if (hs[ai] == -2 || (ai > 0 && !border)) continue;
-#pragma unroll
+        if (hs[ai] == -2) continue;
+#pragma unroll 1
         for (int bi = 0; bi < 3; ++bi) {
-          if (ws[bi] == -2 || ((ai | bi) != 0 && !border)) continue;
-          bf16* px = o.base + o.pix(n, hs[ai], ws[bi]);
-          if (e == 0) {
-            store_group<true>(px + c, nv, own, tail_ok);
-          } else {
-            const int valid = min(8, o.C - (c + e));  // view channels [c+e, c+e+8) carried by `word`
-            if (valid == 8 || (valid > 0 && last_slice && o.c_off + c + e + 8 <= o.cpitch)) {
-              *reinterpret_cast<uint4*>(px + c + e) = word;
-            } else if (valid > 0) {
-              store_group<false>(px + c + e, valid, word);
-            }
-            if (g == 0) store_group<false>(px, min(e, o.C), own);  // leading channels [0, e) of the pixel
-          }
+          if (ws[bi] == -2) continue;
+          put(o.base + o.pix(n, hs[ai], ws[bi]));
         }
       }
     };
@@ -488,6 +491,72 @@ __global__ void upsample_bwd_kernel(ActView gdst /*unpadded, skip-sized*/, ActVi
         load8(gdst.base + gdst.pix(n, dh, dw) + c, nv, v);
 #pragma unroll
         for (int k = 0; k < 8; ++k) acc[k] += wy * wx * v[k];
+      }
+    }
+    bf16* dst = gsrc.base + gsrc.pix(n, sy, sx) + c;
+    if (accumulate) {
+      float old[8];
+      load8(dst, nv, old);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += old[k];
+    }
+    store8(dst, nv, acc);
+  }
+}
+
+// Same gather with the candidate window cut to the destination pixels that can have a non-zero weight
+// (|r * d - s| < 1 in both directions: at most 8 per direction for maps of 4+ pixels), the column weights hoisted out of
+// the row loop and 16-byte loads: the generic kernel above spends ~50 candidate iterations per source pixel on index
+// and weight arithmetic (ncu: issue-bound, IPC 3.1).
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+upsample_bwd_fast_kernel(ActView gdst, ActView gsrc, int off_h, int off_w, int accumulate) {
+  const int ih = gsrc.H, iw = gsrc.W, uh = 2 * ih, uw = 2 * iw;
+  const float rh = (float)(ih - 1) / (float)(uh - 1), rw = (float)(iw - 1) / (float)(uw - 1);
+  const float inv_rh = 1.f / rh, inv_rw = 1.f / rw;
+  const int groups = (gsrc.C + 7) >> 3;
+  const unsigned total = (unsigned)gsrc.N * ih * iw * groups;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned g = i % groups;
+    unsigned r = i / groups;
+    const int sx = (int)(r % iw); r /= iw;
+    const int sy = (int)(r % ih);
+    const int n = (int)(r / ih);
+    const int c = g * 8, nv = min(8, gsrc.C - c);
+    const uint4 mask = group_mask(nv);
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    const int ylo = max(0, (int)floorf((sy - 1) * inv_rh)), yhi = min(uh - 1, (int)ceilf((sy + 1) * inv_rh));
+    const int xlo = max(0, (int)floorf((sx - 1) * inv_rw)), xhi = min(uw - 1, (int)ceilf((sx + 1) * inv_rw));
+    float wxv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int x = xlo + j;
+      const float fx = rw * x;
+      const int x0 = (int)fx, x1 = min(x0 + 1, iw - 1);
+      const float lx = fx - x0;
+      const int dw = x + off_w;
+      const bool ok = x <= xhi && dw >= 0 && dw < gdst.W;
+      wxv[j] = ok ? ((x0 == sx ? 1.f - lx : 0.f) + (x1 == sx ? lx : 0.f)) : 0.f;
+    }
+    for (int y = ylo; y <= yhi; ++y) {
+      const float fy = rh * y;
+      const int y0 = (int)fy, y1 = min(y0 + 1, ih - 1);
+      const float ly = fy - y0;
+      const float wy = (y0 == sy ? 1.f - ly : 0.f) + (y1 == sy ? ly : 0.f);
+      const int dh = y + off_h;
+      if (wy == 0.f || dh < 0 || dh >= gdst.H) continue;
+      const bf16* rowp = gdst.base + gdst.pix(n, dh, xlo + off_w) + c;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (wxv[j] != 0.f) {
+          float v[8];
+          unpack8(load_group<VEC>(rowp + (size_t)j * gdst.cpitch, nv, mask), v);
+          const float w = wy * wxv[j];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[k] = fmaf(w, v[k], acc[k]);
+        }
       }
     }
     bf16* dst = gsrc.base + gsrc.pix(n, sy, sx) + c;
@@ -1189,6 +1258,12 @@ int upsample_bwd_launch(const ActView& gdst, const ActView& gsrc, int accumulate
   const int dY = gdst.H - 2 * gsrc.H, dX = gdst.W - 2 * gsrc.W;
   MIMO_CHECK(dY >= 0 && dX >= 0, MIMO_ERR_ARG, "upsample_bwd: bad sizes");
   const long long total = (long long)gsrc.N * gsrc.H * gsrc.W * ((gsrc.C + 7) / 8);
+  if (gsrc.H >= 4 && gsrc.W >= 4 && total < (1ll << 31)) {   // candidate window <= 8 destination pixels per direction
+    if (view_vec_ok(gdst)) upsample_bwd_fast_kernel<true><<<grid_for(total), kBlock, 0, st>>>(gdst, gsrc, dY / 2, dX / 2, accumulate);
+    else upsample_bwd_fast_kernel<false><<<grid_for(total), kBlock, 0, st>>>(gdst, gsrc, dY / 2, dX / 2, accumulate);
+    MIMO_LAUNCH_CHECK();
+    return MIMO_OK;
+  }
   upsample_bwd_kernel<<<grid_for(total), kBlock, 0, st>>>(gdst, gsrc, dY / 2, dX / 2, accumulate);
   MIMO_LAUNCH_CHECK();
   return MIMO_OK;

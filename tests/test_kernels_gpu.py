@@ -342,6 +342,27 @@ def test_upsample_fwd_bwd(lib, golden_dir):
     assert rel_l2(get_nchw(ob, 1, 0, Cc), g["y"].cuda()) <= 6e-3
 
 
+@pytest.mark.parametrize("N,C_,H,W,OH,OW", [(2, 42, 16, 20, 32, 40), (1, 84, 8, 10, 17, 21), (2, 21, 5, 7, 10, 15), (1, 336, 4, 5, 8, 10),
+                                            (2, 13, 33, 4, 66, 9), (1, 8, 2, 3, 4, 6)])
+def test_upsample_bwd_shapes(lib, N, C_, H, W, OH, OW):
+    """Bilinear x2 (align_corners) backward in gather form against autograd, incl. the zero-padded odd skip sizes; maps of
+    4+ pixels take the windowed kernel, smaller ones the generic one."""
+    torch.manual_seed(12)
+    x = bf16r(torch.randn(N, C_, H, W, device="cuda"))
+    gdst = bf16r(torch.randn(N, C_, OH, OW, device="cuda"))
+    gb = make_buffer(N, OH, OW, 0, p8(C_), fill=0.0)
+    put_nchw(gb, gdst, 0)
+    gs = make_buffer(N, H, W, 0, p8(C_))
+    _lib.check(lib.mimo_upsample_bilinear2x_bwd(act_of(gb, 0, 0, C_), act_of(gs, 0, 0, C_), 0, stream()))
+    xg = x.clone().requires_grad_(True)
+    O.pad_to(O.upsample_bilinear2x_ac(xg), OH, OW).backward(gdst)
+    assert rel_l2(get_nchw(gs, 0, 0, C_), bf16r(xg.grad)) <= TOL
+    # accumulate mode adds onto what is there (the stored bf16 value)
+    before = get_nchw(gs, 0, 0, C_).clone()
+    _lib.check(lib.mimo_upsample_bilinear2x_bwd(act_of(gb, 0, 0, C_), act_of(gs, 0, 0, C_), 1, stream()))
+    assert rel_l2(get_nchw(gs, 0, 0, C_), bf16r(before + xg.grad)) <= 3e-3
+
+
 @pytest.mark.parametrize("C_,c_off,cpitch", [(42, 21, 64), (42, 0, 48), (84, 84, 168), (5, 10, 24), (21, 3, 24), (168, 168, 336)])
 def test_upsample_into_concat_slice(lib, C_, c_off, cpitch):
     """Decoder / core concat geometry: the up-sampled map lands in a channel slice whose offset need not be a multiple
@@ -468,7 +489,7 @@ def _bn_relu_bwd_case(lib, training, C_, c_off, gcp, dy_pad, N, H, W, folded=Fal
     assert torch.all(dyb[:, H:] == 0) and torch.all(dyb[:, :, W:] == 0)  # the zero tail is never written
     dyb = dyb[:, :H, :W].contiguous()
     assert rel_l2(get_nchw(dyb, 0, 0, C_), bf16r(yq.grad)) <= tol
-    assert rel_l2(dgamma, gq.grad) <= max(1e-4, tol / 4) and rel_l2(dbeta, bq.grad) <= max(1e-4, tol / 4)
+    assert rel_l2(dgamma, gq.grad) <= (1e-4 if tol <= TOL else tol / 2) and rel_l2(dbeta, bq.grad) <= (1e-4 if tol <= TOL else tol / 2)
     if training:
         assert torch.all(dbias == 0)
     else:
