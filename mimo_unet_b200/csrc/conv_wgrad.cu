@@ -189,19 +189,37 @@ __global__ void wgrad_unpack_kernel(const float* __restrict__ packed, float* __r
   }
 }
 
+constexpr int kMaxBatchJobs = 48;
+struct UnpackBatch { WgradUnpackJob job[kMaxBatchJobs]; int first_block[kMaxBatchJobs + 1]; int n; };
+
+__global__ void wgrad_unpack_batched_kernel(const UnpackBatch b, float scale, int accumulate) {
+  int j = 0;
+  while (j + 1 < b.n && (int)blockIdx.x >= b.first_block[j + 1]) ++j;
+  const WgradUnpackJob& q = b.job[j];
+  const int nblk = b.first_block[j + 1] - b.first_block[j];
+  const int total = q.cout * q.cin * 9;
+  for (int i = ((int)blockIdx.x - b.first_block[j]) * blockDim.x + threadIdx.x; i < total; i += nblk * blockDim.x) {
+    const int tap = i % 9;
+    const int ci = (i / 9) % q.cin;
+    const int co = i / (9 * q.cin);
+    const float v = q.packed[((size_t)tap * q.cout + co) * q.cin_pitch + ci] * scale;
+    q.grad[i] = accumulate ? q.grad[i] + v : v;
+  }
+}
+
 }  // namespace
 
 // dy     : unpadded view [N][H][W][cout...]           (pad == 0, c_off % 8 == 0)
 // x      : padded activation view [N][H+2][W+2][cin]   (pad == 1, c_off % 8 == 0)
 // dw     : fp32 [9][cout][cin_pitch], cin_pitch % 4 == 0; zeroed here before accumulation
-int conv3x3_wgrad_launch(const ActView& dy, const ActView& x, float* dw, int cin_pitch, cudaStream_t stream) {
+int conv3x3_wgrad_launch(const ActView& dy, const ActView& x, float* dw, int cin_pitch, cudaStream_t stream, bool pre_zeroed) {
   MIMO_CHECK((dy.pad == 0 || dy.pad == 2) && x.pad == 1, MIMO_ERR_ARG, "wgrad: dy must be dense or zero-tailed and x haloed");
   MIMO_CHECK(dy.N == x.N && dy.H == x.H && dy.W == x.W, MIMO_ERR_ARG, "wgrad: dy/x shape mismatch");
   MIMO_CHECK(dy.cpitch % 8 == 0 && dy.c_off % 8 == 0 && x.cpitch % 8 == 0 && x.c_off % 8 == 0, MIMO_ERR_ALIGN,
              "wgrad: channel pitch/offset must be multiples of 8");
   MIMO_CHECK(cin_pitch % 4 == 0 && cin_pitch >= x.C, MIMO_ERR_ALIGN, "wgrad: cin_pitch %d invalid", cin_pitch);
-  if (conv3x3_wgrad_flat_ok(dy, x)) return conv3x3_wgrad_flat_launch(dy, x, dw, cin_pitch, stream);
-  if (conv3x3_wgrad_flatk_ok(dy, x)) return conv3x3_wgrad_flatk_launch(dy, x, dw, cin_pitch, stream);
+  if (conv3x3_wgrad_flat_ok(dy, x)) return conv3x3_wgrad_flat_launch(dy, x, dw, cin_pitch, stream, pre_zeroed);
+  if (conv3x3_wgrad_flatk_ok(dy, x)) return conv3x3_wgrad_flatk_launch(dy, x, dw, cin_pitch, stream, pre_zeroed);
   WgradParams p{};
   p.n_img = dy.N; p.H = dy.H; p.W = dy.W;
   pick_tile64(p.W, p.H, p.n_img, &p.tw, &p.th, &p.tn);
@@ -237,7 +255,7 @@ int conv3x3_wgrad_launch(const ActView& dy, const ActView& x, float* dw, int cin
     int rc = encode_tmap_bf16(&tm_x, x.base + x.c_off, 4, dims, strides, box, 1);
     if (rc) return rc;
   }
-  MIMO_CUDA(cudaMemsetAsync(dw, 0, (size_t)9 * p.cout * cin_pitch * sizeof(float), stream));
+  if (!pre_zeroed) MIMO_CUDA(cudaMemsetAsync(dw, 0, (size_t)9 * p.cout * cin_pitch * sizeof(float), stream));
   static bool attr_set = false;
   const size_t smem_bytes = (size_t)kStages * kStageBytes + (2 * kStages + 1) * 8 + 16 + 1024;
   if (!attr_set) {
@@ -258,6 +276,25 @@ int wgrad_unpack_launch(const float* packed, float* grad_oihw, int cout, int cin
   if (grid > 4 * num_sms()) grid = 4 * num_sms();
   wgrad_unpack_kernel<<<grid, block, 0, stream>>>(packed, grad_oihw, cout, cin, cin_pitch, scale, accumulate);
   MIMO_LAUNCH_CHECK();
+  return MIMO_OK;
+}
+
+int wgrad_unpack_batched_launch(const WgradUnpackJob* jobs, int n, float scale, int accumulate, cudaStream_t stream) {
+  for (int base = 0; base < n; base += kMaxBatchJobs) {
+    UnpackBatch b{};
+    b.n = n - base < kMaxBatchJobs ? n - base : kMaxBatchJobs;
+    int blocks = 0;
+    for (int j = 0; j < b.n; ++j) {
+      b.job[j] = jobs[base + j];
+      b.first_block[j] = blocks;
+      int nb = ceil_div(jobs[base + j].cout * jobs[base + j].cin * 9, 256 * 4);
+      if (nb > num_sms()) nb = num_sms();
+      blocks += nb < 1 ? 1 : nb;
+    }
+    b.first_block[b.n] = blocks;
+    wgrad_unpack_batched_kernel<<<blocks, 256, 0, stream>>>(b, scale, accumulate);
+    MIMO_LAUNCH_CHECK();
+  }
   return MIMO_OK;
 }
 

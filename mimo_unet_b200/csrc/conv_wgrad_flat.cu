@@ -214,7 +214,7 @@ bool conv3x3_wgrad_flat_ok(const ActView& dy, const ActView& x) {
   return wg_plan_slots(ceil_div(2 * x.wb() + 131, 128), &smem) > 0;
 }
 
-int conv3x3_wgrad_flat_launch(const ActView& dy, const ActView& x, float* dw, int cin_pitch, cudaStream_t stream) {
+int conv3x3_wgrad_flat_launch(const ActView& dy, const ActView& x, float* dw, int cin_pitch, cudaStream_t stream, bool pre_zeroed) {
   WgFlatParams p{};
   p.wb = x.wb();
   const long long total_pos = (long long)x.N * x.hb() * x.wb();
@@ -244,7 +244,7 @@ int conv3x3_wgrad_flat_launch(const ActView& dy, const ActView& x, float* dw, in
     int rc = encode_tmap_bf16(&tm_x, x.base + x.c_off, 2, dims, strides, box, 1);
     if (rc) return rc;
   }
-  MIMO_CUDA(cudaMemsetAsync(dw, 0, (size_t)9 * p.cout * cin_pitch * sizeof(float), stream));
+  if (!pre_zeroed) MIMO_CUDA(cudaMemsetAsync(dw, 0, (size_t)9 * p.cout * cin_pitch * sizeof(float), stream));
   static bool attr_set = false;
   if (!attr_set) {
     MIMO_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -253,7 +253,7 @@ bool conv3x3_wgrad_flatk_ok(const ActView& dy, const ActView& x) {
 }
 
 // dy: zero-tail view (pad == 2), x: haloed view (pad == 1), both with c_off % 8 == 0; cin_pitch % 4 == 0
-int conv3x3_wgrad_flatk_launch(const ActView& dy, const ActView& x, float* dw, int cin_pitch, cudaStream_t stream) {
+int conv3x3_wgrad_flatk_launch(const ActView& dy, const ActView& x, float* dw, int cin_pitch, cudaStream_t stream, bool pre_zeroed) {
   WgFlatKParams p{};
   p.wb = x.wb();
   const long long total_pos = (long long)x.N * x.hb() * x.wb();
@@ -287,7 +287,7 @@ int conv3x3_wgrad_flatk_launch(const ActView& dy, const ActView& x, float* dw, i
     if (rc) return rc;
   }
   p.ko = getenv("MIMO_WGK_KO") ? atoi(getenv("MIMO_WGK_KO")) : 0;
-  if (!(p.ko & 2)) MIMO_CUDA(cudaMemsetAsync(dw, 0, (size_t)9 * p.cout * cin_pitch * sizeof(float), stream));
+  if (!(p.ko & 2) && !pre_zeroed) MIMO_CUDA(cudaMemsetAsync(dw, 0, (size_t)9 * p.cout * cin_pitch * sizeof(float), stream));
   const size_t smem_bytes = (size_t)kStages * kStageBytes + (2 * kStages + 2) * 8 + 16 + 1024;
   static bool attr_set = false;
   if (!attr_set) {

@@ -125,6 +125,30 @@ __global__ void weight_pack_kernel(const float* __restrict__ w, int cout, int ci
   }
 }
 
+constexpr int kMaxPackJobs = 48;
+struct PackBatch { WeightPackJob job[kMaxPackJobs]; int first_block[kMaxPackJobs + 1]; int n; };
+
+// all layers of the network in one launch: block ranges per layer, same element math as weight_pack_kernel
+__global__ void weight_pack_batched_kernel(const PackBatch b) {
+  int j = 0;
+  while (j + 1 < b.n && (int)blockIdx.x >= b.first_block[j + 1]) ++j;
+  const WeightPackJob& q = b.job[j];
+  const int nblk = b.first_block[j + 1] - b.first_block[j];
+  const int cout = q.cout, cin = q.cin, cin_pitch = q.cin_pitch, cout_pitch = q.cout_pitch;
+  const int total_f = 9 * cout * cin_pitch;
+  const int total_d = q.wd ? 9 * cin * cout_pitch : 0;
+  for (int i = ((int)blockIdx.x - b.first_block[j]) * blockDim.x + threadIdx.x; i < total_f + total_d; i += nblk * blockDim.x) {
+    if (i < total_f) {
+      const int ci = i % cin_pitch, co = (i / cin_pitch) % cout, tap = i / (cin_pitch * cout);
+      q.wf[i] = __float2bfloat16_rn(ci < cin ? q.w[((size_t)co * cin + ci) * 9 + tap] : 0.f);
+    } else {
+      const int k = i - total_f;
+      const int co = k % cout_pitch, ci = (k / cout_pitch) % cin, tap = k / (cout_pitch * cin);
+      q.wd[k] = __float2bfloat16_rn(co < cout ? q.w[((size_t)co * cin + ci) * 9 + (8 - tap)] : 0.f);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // BatchNorm statistics finalize (training): reduce per-tile partials, produce scale/shift, saved mean /
 // invstd for backward, and update the running estimates (momentum 0.1, unbiased running variance,
@@ -1016,33 +1040,36 @@ bn_bwd_bulk_kernel(const BulkArgs a) {
         bf16* dp = nullptr;
         if (MODE == 1) dp = a.dy.base + a.dy.pix(n, h, w0) + c;
         const int base = rr * npx_w * groups + g;
+        const bool has_extra = a.fold && ((h == 1) || (h == a.H - 2));
         for (int w = pl; w < npx_w; w += pix_lanes) {
           float gv[8], yv[8], out[8];
           if (a.fold) {
             // G(h, w) = dpad(h+1, w+1) + the halo cells that mirror onto (h, w): columns 0 / W+1 for w == 1 / W-2, and the
-            // whole extra row (with its own two corner columns) for h == 1 / H-2
+            // whole extra row (with its own two corner columns) for h == 1 / H-2. Interior pixels take the first load only.
             unpack8(gs[(w + 1) * groups + g], gv);
-            const bool has_extra = (h == 1) || (h == a.H - 2);
-            const int wm = (w == 1) ? 0 : ((w == W - 2) ? W + 1 : -1);
-            const int wm2 = (W == 3 && w == 1) ? W + 1 : -1;
-            const int nrow = has_extra ? 2 : 1;
-            for (int r = 0; r < nrow; ++r) {
-              const uint4* rowp = gs + (size_t)r * (W + 2) * groups + g;
-              float t[8];
-              if (r == 1) {
-                unpack8(rowp[(w + 1) * groups], t);
+            const bool edge_w = (w == 1) || (w == W - 2);
+            if (has_extra || edge_w) {
+              const int wm = (w == 1) ? 0 : ((w == W - 2) ? W + 1 : -1);
+              const int wm2 = (W == 3 && w == 1) ? W + 1 : -1;
+              const int nrow = has_extra ? 2 : 1;
+              for (int r = 0; r < nrow; ++r) {
+                const uint4* rowp = gs + (size_t)r * (W + 2) * groups + g;
+                float t[8];
+                if (r == 1) {
+                  unpack8(rowp[(w + 1) * groups], t);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) gv[k] += t[k];
-              }
-              if (wm >= 0) {
-                unpack8(rowp[wm * groups], t);
+                  for (int k = 0; k < 8; ++k) gv[k] += t[k];
+                }
+                if (wm >= 0) {
+                  unpack8(rowp[wm * groups], t);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) gv[k] += t[k];
-              }
-              if (wm2 >= 0) {
-                unpack8(rowp[wm2 * groups], t);
+                  for (int k = 0; k < 8; ++k) gv[k] += t[k];
+                }
+                if (wm2 >= 0) {
+                  unpack8(rowp[wm2 * groups], t);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) gv[k] += t[k];
+                  for (int k = 0; k < 8; ++k) gv[k] += t[k];
+                }
               }
             }
           } else {
@@ -1181,6 +1208,27 @@ int weight_pack_launch(const float* w, int cout, int cin, bf16* wf, int cin_pitc
   const long long total = 9LL * cout * cin_pitch + (wd ? 9LL * cin * cout_pitch : 0);
   weight_pack_kernel<<<grid_for(total), kBlock, 0, st>>>(w, cout, cin, wf, cin_pitch, wd, cout_pitch);
   MIMO_LAUNCH_CHECK();
+  return MIMO_OK;
+}
+
+int weight_pack_batched_launch(const WeightPackJob* jobs, int n, cudaStream_t st) {
+  for (int base = 0; base < n; base += kMaxPackJobs) {
+    PackBatch b{};
+    b.n = n - base < kMaxPackJobs ? n - base : kMaxPackJobs;
+    int blocks = 0;
+    for (int j = 0; j < b.n; ++j) {
+      const WeightPackJob& q = jobs[base + j];
+      b.job[j] = q;
+      b.first_block[j] = blocks;
+      const long long total = 9LL * q.cout * q.cin_pitch + (q.wd ? 9LL * q.cin * q.cout_pitch : 0);
+      int nb = (int)ceil_div_ll(total, kBlock * 4);
+      if (nb > 2 * num_sms()) nb = 2 * num_sms();
+      blocks += nb < 1 ? 1 : nb;
+    }
+    b.first_block[b.n] = blocks;
+    weight_pack_batched_kernel<<<blocks, kBlock, 0, st>>>(b);
+    MIMO_LAUNCH_CHECK();
+  }
   return MIMO_OK;
 }
 

@@ -79,6 +79,8 @@ struct mimo_unet_plan {
   int tmp0 = -1, tmp1 = -1, tmp2 = -1, tmp3 = -1;  // folded upsample-branch gradients per level
   std::vector<int> g_feat, g_x1;         // per subnetwork
   size_t head_part = 0;
+  size_t dwp_begin = 0, dwp_end = 0;
+  std::vector<WgradUnpackJob> unpack_jobs;   // pending weight-gradient transposes of the current backward stage
   int head_state0 = -1;
   int n_state = 0;
   size_t ws_bytes = 0;
@@ -137,7 +139,6 @@ void setup_conv(mimo_unet_plan* P, Arena& A, ConvL& c, int cin, int cout, int N,
   c.psq = A.take((size_t)c.m_tiles * c.cout_p * sizeof(float));
   c.vec = A.take((size_t)6 * c.cout_p * sizeof(float));
   c.bnpart = A.take((size_t)bn_bwd_parts(cout) * 2 * cout * sizeof(float));
-  c.dwp = A.take((size_t)9 * cout * c.cin_p * sizeof(float));
   c.y = add_buf(P, A, N, H, W, 0, cout);
   c.dy = add_buf(P, A, N, H, W, 2, cout);  // zero-tail layout: read by the flat dgrad / wgrad kernels
   c.dpad = add_buf(P, A, N, H + 2, W + 2, 0, cin);
@@ -192,8 +193,6 @@ bf16* bptr(const mimo_unet_plan* P, size_t off) { return reinterpret_cast<bf16*>
 
 int conv_bn_forward(mimo_unet_plan* P, ConvL& c, const ActView& in, const ActView& out, const ActView* pool, const float* drop,
                     bool training, cudaStream_t st) {
-  const float* w = (const float*)P->state[c.state0];
-  RUN(kPackW, weight_pack_launch(w, c.cout, c.cin, bptr(P, c.wf), c.cin_p, bptr(P, c.wd), c.cout_p, st));
   bf16* y = reinterpret_cast<bf16*>(P->ws + P->bufs[c.y].off);
   float* vec = fptr(P, c.vec);
   float *scale = vec, *shift = vec + c.cout_p, *mean = vec + 2 * c.cout_p, *invstd = vec + 3 * c.cout_p;
@@ -245,8 +244,8 @@ int conv_bn_backward(mimo_unet_plan* P, ConvL& c, const ActView& G, const ActVie
                     dyv, st, fold_src));
   ++P->launches; ++P->launches;  // bn_bwd is three kernels
   if (P->grads[c.state0] != nullptr) {
-    RUN(kConvWgrad, conv3x3_wgrad_launch(dyv, in, fptr(P, c.dwp), c.cin_p, st));
-    RUN(kWgradUnpack, wgrad_unpack_launch(fptr(P, c.dwp), (float*)P->grads[c.state0], c.cout, c.cin, c.cin_p, 1.f, accumulate, st));
+    RUN(kConvWgrad, conv3x3_wgrad_launch(dyv, in, fptr(P, c.dwp), c.cin_p, st, true));
+    P->unpack_jobs.push_back({fptr(P, c.dwp), (float*)P->grads[c.state0], c.cout, c.cin, c.cin_p});  // flushed per stage
   }
   if (need_in_grad) {
     bf16* dpad = bptr(P, P->bufs[c.dpad].off);
@@ -374,6 +373,11 @@ int mimo_unet_plan_create(const mimo_unet_config_t* cfg, mimo_unet_plan_t** out)
   P->head_state0 = cur;
   cur += 2 * S;
   P->n_state = cur;
+  // packed fp32 weight gradients of all layers in ONE contiguous range: cleared by a single memset per backward pass
+  P->dwp_begin = A.take(0);
+  for (auto& n : P->nodes)
+    for (ConvL* cl : {&n.c1, &n.c2}) cl->dwp = A.take((size_t)9 * cl->cout * cl->cin_p * sizeof(float));
+  P->dwp_end = A.off;
   P->head_part = A.take((size_t)head_bwd_parts() * (cfg->out_channels * f + cfg->out_channels) * sizeof(float));
   P->ws_bytes = A.off + 256;
   *out = P;
@@ -470,6 +474,13 @@ int mimo_unet_forward(mimo_unet_plan_t* P, const float* x, const long long* gath
   auto mask = [&](int ni) { return P->masks_copy[ni]; };
   const bool tr = training != 0;
 
+  {  // bf16 weight packs of every layer (fprop layout + flipped dgrad layout): one launch
+    std::vector<WeightPackJob> jobs;
+    for (auto& n : P->nodes)
+      for (ConvL* cl : {&n.c1, &n.c2})
+        jobs.push_back({(const float*)P->state[cl->state0], bptr(P, cl->wf), bptr(P, cl->wd), cl->cout, cl->cin, cl->cin_p, cl->cout_p});
+    RUN(kPackW, weight_pack_batched_launch(jobs.data(), (int)jobs.size(), st));
+  }
   for (int s = 0; s < S; ++s) {
     const ActView xin = view_of(P, P->xin[s], 0, Cin);
     // with a gather table x is the un-shuffled batch [B][Cin][H][W] shared by all subnetworks
@@ -523,6 +534,15 @@ int mimo_unet_backward(mimo_unet_plan_t* P, const float* dout, const float* grad
       for (ConvL* c : {&n.c1, &n.c2}) MIMO_CUDA(cudaMemsetAsync(P->ws + P->bufs[c->dy].off, 0, P->bufs[c->dy].bytes(), st));
     P->dy_tails_zeroed = true;
   }
+  MIMO_CUDA(cudaMemsetAsync(P->ws + P->dwp_begin, 0, P->dwp_end - P->dwp_begin, st));
+  P->unpack_jobs.clear();
+  // packed [9][cout][cin] -> OIHW .grad of every layer of a stage in one launch, right before the stage's event
+  auto flush_unpack = [&]() -> int {
+    if (P->unpack_jobs.empty()) return MIMO_OK;
+    RUN(kWgradUnpack, wgrad_unpack_batched_launch(P->unpack_jobs.data(), (int)P->unpack_jobs.size(), 1.f, accumulate, st));
+    P->unpack_jobs.clear();
+    return MIMO_OK;
+  };
 
   // ---- decoders ----
   for (int s = 0; s < S; ++s) {
@@ -541,6 +561,7 @@ int mimo_unet_backward(mimo_unet_plan_t* P, const float* dout, const float* grad
     RUN(kGradGather, grad_gather_launch(&dp, nullptr, nullptr, t0, s > 0 ? 1 : 0, st));
   }
   RUN(kUpsampleBwd, upsample_bwd_launch(view_of(P, P->tmp0, 0, c / 2), view_of(P, P->g_u3, 0, c / 2), 0, st));
+  if ((rc = flush_unpack())) return rc;
   if (P->stage_ev[0]) MIMO_CUDA(cudaEventRecord(P->stage_ev[0], st));
   // ---- core up path ----
   if ((rc = node_backward(P, P->up3, tr, mask(P->up3), accumulate, st))) return rc;
@@ -564,6 +585,7 @@ int mimo_unet_backward(mimo_unet_plan_t* P, const float* dout, const float* grad
     RUN(kGradGather, grad_gather_launch(&dp, nullptr, nullptr, t, 0, st));
     RUN(kUpsampleBwd, upsample_bwd_launch(t, view_of(P, P->g_x5, 0, 4 * c), 0, st));
   }
+  if ((rc = flush_unpack())) return rc;
   if (P->stage_ev[1]) MIMO_CUDA(cudaEventRecord(P->stage_ev[1], st));
   // ---- core down path: skip gradient (fold of the concat slice) + max-pool backward ----
   if ((rc = node_backward(P, P->down4, tr, mask(P->down4), accumulate, st))) return rc;
@@ -593,6 +615,7 @@ int mimo_unet_backward(mimo_unet_plan_t* P, const float* dout, const float* grad
     const ActView act = view_of(P, P->cat3, 0, c);
     RUN(kGradGather, grad_gather_launch(&dskip, &gp, &act, view_of(P, P->g_xc, 0, c), 0, st));
   }
+  if ((rc = flush_unpack())) return rc;
   if (P->stage_ev[2]) MIMO_CUDA(cudaEventRecord(P->stage_ev[2], st));
   // ---- encoders ----
   for (int s = 0; s < S; ++s) {
@@ -616,6 +639,7 @@ int mimo_unet_backward(mimo_unet_plan_t* P, const float* dout, const float* grad
       ++P->launches;
     }
   }
+  if ((rc = flush_unpack())) return rc;
   if (P->stage_ev[3]) MIMO_CUDA(cudaEventRecord(P->stage_ev[3], st));
   return MIMO_OK;
 }

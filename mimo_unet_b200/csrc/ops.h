@@ -16,11 +16,18 @@ int conv3x3_launch(const ActView& in, int mode, const bf16* wpacked, int cout, i
 bool conv3x3_flatk_ok(const ActView& in, int mode, int cout);
 int conv3x3_flatk_launch(const ActView& in, int mode, const bf16* wpacked, int cout, int cin_pitch, bf16* out, int out_cpitch,
                          float* stat_sum, float* stat_sq, const float* bias, int relu, cudaStream_t stream);
-int conv3x3_wgrad_launch(const ActView& dy, const ActView& x, float* dw_packed, int cin_pitch, cudaStream_t stream);
+// pre_zeroed: the caller has already cleared dw_packed on `stream` (the executor clears all layers with one memset)
+int conv3x3_wgrad_launch(const ActView& dy, const ActView& x, float* dw_packed, int cin_pitch, cudaStream_t stream, bool pre_zeroed = false);
 bool conv3x3_wgrad_flat_ok(const ActView& dy, const ActView& x);
-int conv3x3_wgrad_flat_launch(const ActView& dy, const ActView& x, float* dw_packed, int cin_pitch, cudaStream_t stream);
+int conv3x3_wgrad_flat_launch(const ActView& dy, const ActView& x, float* dw_packed, int cin_pitch, cudaStream_t stream, bool pre_zeroed = false);
 bool conv3x3_wgrad_flatk_ok(const ActView& dy, const ActView& x);
-int conv3x3_wgrad_flatk_launch(const ActView& dy, const ActView& x, float* dw_packed, int cin_pitch, cudaStream_t stream);
+int conv3x3_wgrad_flatk_launch(const ActView& dy, const ActView& x, float* dw_packed, int cin_pitch, cudaStream_t stream, bool pre_zeroed = false);
+// batched variants: one launch for many layers (the per-layer kernels are a few microseconds each; their launch gaps
+// cost more than their work)
+struct WeightPackJob { const float* w; bf16* wf; bf16* wd; int cout, cin, cin_pitch, cout_pitch; };
+struct WgradUnpackJob { const float* packed; float* grad; int cout, cin, cin_pitch; };
+int weight_pack_batched_launch(const WeightPackJob* jobs, int n, cudaStream_t st);
+int wgrad_unpack_batched_launch(const WgradUnpackJob* jobs, int n, float scale, int accumulate, cudaStream_t st);
 int wgrad_unpack_launch(const float* packed, float* grad_oihw, int cout, int cin, int cin_pitch, float scale, int accumulate,
                         cudaStream_t stream);
 
