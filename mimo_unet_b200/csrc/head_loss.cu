@@ -363,66 +363,98 @@ __device__ __forceinline__ void buffer_weights(const LossBufferState* st, const 
   for (int s = 0; s < S; ++s) w[s] = w[s] / den * (float)S;
 }
 
-__global__ void laplace_train_kernel(const float* __restrict__ out, const float* __restrict__ y, long long y_bs, long long y_ss,
-                                     const float* __restrict__ mask, long long m_bs, long long m_ss,
-                                     const long long* __restrict__ gather /*[S][B] or null*/, int B, int S, int C, long long HW,
-                                     float eps_min, float eps_max, const LossBufferState* __restrict__ lb,
-                                     const float* __restrict__ fixed_w /*[S] or null*/, float* __restrict__ dout,
-                                     float* __restrict__ part /*[B*S][gridDim.x]*/) {
+// Persistent grid over (row = b*S + s, chunk) items: the loss-buffer weights are computed once per BLOCK (a serial
+// softmax over the buffer rows, ~2 us of latency), not once per 16 KB chunk -- with one short-lived block per chunk the
+// prologue cost as much as the streaming itself (ncu: 3.9 TB/s at 210 MB, 2.5 TB/s at 52 MB).
+__global__ void __launch_bounds__(256, 4)
+laplace_train_kernel(const float* __restrict__ out, const float* __restrict__ y, long long y_bs, long long y_ss,
+                     const float* __restrict__ mask, long long m_bs, long long m_ss,
+                     const long long* __restrict__ gather /*[S][B] or null*/, int B, int S, int C, long long HW,
+                     float eps_min, float eps_max, const LossBufferState* __restrict__ lb,
+                     const float* __restrict__ fixed_w /*[S] or null*/, float* __restrict__ dout,
+                     float* __restrict__ part /*[B*S][nblk]*/, int nblk) {
   __shared__ float sh[32];
-  __shared__ float sw;
-  const int row = blockIdx.y;  // b*S + s
-  const int b = row / S, s = row - b * S;
+  __shared__ float sw[64];
   if (threadIdx.x == 0) {
-    float w[64];
-    if (fixed_w) sw = fixed_w[s];
-    else if (lb) { buffer_weights(lb, reinterpret_cast<const float*>(lb + 1), w); sw = w[s]; }
-    else sw = 1.f;
+    if (fixed_w) { for (int s = 0; s < S; ++s) sw[s] = fixed_w[s]; }
+    else if (lb) buffer_weights(lb, reinterpret_cast<const float*>(lb + 1), sw);
+    else { for (int s = 0; s < S; ++s) sw[s] = 1.f; }
   }
   __syncthreads();
   const long long n = (long long)C * HW;
-  const float coef = sw / ((float)S * (float)B * (float)n);
-  const long long src_b = gather ? gather[(long long)s * B + b] : b;
-  const float* mu = out + (long long)row * 2 * n;
-  const float* ls = mu + n;
-  const float* yy = y + src_b * y_bs + s * y_ss;
-  const float* mm = mask ? mask + src_b * m_bs + s * m_ss : nullptr;
-  float* gmu = dout ? dout + (long long)row * 2 * n : nullptr;
-  float* gls = dout ? gmu + n : nullptr;
-  float acc = 0.f;
-  const bool vec = ((n & 3) == 0) && ((reinterpret_cast<uintptr_t>(mu) & 15) == 0) && ((reinterpret_cast<uintptr_t>(yy) & 15) == 0) &&
-                   (!mm || (reinterpret_cast<uintptr_t>(mm) & 15) == 0) && (!dout || (reinterpret_cast<uintptr_t>(gmu) & 15) == 0);
-  if (vec) {
-    const long long n4 = n >> 2;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-      const float4 a = reinterpret_cast<const float4*>(mu)[i];
-      const float4 l4 = reinterpret_cast<const float4*>(ls)[i];
-      const float4 t = reinterpret_cast<const float4*>(yy)[i];
-      float4 m4 = make_float4(1.f, 1.f, 1.f, 1.f);
-      if (mm) m4 = reinterpret_cast<const float4*>(mm)[i];
-      float4 ga, gl;
-      float l;
-      laplace_elem(a.x, l4.x, t.x, m4.x, eps_min, eps_max, &l, &ga.x, &gl.x); acc += l;
-      laplace_elem(a.y, l4.y, t.y, m4.y, eps_min, eps_max, &l, &ga.y, &gl.y); acc += l;
-      laplace_elem(a.z, l4.z, t.z, m4.z, eps_min, eps_max, &l, &ga.z, &gl.z); acc += l;
-      laplace_elem(a.w, l4.w, t.w, m4.w, eps_min, eps_max, &l, &ga.w, &gl.w); acc += l;
-      if (dout) {
-        ga.x *= coef; ga.y *= coef; ga.z *= coef; ga.w *= coef;
-        gl.x *= coef; gl.y *= coef; gl.z *= coef; gl.w *= coef;
-        reinterpret_cast<float4*>(gmu)[i] = ga;
-        reinterpret_cast<float4*>(gls)[i] = gl;
+  const float inv_cnt = 1.f / ((float)S * (float)B * (float)n);
+  const int items = B * S * nblk;
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    const int row = item / nblk, chunk = item - row * nblk;  // row = b*S + s
+    const int b = row / S, s = row - b * S;
+    const float coef = sw[s] * inv_cnt;
+    const long long src_b = gather ? gather[(long long)s * B + b] : b;
+    const float* mu = out + (long long)row * 2 * n;
+    const float* ls = mu + n;
+    const float* yy = y + src_b * y_bs + s * y_ss;
+    const float* mm = mask ? mask + src_b * m_bs + s * m_ss : nullptr;
+    float* gmu = dout ? dout + (long long)row * 2 * n : nullptr;
+    float* gls = dout ? gmu + n : nullptr;
+    float acc = 0.f;
+    const bool vec = ((n & 3) == 0) && ((reinterpret_cast<uintptr_t>(mu) & 15) == 0) && ((reinterpret_cast<uintptr_t>(yy) & 15) == 0) &&
+                     (!mm || (reinterpret_cast<uintptr_t>(mm) & 15) == 0) && (!dout || (reinterpret_cast<uintptr_t>(gmu) & 15) == 0);
+    if (vec) {
+      // chunk `chunk` of the row: 16-byte groups [lo, hi); two independent groups per thread and trip, streaming cache hints
+      const long long n4 = n >> 2;
+      const long long per = (n4 + nblk - 1) / nblk;
+      const long long lo = chunk * per, hi = (lo + per < n4) ? lo + per : n4;
+      for (long long i0 = lo + threadIdx.x; i0 < hi; i0 += 2 * blockDim.x) {
+        const long long i1 = i0 + blockDim.x;
+        const bool two = i1 < hi;
+        const float4 a0 = __ldcs(reinterpret_cast<const float4*>(mu) + i0);
+        const float4 l0 = __ldcs(reinterpret_cast<const float4*>(ls) + i0);
+        const float4 t0 = __ldcs(reinterpret_cast<const float4*>(yy) + i0);
+        const float4 m0 = mm ? __ldcs(reinterpret_cast<const float4*>(mm) + i0) : make_float4(1.f, 1.f, 1.f, 1.f);
+        float4 a1 = a0, l1 = l0, t1 = t0, m1 = m0;
+        if (two) {
+          a1 = __ldcs(reinterpret_cast<const float4*>(mu) + i1);
+          l1 = __ldcs(reinterpret_cast<const float4*>(ls) + i1);
+          t1 = __ldcs(reinterpret_cast<const float4*>(yy) + i1);
+          if (mm) m1 = __ldcs(reinterpret_cast<const float4*>(mm) + i1);
+        }
+        float4 ga, gl;
+        float l;
+        laplace_elem(a0.x, l0.x, t0.x, m0.x, eps_min, eps_max, &l, &ga.x, &gl.x); acc += l;
+        laplace_elem(a0.y, l0.y, t0.y, m0.y, eps_min, eps_max, &l, &ga.y, &gl.y); acc += l;
+        laplace_elem(a0.z, l0.z, t0.z, m0.z, eps_min, eps_max, &l, &ga.z, &gl.z); acc += l;
+        laplace_elem(a0.w, l0.w, t0.w, m0.w, eps_min, eps_max, &l, &ga.w, &gl.w); acc += l;
+        if (dout) {
+          ga.x *= coef; ga.y *= coef; ga.z *= coef; ga.w *= coef;
+          gl.x *= coef; gl.y *= coef; gl.z *= coef; gl.w *= coef;
+          __stcs(reinterpret_cast<float4*>(gmu) + i0, ga);
+          __stcs(reinterpret_cast<float4*>(gls) + i0, gl);
+        }
+        if (two) {
+          laplace_elem(a1.x, l1.x, t1.x, m1.x, eps_min, eps_max, &l, &ga.x, &gl.x); acc += l;
+          laplace_elem(a1.y, l1.y, t1.y, m1.y, eps_min, eps_max, &l, &ga.y, &gl.y); acc += l;
+          laplace_elem(a1.z, l1.z, t1.z, m1.z, eps_min, eps_max, &l, &ga.z, &gl.z); acc += l;
+          laplace_elem(a1.w, l1.w, t1.w, m1.w, eps_min, eps_max, &l, &ga.w, &gl.w); acc += l;
+          if (dout) {
+            ga.x *= coef; ga.y *= coef; ga.z *= coef; ga.w *= coef;
+            gl.x *= coef; gl.y *= coef; gl.z *= coef; gl.w *= coef;
+            __stcs(reinterpret_cast<float4*>(gmu) + i1, ga);
+            __stcs(reinterpret_cast<float4*>(gls) + i1, gl);
+          }
+        }
+      }
+    } else {
+      const long long per = (n + nblk - 1) / nblk;
+      const long long lo = chunk * per, hi = (lo + per < n) ? lo + per : n;
+      for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        float l, ga, gl;
+        laplace_elem(mu[i], ls[i], yy[i], mm ? mm[i] : 1.f, eps_min, eps_max, &l, &ga, &gl);
+        acc += l;
+        if (dout) { gmu[i] = ga * coef; gls[i] = gl * coef; }
       }
     }
-  } else {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-      float l, ga, gl;
-      laplace_elem(mu[i], ls[i], yy[i], mm ? mm[i] : 1.f, eps_min, eps_max, &l, &ga, &gl);
-      acc += l;
-      if (dout) { gmu[i] = ga * coef; gls[i] = gl * coef; }
-    }
+    const float sres = block_sum(acc, sh);
+    if (threadIdx.x == 0) part[(size_t)row * nblk + chunk] = sres;
   }
-  const float sres = block_sum(acc, sh);
-  if (threadIdx.x == 0) part[(size_t)row * gridDim.x + blockIdx.x] = sres;
 }
 
 // one block: loss[s] = sum over (b, blocks) / (B*n); weights; weighted mean; buffer update
@@ -430,18 +462,20 @@ __global__ void laplace_train_finalize_kernel(const float* __restrict__ part, in
                                               LossBufferState* lb, const float* __restrict__ fixed_w, int update_buffer,
                                               float* __restrict__ loss /*[S]*/, float* __restrict__ weights /*[S]*/,
                                               float* __restrict__ weighted /*[1]*/) {
-  __shared__ float sh[32];
   __shared__ float sl[64];
-  for (int s = 0; s < S; ++s) {
-    float a = 0.f;
-    for (int i = threadIdx.x; i < B * nblk; i += blockDim.x) {
+  // one warp per subnetwork (fixed lane-strided order + butterfly: deterministic), all subnetworks in parallel
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int s = warp; s < S; s += nwarps) {
+    double a = 0.0;
+    for (int i = lane; i < B * nblk; i += 32) {
       const int b = i / nblk, k = i - b * nblk;
-      a += part[(size_t)(b * S + s) * nblk + k];
+      a += (double)part[(size_t)(b * S + s) * nblk + k];
     }
-    const float t = block_sum(a, sh);
-    if (threadIdx.x == 0) sl[s] = (float)((double)t / count);
-    __syncthreads();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) sl[s] = (float)(a / count);
   }
+  __syncthreads();
   if (threadIdx.x == 0) {
     float w[64];
     float* buf = lb ? reinterpret_cast<float*>(lb + 1) : nullptr;
@@ -590,6 +624,36 @@ aggregate_vec4_kernel(const float* __restrict__ p1, long long p1_bs, long long p
   }
 }
 
+// Large member counts (MC dropout: S = 16, 32): one output element per thread, the S locations stay in registers between
+// the mean and the squared-deviation pass (the vec4 kernel would need 4 S registers), all 2 S loads are independent.
+template <int SREG>
+__global__ void __launch_bounds__(256)
+aggregate_reg_kernel(const float* __restrict__ p1, long long p1_bs, long long p1_ss, const float* __restrict__ p2, long long p2_bs,
+                     long long p2_ss, int B, long long inner, float* __restrict__ mean, float* __restrict__ alea,
+                     float* __restrict__ epi) {
+  const long long total = (long long)B * inner;
+  const float invS = 1.f / (float)SREG;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / inner, j = i - b * inner;
+    const float* a = p1 + b * p1_bs + j;
+    const float* l = p2 + b * p2_bs + j;
+    float va[SREG], vl[SREG];
+#pragma unroll
+    for (int s = 0; s < SREG; ++s) { va[s] = __ldcs(a + s * p1_ss); vl[s] = __ldcs(l + s * p2_ss); }
+    float m = 0.f, al = 0.f, e = 0.f;
+#pragma unroll
+    for (int s = 0; s < SREG; ++s) {
+      m += va[s];
+      const float sd = expf(vl[s]) * 1.41421356237309515f;
+      al += sd * sd;
+    }
+    m *= invS;
+#pragma unroll
+    for (int s = 0; s < SREG; ++s) { const float d = va[s] - m; e += d * d; }
+    __stcs(mean + i, m); __stcs(alea + i, al * invS); __stcs(epi + i, e / (float)(SREG - 1));
+  }
+}
+
 inline int grid_for(long long work, int per_thread = 1) {
   long long g = ceil_div_ll(work, (long long)kBlock * per_thread);
   const long long cap = (long long)num_sms() * 8;
@@ -722,9 +786,12 @@ int laplace_train_launch(const float* out, const float* y, long long y_bs, long 
   MIMO_CHECK(S >= 1 && S <= 64, MIMO_ERR_ARG, "laplace_train: 1..64 subnetworks supported");
   const long long n = (long long)C * HW;
   const int nblk = laplace_train_blocks(n);
-  dim3 grid(nblk, B * S);
+  const long long items = (long long)B * S * nblk;
+  MIMO_CHECK(items < (1ll << 31), MIMO_ERR_ARG, "laplace_train: too many work items");
+  int grid = 4 * num_sms();
+  if (grid > items) grid = (int)items;
   laplace_train_kernel<<<grid, kBlock, 0, st>>>(out, y, y_bs, y_ss, mask, m_bs, m_ss, gather, B, S, C, HW, eps_min, eps_max,
-                                                (const LossBufferState*)lb_state, fixed_w, dout, part);
+                                                (const LossBufferState*)lb_state, fixed_w, dout, part, nblk);
   MIMO_LAUNCH_CHECK();
   laplace_train_finalize_kernel<<<1, kBlock, 0, st>>>(part, nblk, B, S, (double)B * (double)n, (LossBufferState*)lb_state, fixed_w,
                                                       update_buffer, loss, weights, weighted);
@@ -743,6 +810,13 @@ int aggregate_launch(const float* p1, long long p1_bs, long long p1_ss, const fl
   MIMO_CHECK(S >= 1, MIMO_ERR_ARG, "aggregate: S must be >= 1");
   const bool vec = (inner % 4) == 0 && (p1_bs % 4) == 0 && (p1_ss % 4) == 0 && (p2_bs % 4) == 0 && (p2_ss % 4) == 0 &&
                    (((uintptr_t)p1 | (uintptr_t)p2 | (uintptr_t)mean | (uintptr_t)alea | (uintptr_t)epi) % 16) == 0;
+  if (S == 16 || S == 32) {
+    const int grid = grid_for((long long)B * inner, 1);
+    if (S == 16) aggregate_reg_kernel<16><<<grid, kBlock, 0, st>>>(p1, p1_bs, p1_ss, p2, p2_bs, p2_ss, B, inner, mean, alea, epi);
+    else aggregate_reg_kernel<32><<<grid, kBlock, 0, st>>>(p1, p1_bs, p1_ss, p2, p2_bs, p2_ss, B, inner, mean, alea, epi);
+    MIMO_LAUNCH_CHECK();
+    return MIMO_OK;
+  }
   if (vec) {
     const long long inner4 = inner / 4;
     const int grid = grid_for((long long)B * inner4, 1);
