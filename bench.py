@@ -293,8 +293,16 @@ def run_gpu_arm(args):
         t_conv = (per_step["conv_fprop"][0] + per_step["conv_dgrad"][0]) * 1e-3
         sustained, burst, hbm, src = load_peaks()
         achieved = (fprop_fl + dgrad_fl) / t_conv / 1e12
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "conv_traffic.json")  # written by tools/gpu/evidence.sh from an ncu metric pass
+        if os.path.isfile(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
         roof = {"bound": "tensor", "kernel": "conv3x3_flat_kernel + conv3x3_igemm_kernel (all fprop+dgrad launches of a step)", "achieved": achieved, "peak": sustained,
-                "unit": "TFLOP/s", "frac": achieved / sustained, "traffic": None,
+                "unit": "TFLOP/s", "frac": achieved / sustained, "traffic": traffic,
+                "traffic_note": "mean DRAM bytes (read+write) per conv fprop/dgrad launch, ncu metric pass committed as profiles/conv_traffic.json",
                 "peak_source": f"bf16_tflops_sustained of {src} MEASURED_PEAKS.json (kernel timed inside a long step)",
                 "launches_per_step": per_step["conv_fprop"][1] + per_step["conv_dgrad"][1],
                 "avg_launch_us": t_conv * 1e6 / max(1, per_step["conv_fprop"][1] + per_step["conv_dgrad"][1]),

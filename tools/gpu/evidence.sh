@@ -17,6 +17,10 @@ t "bench_loss rc=$?"; cat gpurun_out/${R}_loss_bw.txt
 rm -f gpurun_out/*.ncu-rep gpurun_out/${R}_ncu_summary.txt
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/${R}_launches_c2.csv python tools/one_step.py C2 > gpurun_out/ncu_launches.log 2>&1
 t "launch list rc=$? lines=$(wc -l < gpurun_out/${R}_launches_c2.csv)"
+# DRAM traffic of every conv fprop/dgrad launch of one step (bench.py's roofline.traffic = their mean)
+timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --profile-from-start off -k regex:"conv3x3_flat_kernel|conv3x3_flatk_kernel|conv3x3_igemm_kernel" --csv --log-file gpurun_out/${R}_conv_traffic.csv python tools/one_step.py C2 > gpurun_out/ncu_traffic.log 2>&1
+t "conv traffic rc=$?"
+python tools/conv_traffic.py gpurun_out/${R}_conv_traffic.csv gpurun_out/conv_traffic.json
 NCU="ncu --set full --clock-control none --import-source on --profile-from-start off"
 cap() {  # name kernel-regex skip count
   timeout 300 $NCU -k regex:$2 -s $3 -c $4 -o gpurun_out/$1 python tools/one_step.py C2 > gpurun_out/ncu_$1.log 2>&1; t "$1 rc=$?"
@@ -27,6 +31,6 @@ cap conv_flat      "conv3x3_flat_kernel"        0 4
 cap conv_flatk     "conv3x3_flatk_kernel"       0 3
 cap conv_igemm     "conv3x3_igemm_kernel"       0 4
 cap wgrad_flat     "conv3x3_wgrad_flat_kernel"  0 2
-cap wgrad_4d       "conv3x3_wgrad_kernel"       0 3
-cap elem           "bn_bwd_reduce_kernel|bn_bwd_apply_kernel|bn_relu_apply_kernel|grad_gather" 0 4
+cap wgrad_flatk    "conv3x3_wgrad_flatk_kernel" 0 3
+cap elem           "bn_bwd_bulk_kernel|bn_relu_apply_kernel|grad_gather_pool_kernel|upsample_fast_kernel" 0 6
 cat gpurun_out/${R}_ncu_summary.txt
