@@ -210,6 +210,9 @@ int mimo_unet_backward_stage_first_state(const mimo_unet_plan_t* plan, int stage
 int mimo_unet_debug_view(const mimo_unet_plan_t* plan, const char* name, mimo_act_t* view, int* kind);
 /* number of kernels the last forward / backward enqueued (bench.py's gpu_launches) */
 int mimo_unet_last_launches(const mimo_unet_plan_t* plan);
+/* CUDA graphs of the executor's fixed launch sequences (built after two eager calls per plan; env MIMO_GRAPH=0 disables):
+ * bit 0 forward body, bits 1..4 the four backward stages, bit 8 = a capture failed and the plan stays eager. */
+int mimo_unet_graph_state(const mimo_unet_plan_t* plan);
 /* optional per-launch CUDA-event timing by kernel class (records events on the caller's stream; read synchronises) */
 int mimo_unet_profile_classes(void);
 const char* mimo_unet_profile_class_name(int i);

@@ -97,6 +97,7 @@ SIGNATURES = {
     "mimo_unet_set_backward_events": (i32, [vp, C.POINTER(C.c_void_p)]),
     "mimo_unet_backward_stage_first_state": (i32, [vp, i32]),
     "mimo_unet_last_launches": (i32, [vp]),
+    "mimo_unet_graph_state": (i32, [vp]),
     "mimo_unet_profile_classes": (i32, []),
     "mimo_unet_profile_class_name": (C.c_char_p, [i32]),
     "mimo_unet_profile_enable": (i32, [vp, i32]),

@@ -8,6 +8,8 @@
 //   per subnetwork s:  up(u3) cat x1_s -> DoubleConv -> 1x1 head
 // Concats are never materialised as copies: producers write straight into channel slices of the consumer's
 // (reflect-haloed) input buffer.
+#include <stdlib.h>
+
 #include <map>
 #include <string>
 #include <vector>
@@ -80,6 +82,15 @@ struct mimo_unet_plan {
   std::vector<int> g_feat, g_x1;         // per subnetwork
   size_t head_part = 0;
   size_t dwp_begin = 0, dwp_end = 0;
+  // CUDA graphs of the fixed launch sequences (forward body; the four backward stages). Only launches whose arguments are
+  // workspace / bound-state pointers are captured; the kernels that touch caller tensors (input packing, heads) stay eager,
+  // so a graph stays valid for as long as the binding does.
+  struct GraphSlot { cudaGraphExec_t exec = nullptr; unsigned long long key = ~0ull; int launches = 0; };
+  GraphSlot g_fwd, g_bwd[4];
+  cudaStream_t cap_stream = nullptr;   // private stream the graphs are captured on
+  int graph_mode = 1;          // env MIMO_GRAPH (0 disables)
+  bool graph_failed = false;   // a capture failed once: stay eager
+  int fwd_calls = 0, bwd_calls = 0;
   std::vector<WgradUnpackJob> unpack_jobs;   // pending weight-gradient transposes of the current backward stage
   int head_state0 = -1;
   int n_state = 0;
@@ -187,6 +198,68 @@ inline void prof_end(mimo_unet_plan* P, cudaStream_t st) {
     if (_rc != MIMO_OK) return _rc; \
     ++P->launches;                  \
   } while (0)
+
+void drop_graphs(mimo_unet_plan* P) {
+  if (P->g_fwd.exec) { cudaGraphExecDestroy(P->g_fwd.exec); P->g_fwd.exec = nullptr; }
+  for (auto& g : P->g_bwd)
+    if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+}
+
+// Runs `body` (a fixed sequence of launches on `st`) through a cached CUDA graph: replay when the key matches, otherwise
+// capture + instantiate + launch. Any capture problem (stream already capturing, unsupported call) falls back to the
+// plain launches for good.
+template <class F>
+int run_graphed(mimo_unet_plan* P, mimo_unet_plan::GraphSlot& slot, unsigned long long key, bool allow, cudaStream_t& st, F&& body) {
+  if (!allow) return body();
+  if (slot.exec && slot.key == key) {
+    MIMO_CUDA(cudaGraphLaunch(slot.exec, st));
+    P->launches += slot.launches;
+    return MIMO_OK;
+  }
+  if (slot.exec) { cudaGraphExecDestroy(slot.exec); slot.exec = nullptr; }
+  // `st` is the variable the body's launches read (captured by reference). The capture runs on a private stream -- the
+  // caller's stream is usually the legacy default stream, which cannot capture, and nothing executes during capture anyway
+  // -- and the instantiated graph is launched on the caller's stream.
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { cudaGetLastError(); return body(); }
+  if (!P->cap_stream && cudaStreamCreateWithFlags(&P->cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    cudaGetLastError();
+    P->graph_failed = true;
+    return body();
+  }
+  if (cudaStreamBeginCapture(P->cap_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    P->graph_failed = true;
+    return body();
+  }
+  const cudaStream_t user_stream = st;
+  st = P->cap_stream;
+  const int l0 = P->launches;
+  const int rc = body();
+  st = user_stream;
+  cudaGraph_t g = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(P->cap_stream, &g);
+  if (rc != MIMO_OK || e != cudaSuccess || g == nullptr) {
+    if (g) cudaGraphDestroy(g);
+    cudaGetLastError();
+    P->graph_failed = true;
+    P->launches = l0;
+    return rc != MIMO_OK ? rc : body();
+  }
+  const cudaError_t ei = cudaGraphInstantiate(&slot.exec, g, 0);
+  cudaGraphDestroy(g);
+  if (ei != cudaSuccess) {
+    slot.exec = nullptr;
+    cudaGetLastError();
+    P->graph_failed = true;
+    P->launches = l0;
+    return body();
+  }
+  slot.key = key;
+  slot.launches = P->launches - l0;
+  MIMO_CUDA(cudaGraphLaunch(slot.exec, st));
+  return MIMO_OK;
+}
 
 float* fptr(const mimo_unet_plan* P, size_t off) { return reinterpret_cast<float*>(P->ws + off); }
 bf16* bptr(const mimo_unet_plan* P, size_t off) { return reinterpret_cast<bf16*>(P->ws + off); }
@@ -310,6 +383,7 @@ int mimo_unet_plan_create(const mimo_unet_config_t* cfg, mimo_unet_plan_t** out)
              "plan_create: H and W must be >= 32 (reflect padding needs every feature map >= 2 px), got %dx%d", cfg->height, cfg->width);
   mimo_unet_plan* P = new mimo_unet_plan();
   P->cfg = *cfg;
+  { const char* e = getenv("MIMO_GRAPH"); P->graph_mode = e ? atoi(e) : 1; }
   const int S = cfg->num_subnetworks, f = cfg->filter_base_count, N = cfg->batch, Cin = cfg->in_channels;
   P->Hs[0] = cfg->height; P->Ws[0] = cfg->width;
   for (int l = 1; l < 5; ++l) { P->Hs[l] = P->Hs[l - 1] / 2; P->Ws[l] = P->Ws[l - 1] / 2; }
@@ -385,8 +459,11 @@ int mimo_unet_plan_create(const mimo_unet_config_t* cfg, mimo_unet_plan_t** out)
 }
 
 void mimo_unet_plan_destroy(mimo_unet_plan_t* plan) {
-  if (plan)
+  if (plan) {
     for (auto& e : plan->ev) cudaEventDestroy(e);
+    drop_graphs(plan);
+    if (plan->cap_stream) cudaStreamDestroy(plan->cap_stream);
+  }
   delete plan;
 }
 size_t mimo_unet_workspace_bytes(const mimo_unet_plan_t* plan) { return plan ? plan->ws_bytes : 0; }
@@ -397,6 +474,13 @@ int mimo_unet_dropout_channels(const mimo_unet_plan_t* plan, int i) {
   return plan->nodes[i].c2.cout;
 }
 int mimo_unet_last_launches(const mimo_unet_plan_t* plan) { return plan ? plan->launches : 0; }
+int mimo_unet_graph_state(const mimo_unet_plan_t* plan) {
+  if (!plan) return 0;
+  int m = plan->g_fwd.exec ? 1 : 0;
+  for (int k = 0; k < 4; ++k) m |= plan->g_bwd[k].exec ? (2 << k) : 0;
+  if (plan->graph_failed) m |= 0x100;
+  return m;
+}
 
 int mimo_unet_profile_classes(void) { return kNumProfClasses; }
 const char* mimo_unet_profile_class_name(int i) { return (i >= 0 && i < kNumProfClasses) ? kProfNames[i] : ""; }
@@ -455,6 +539,7 @@ int mimo_unet_bind(mimo_unet_plan_t* P, void* workspace, size_t workspace_bytes,
   P->bound = true;
   P->have_forward = false;
   P->dy_tails_zeroed = false;
+  drop_graphs(P);   // the graphs embed the previous binding's pointers
   return MIMO_OK;
 }
 
@@ -474,37 +559,47 @@ int mimo_unet_forward(mimo_unet_plan_t* P, const float* x, const long long* gath
   auto mask = [&](int ni) { return P->masks_copy[ni]; };
   const bool tr = training != 0;
 
-  {  // bf16 weight packs of every layer (fprop layout + flipped dgrad layout): one launch
-    std::vector<WeightPackJob> jobs;
-    for (auto& n : P->nodes)
-      for (ConvL* cl : {&n.c1, &n.c2})
-        jobs.push_back({(const float*)P->state[cl->state0], bptr(P, cl->wf), bptr(P, cl->wd), cl->cout, cl->cin, cl->cin_p, cl->cout_p});
-    RUN(kPackW, weight_pack_batched_launch(jobs.data(), (int)jobs.size(), st));
-  }
+  // caller tensors are only touched by eager launches: input packing here, the 1x1 heads after the body
   for (int s = 0; s < S; ++s) {
     const ActView xin = view_of(P, P->xin[s], 0, Cin);
     // with a gather table x is the un-shuffled batch [B][Cin][H][W] shared by all subnetworks
     if (gather) RUN(kPackIn, pack_input_launch(x, (long long)Cin * HW, HW, gather + (long long)s * B, xin, st));
     else RUN(kPackIn, pack_input_launch(x + (long long)s * Cin * HW, (long long)S * Cin * HW, HW, nullptr, xin, st));
-    int rc = node_forward(P, P->enc_in[s], tr, mask(P->enc_in[s]), st);
-    if (rc) return rc;
-    rc = node_forward(P, P->enc_down[s], tr, mask(P->enc_down[s]), st);
-    if (rc) return rc;
   }
-  int rc;
-  if ((rc = node_forward(P, P->down2, tr, mask(P->down2), st))) return rc;
-  if ((rc = node_forward(P, P->down3, tr, mask(P->down3), st))) return rc;
-  if ((rc = node_forward(P, P->down4, tr, mask(P->down4), st))) return rc;
-  RUN(kUpsample, upsample_launch(view_of(P, P->x5, 0, 4 * c), view_of(P, P->cat1, 4 * c, 4 * c), st));
-  if ((rc = node_forward(P, P->up1, tr, mask(P->up1), st))) return rc;
-  RUN(kUpsample, upsample_launch(view_of(P, P->u1, 0, 2 * c), view_of(P, P->cat2, 2 * c, 2 * c), st));
-  if ((rc = node_forward(P, P->up2, tr, mask(P->up2), st))) return rc;
-  RUN(kUpsample, upsample_launch(view_of(P, P->u2, 0, c), view_of(P, P->cat3, c, c), st));
-  if ((rc = node_forward(P, P->up3, tr, mask(P->up3), st))) return rc;
+  auto body = [&]() -> int {
+    {  // bf16 weight packs of every layer (fprop layout + flipped dgrad layout): one launch
+      std::vector<WeightPackJob> jobs;
+      for (auto& n : P->nodes)
+        for (ConvL* cl : {&n.c1, &n.c2})
+          jobs.push_back({(const float*)P->state[cl->state0], bptr(P, cl->wf), bptr(P, cl->wd), cl->cout, cl->cin, cl->cin_p, cl->cout_p});
+      RUN(kPackW, weight_pack_batched_launch(jobs.data(), (int)jobs.size(), st));
+    }
+    int rc;
+    for (int s = 0; s < S; ++s) {
+      if ((rc = node_forward(P, P->enc_in[s], tr, mask(P->enc_in[s]), st))) return rc;
+      if ((rc = node_forward(P, P->enc_down[s], tr, mask(P->enc_down[s]), st))) return rc;
+    }
+    if ((rc = node_forward(P, P->down2, tr, mask(P->down2), st))) return rc;
+    if ((rc = node_forward(P, P->down3, tr, mask(P->down3), st))) return rc;
+    if ((rc = node_forward(P, P->down4, tr, mask(P->down4), st))) return rc;
+    RUN(kUpsample, upsample_launch(view_of(P, P->x5, 0, 4 * c), view_of(P, P->cat1, 4 * c, 4 * c), st));
+    if ((rc = node_forward(P, P->up1, tr, mask(P->up1), st))) return rc;
+    RUN(kUpsample, upsample_launch(view_of(P, P->u1, 0, 2 * c), view_of(P, P->cat2, 2 * c, 2 * c), st));
+    if ((rc = node_forward(P, P->up2, tr, mask(P->up2), st))) return rc;
+    RUN(kUpsample, upsample_launch(view_of(P, P->u2, 0, c), view_of(P, P->cat3, c, c), st));
+    if ((rc = node_forward(P, P->up3, tr, mask(P->up3), st))) return rc;
+    for (int s = 0; s < S; ++s) {
+      RUN(kUpsample, upsample_launch(view_of(P, P->u3, 0, c / 2), view_of(P, P->dcat[s], f, c / 2), st));
+      if ((rc = node_forward(P, P->dec[s], tr, mask(P->dec[s]), st))) return rc;
+    }
+    return MIMO_OK;
+  };
+  ++P->fwd_calls;
+  const bool allow = P->graph_mode != 0 && !P->graph_failed && !P->prof && drop_masks == nullptr && P->fwd_calls > 2;
+  int rc = run_graphed(P, P->g_fwd, tr ? 1ull : 0ull, allow, st, body);
+  if (rc) return rc;
   const int K = cfg.out_channels;
   for (int s = 0; s < S; ++s) {
-    RUN(kUpsample, upsample_launch(view_of(P, P->u3, 0, c / 2), view_of(P, P->dcat[s], f, c / 2), st));
-    if ((rc = node_forward(P, P->dec[s], tr, mask(P->dec[s]), st))) return rc;
     const ActView feat = view_of(P, P->nodes[P->dec[s]].out);
     RUN(kHeadFwd, head_fwd_launch(feat, (const float*)P->state[P->head_state0 + 2 * s], (const float*)P->state[P->head_state0 + 2 * s + 1], K,
                         out + (long long)s * K * HW, (long long)S * K * HW, st));
@@ -534,17 +629,7 @@ int mimo_unet_backward(mimo_unet_plan_t* P, const float* dout, const float* grad
       for (ConvL* c : {&n.c1, &n.c2}) MIMO_CUDA(cudaMemsetAsync(P->ws + P->bufs[c->dy].off, 0, P->bufs[c->dy].bytes(), st));
     P->dy_tails_zeroed = true;
   }
-  MIMO_CUDA(cudaMemsetAsync(P->ws + P->dwp_begin, 0, P->dwp_end - P->dwp_begin, st));
-  P->unpack_jobs.clear();
-  // packed [9][cout][cin] -> OIHW .grad of every layer of a stage in one launch, right before the stage's event
-  auto flush_unpack = [&]() -> int {
-    if (P->unpack_jobs.empty()) return MIMO_OK;
-    RUN(kWgradUnpack, wgrad_unpack_batched_launch(P->unpack_jobs.data(), (int)P->unpack_jobs.size(), 1.f, accumulate, st));
-    P->unpack_jobs.clear();
-    return MIMO_OK;
-  };
-
-  // ---- decoders ----
+  // ---- heads (read the caller's dout): eager ----
   for (int s = 0; s < S; ++s) {
     Node& n = P->nodes[P->dec[s]];
     const ActView feat = view_of(P, n.out);
@@ -553,93 +638,130 @@ int mimo_unet_backward(mimo_unet_plan_t* P, const float* dout, const float* grad
                         grad_scale, G, fptr(P, P->head_part), (float*)P->grads[P->head_state0 + 2 * s],
                         (float*)P->grads[P->head_state0 + 2 * s + 1], accumulate, st));
     ++P->launches;
-    if ((rc = node_backward(P, P->dec[s], tr, mask(P->dec[s]), accumulate, st))) return rc;
-    // gradient of the shared up-sampled core output: fold the [f, f + c/2) slice of every decoder into ONE buffer
-    // (the bilinear backward is linear, so it runs once on the sum instead of once per subnetwork)
-    const ActView dp = view_of(P, n.c1.dpad, f, c / 2);
-    const ActView t0 = view_of(P, P->tmp0, 0, c / 2);
-    RUN(kGradGather, grad_gather_launch(&dp, nullptr, nullptr, t0, s > 0 ? 1 : 0, st));
   }
-  RUN(kUpsampleBwd, upsample_bwd_launch(view_of(P, P->tmp0, 0, c / 2), view_of(P, P->g_u3, 0, c / 2), 0, st));
-  if ((rc = flush_unpack())) return rc;
-  if (P->stage_ev[0]) MIMO_CUDA(cudaEventRecord(P->stage_ev[0], st));
-  // ---- core up path ----
-  if ((rc = node_backward(P, P->up3, tr, mask(P->up3), accumulate, st))) return rc;
-  {
-    const ActView dp = view_of(P, P->nodes[P->up3].c1.dpad, c, c);
-    const ActView t = view_of(P, P->tmp1, 0, c);
-    RUN(kGradGather, grad_gather_launch(&dp, nullptr, nullptr, t, 0, st));
-    RUN(kUpsampleBwd, upsample_bwd_launch(t, view_of(P, P->g_u2, 0, c), 0, st));
-  }
-  if ((rc = node_backward(P, P->up2, tr, mask(P->up2), accumulate, st))) return rc;
-  {
-    const ActView dp = view_of(P, P->nodes[P->up2].c1.dpad, 2 * c, 2 * c);
-    const ActView t = view_of(P, P->tmp2, 0, 2 * c);
-    RUN(kGradGather, grad_gather_launch(&dp, nullptr, nullptr, t, 0, st));
-    RUN(kUpsampleBwd, upsample_bwd_launch(t, view_of(P, P->g_u1, 0, 2 * c), 0, st));
-  }
-  if ((rc = node_backward(P, P->up1, tr, mask(P->up1), accumulate, st))) return rc;
-  {
-    const ActView dp = view_of(P, P->nodes[P->up1].c1.dpad, 4 * c, 4 * c);
-    const ActView t = view_of(P, P->tmp3, 0, 4 * c);
-    RUN(kGradGather, grad_gather_launch(&dp, nullptr, nullptr, t, 0, st));
-    RUN(kUpsampleBwd, upsample_bwd_launch(t, view_of(P, P->g_x5, 0, 4 * c), 0, st));
-  }
-  if ((rc = flush_unpack())) return rc;
-  if (P->stage_ev[1]) MIMO_CUDA(cudaEventRecord(P->stage_ev[1], st));
-  // ---- core down path: skip gradient (fold of the concat slice) + max-pool backward ----
-  if ((rc = node_backward(P, P->down4, tr, mask(P->down4), accumulate, st))) return rc;
-  {
-    const ActView dpp = view_of(P, P->nodes[P->down4].c1.dpad, 0, 4 * c);
-    const ActView gp = view_of(P, P->gp_x4, 0, 4 * c);
-    RUN(kGradGather, grad_gather_launch(&dpp, nullptr, nullptr, gp, 0, st));
-    const ActView dskip = view_of(P, P->nodes[P->up1].c1.dpad, 0, 4 * c);
-    const ActView act = view_of(P, P->cat1, 0, 4 * c);
-    RUN(kGradGather, grad_gather_launch(&dskip, &gp, &act, view_of(P, P->g_x4, 0, 4 * c), 0, st));
-  }
-  if ((rc = node_backward(P, P->down3, tr, mask(P->down3), accumulate, st))) return rc;
-  {
-    const ActView dpp = view_of(P, P->nodes[P->down3].c1.dpad, 0, 2 * c);
-    const ActView gp = view_of(P, P->gp_x3, 0, 2 * c);
-    RUN(kGradGather, grad_gather_launch(&dpp, nullptr, nullptr, gp, 0, st));
-    const ActView dskip = view_of(P, P->nodes[P->up2].c1.dpad, 0, 2 * c);
-    const ActView act = view_of(P, P->cat2, 0, 2 * c);
-    RUN(kGradGather, grad_gather_launch(&dskip, &gp, &act, view_of(P, P->g_x3, 0, 2 * c), 0, st));
-  }
-  if ((rc = node_backward(P, P->down2, tr, mask(P->down2), accumulate, st))) return rc;
-  {
-    const ActView dpp = view_of(P, P->nodes[P->down2].c1.dpad, 0, c);
-    const ActView gp = view_of(P, P->gp_xc, 0, c);
-    RUN(kGradGather, grad_gather_launch(&dpp, nullptr, nullptr, gp, 0, st));
-    const ActView dskip = view_of(P, P->nodes[P->up3].c1.dpad, 0, c);
-    const ActView act = view_of(P, P->cat3, 0, c);
-    RUN(kGradGather, grad_gather_launch(&dskip, &gp, &act, view_of(P, P->g_xc, 0, c), 0, st));
-  }
-  if ((rc = flush_unpack())) return rc;
-  if (P->stage_ev[2]) MIMO_CUDA(cudaEventRecord(P->stage_ev[2], st));
-  // ---- encoders ----
-  for (int s = 0; s < S; ++s) {
-    if ((rc = node_backward(P, P->enc_down[s], tr, mask(P->enc_down[s]), accumulate, st))) return rc;
-    const ActView dpp = view_of(P, P->nodes[P->enc_down[s]].c1.dpad, 0, f);
-    const ActView gp = view_of(P, P->gp1[s], 0, f);
-    RUN(kGradGather, grad_gather_launch(&dpp, nullptr, nullptr, gp, 0, st));
-    const ActView dskip = view_of(P, P->nodes[P->dec[s]].c1.dpad, 0, f);
-    const ActView act = view_of(P, P->dcat[s], 0, f);
-    RUN(kGradGather, grad_gather_launch(&dskip, &gp, &act, view_of(P, P->g_x1[s], 0, f), 0, st));
-    if ((rc = node_backward(P, P->enc_in[s], tr, mask(P->enc_in[s]), accumulate, st))) return rc;
-    if (dx) {
-      const ActView dp = view_of(P, P->nodes[P->enc_in[s]].c1.dpad, 0, Cin);
-      const long long total = (long long)cfg.batch * HW;
-      int grid = (int)((total + 255) / 256);
-      if (grid > num_sms() * 16) grid = num_sms() * 16;
-      prof_begin(P, kOther, st);
-      unpack_input_grad_kernel<<<grid, 256, 0, st>>>(dp, cfg.height, cfg.width, Cin, dx + (long long)s * Cin * HW, (long long)S * Cin * HW, HW);
-      prof_end(P, st);
-      MIMO_LAUNCH_CHECK();
-      ++P->launches;
+  // packed [9][cout][cin] -> OIHW .grad of every layer of a stage in one launch, at the end of the stage
+  auto flush_unpack = [&]() -> int {
+    if (P->unpack_jobs.empty()) return MIMO_OK;
+    RUN(kWgradUnpack, wgrad_unpack_batched_launch(P->unpack_jobs.data(), (int)P->unpack_jobs.size(), 1.f, accumulate, st));
+    P->unpack_jobs.clear();
+    return MIMO_OK;
+  };
+  // The four stages (decoders -> core up path -> core down path -> encoders) are four fixed launch sequences over the
+  // workspace: each one is replayed from its own CUDA graph; the caller's stage events are recorded eagerly in between
+  // (ordinary stream semantics for the overlapped gradient all-reduce).
+  auto stage0 = [&]() -> int {
+    int rc;
+    MIMO_CUDA(cudaMemsetAsync(P->ws + P->dwp_begin, 0, P->dwp_end - P->dwp_begin, st));
+    P->unpack_jobs.clear();
+    for (int s = 0; s < S; ++s) {
+      Node& n = P->nodes[P->dec[s]];
+      if ((rc = node_backward(P, P->dec[s], tr, mask(P->dec[s]), accumulate, st))) return rc;
+      // gradient of the shared up-sampled core output: fold the [f, f + c/2) slice of every decoder into ONE buffer
+      // (the bilinear backward is linear, so it runs once on the sum instead of once per subnetwork)
+      const ActView dp = view_of(P, n.c1.dpad, f, c / 2);
+      const ActView t0 = view_of(P, P->tmp0, 0, c / 2);
+      RUN(kGradGather, grad_gather_launch(&dp, nullptr, nullptr, t0, s > 0 ? 1 : 0, st));
     }
-  }
-  if ((rc = flush_unpack())) return rc;
+    RUN(kUpsampleBwd, upsample_bwd_launch(view_of(P, P->tmp0, 0, c / 2), view_of(P, P->g_u3, 0, c / 2), 0, st));
+    return flush_unpack();
+  };
+  auto stage1 = [&]() -> int {
+    int rc;
+    P->unpack_jobs.clear();
+    if ((rc = node_backward(P, P->up3, tr, mask(P->up3), accumulate, st))) return rc;
+    {
+      const ActView dp = view_of(P, P->nodes[P->up3].c1.dpad, c, c);
+      const ActView t = view_of(P, P->tmp1, 0, c);
+      RUN(kGradGather, grad_gather_launch(&dp, nullptr, nullptr, t, 0, st));
+      RUN(kUpsampleBwd, upsample_bwd_launch(t, view_of(P, P->g_u2, 0, c), 0, st));
+    }
+    if ((rc = node_backward(P, P->up2, tr, mask(P->up2), accumulate, st))) return rc;
+    {
+      const ActView dp = view_of(P, P->nodes[P->up2].c1.dpad, 2 * c, 2 * c);
+      const ActView t = view_of(P, P->tmp2, 0, 2 * c);
+      RUN(kGradGather, grad_gather_launch(&dp, nullptr, nullptr, t, 0, st));
+      RUN(kUpsampleBwd, upsample_bwd_launch(t, view_of(P, P->g_u1, 0, 2 * c), 0, st));
+    }
+    if ((rc = node_backward(P, P->up1, tr, mask(P->up1), accumulate, st))) return rc;
+    {
+      const ActView dp = view_of(P, P->nodes[P->up1].c1.dpad, 4 * c, 4 * c);
+      const ActView t = view_of(P, P->tmp3, 0, 4 * c);
+      RUN(kGradGather, grad_gather_launch(&dp, nullptr, nullptr, t, 0, st));
+      RUN(kUpsampleBwd, upsample_bwd_launch(t, view_of(P, P->g_x5, 0, 4 * c), 0, st));
+    }
+    return flush_unpack();
+  };
+  // core down path: skip gradient (fold of the concat slice) + max-pool backward
+  auto stage2 = [&]() -> int {
+    int rc;
+    P->unpack_jobs.clear();
+    if ((rc = node_backward(P, P->down4, tr, mask(P->down4), accumulate, st))) return rc;
+    {
+      const ActView dpp = view_of(P, P->nodes[P->down4].c1.dpad, 0, 4 * c);
+      const ActView gp = view_of(P, P->gp_x4, 0, 4 * c);
+      RUN(kGradGather, grad_gather_launch(&dpp, nullptr, nullptr, gp, 0, st));
+      const ActView dskip = view_of(P, P->nodes[P->up1].c1.dpad, 0, 4 * c);
+      const ActView act = view_of(P, P->cat1, 0, 4 * c);
+      RUN(kGradGather, grad_gather_launch(&dskip, &gp, &act, view_of(P, P->g_x4, 0, 4 * c), 0, st));
+    }
+    if ((rc = node_backward(P, P->down3, tr, mask(P->down3), accumulate, st))) return rc;
+    {
+      const ActView dpp = view_of(P, P->nodes[P->down3].c1.dpad, 0, 2 * c);
+      const ActView gp = view_of(P, P->gp_x3, 0, 2 * c);
+      RUN(kGradGather, grad_gather_launch(&dpp, nullptr, nullptr, gp, 0, st));
+      const ActView dskip = view_of(P, P->nodes[P->up2].c1.dpad, 0, 2 * c);
+      const ActView act = view_of(P, P->cat2, 0, 2 * c);
+      RUN(kGradGather, grad_gather_launch(&dskip, &gp, &act, view_of(P, P->g_x3, 0, 2 * c), 0, st));
+    }
+    if ((rc = node_backward(P, P->down2, tr, mask(P->down2), accumulate, st))) return rc;
+    {
+      const ActView dpp = view_of(P, P->nodes[P->down2].c1.dpad, 0, c);
+      const ActView gp = view_of(P, P->gp_xc, 0, c);
+      RUN(kGradGather, grad_gather_launch(&dpp, nullptr, nullptr, gp, 0, st));
+      const ActView dskip = view_of(P, P->nodes[P->up3].c1.dpad, 0, c);
+      const ActView act = view_of(P, P->cat3, 0, c);
+      RUN(kGradGather, grad_gather_launch(&dskip, &gp, &act, view_of(P, P->g_xc, 0, c), 0, st));
+    }
+    return flush_unpack();
+  };
+  auto stage3 = [&]() -> int {
+    int rc;
+    P->unpack_jobs.clear();
+    for (int s = 0; s < S; ++s) {
+      if ((rc = node_backward(P, P->enc_down[s], tr, mask(P->enc_down[s]), accumulate, st))) return rc;
+      const ActView dpp = view_of(P, P->nodes[P->enc_down[s]].c1.dpad, 0, f);
+      const ActView gp = view_of(P, P->gp1[s], 0, f);
+      RUN(kGradGather, grad_gather_launch(&dpp, nullptr, nullptr, gp, 0, st));
+      const ActView dskip = view_of(P, P->nodes[P->dec[s]].c1.dpad, 0, f);
+      const ActView act = view_of(P, P->dcat[s], 0, f);
+      RUN(kGradGather, grad_gather_launch(&dskip, &gp, &act, view_of(P, P->g_x1[s], 0, f), 0, st));
+      if ((rc = node_backward(P, P->enc_in[s], tr, mask(P->enc_in[s]), accumulate, st))) return rc;
+      if (dx) {
+        const ActView dp = view_of(P, P->nodes[P->enc_in[s]].c1.dpad, 0, Cin);
+        const long long total = (long long)cfg.batch * HW;
+        int grid = (int)((total + 255) / 256);
+        if (grid > num_sms() * 16) grid = num_sms() * 16;
+        prof_begin(P, kOther, st);
+        unpack_input_grad_kernel<<<grid, 256, 0, st>>>(dp, cfg.height, cfg.width, Cin, dx + (long long)s * Cin * HW, (long long)S * Cin * HW, HW);
+        prof_end(P, st);
+        MIMO_LAUNCH_CHECK();
+        ++P->launches;
+      }
+    }
+    return flush_unpack();
+  };
+  ++P->bwd_calls;
+  bool has_mask = false;
+  for (const float* m : P->masks_copy) has_mask = has_mask || (m != nullptr);
+  const bool allow = P->graph_mode != 0 && !P->graph_failed && !P->prof && !has_mask && dx == nullptr && P->bwd_calls > 2;
+  const unsigned long long key = (tr ? 1ull : 0ull) | (accumulate ? 2ull : 0ull);
+  if ((rc = run_graphed(P, P->g_bwd[0], key, allow, st, stage0))) return rc;
+  if (P->stage_ev[0]) MIMO_CUDA(cudaEventRecord(P->stage_ev[0], st));
+  if ((rc = run_graphed(P, P->g_bwd[1], key, allow, st, stage1))) return rc;
+  if (P->stage_ev[1]) MIMO_CUDA(cudaEventRecord(P->stage_ev[1], st));
+  if ((rc = run_graphed(P, P->g_bwd[2], key, allow, st, stage2))) return rc;
+  if (P->stage_ev[2]) MIMO_CUDA(cudaEventRecord(P->stage_ev[2], st));
+  if ((rc = run_graphed(P, P->g_bwd[3], key, allow, st, stage3))) return rc;
   if (P->stage_ev[3]) MIMO_CUDA(cudaEventRecord(P->stage_ev[3], st));
   return MIMO_OK;
 }

@@ -99,6 +99,11 @@ class UNetPlan:
         return int(self.lib.mimo_unet_backward_stage_first_state(self.handle, stage))
 
     @property
+    def graph_state(self) -> int:
+        """bit 0: forward body runs from a CUDA graph; bits 1..4: backward stages; bit 8: capture failed (eager for good)."""
+        return int(self.lib.mimo_unet_graph_state(self.handle))
+
+    @property
     def last_launches(self) -> int:
         return int(self.lib.mimo_unet_last_launches(self.handle))
 

@@ -208,3 +208,48 @@ def test_layerwise_teacher_forced_forward(cases):
         # halo of the stored input equals the reflect padding of its interior
         xp = plan.debug_tensor_padded(nd + ".in")
         assert torch.equal(xp, torch.nn.functional.pad(xin, (1, 1, 1, 1), mode="reflect")), nd
+
+
+def test_graph_replay_matches_eager(cases):
+    """After two eager calls the executor replays the forward body and the four backward stages from CUDA graphs (captured
+    on a private stream, launched on the caller's): same outputs and gradients as the eager launches, the graphs follow a
+    change of the BatchNorm mode, and input-gradient requests stay on the eager path."""
+    c = cases["m2_f8_32x32"]
+    cfg = c["cfg"]
+    S, f, cin = cfg["S"], cfg["f"], cfg["cin"]
+    sd = O.make_state_dict(cin, 2, S, f, cfg["seed"])
+    x = c["x"].cuda().contiguous()
+    B, _, _, H, W = x.shape
+    plan = UNetPlan(cin, 2, S, f, B, H, W, torch.device("cuda"))
+    names = [n for n, _, _ in O.state_dict_spec(cin, 2, S, f)]
+    state = [sd[n].cuda().contiguous() for n in names]
+    grads = [torch.zeros_like(t) if t.dtype == torch.float32 and ("running" not in n) else None for n, t in zip(names, state)]
+    plan.bind(state, grads)
+    torch.manual_seed(0)
+    dout = (torch.randn(B, S, 2, H, W, device="cuda") * 1e-2).contiguous()
+    outs, gsets = [], []
+    for it in range(5):
+        out = torch.empty(B, S, 2, H, W, device="cuda")
+        plan.forward(x, out, True)
+        plan.backward(dout)
+        torch.cuda.synchronize()
+        outs.append(out.clone())
+        gsets.append([g.clone() for g in grads if g is not None])
+        if it == 1:
+            assert plan.graph_state == 0, "the first two calls are eager"
+    assert plan.graph_state == 0x1F, f"forward + four backward stage graphs expected, got {plan.graph_state:#x}"
+    assert torch.equal(outs[0], outs[4])  # the forward is deterministic
+    for a, b in zip(gsets[0], gsets[4]):
+        assert rel_l2(b, a) <= 1e-5  # fp32 atomics in the weight gradients: order may differ
+    # BatchNorm mode change -> new key -> recapture; eval output must match an eager eval plan
+    out_e = torch.empty(B, S, 2, H, W, device="cuda")
+    plan.forward(x, out_e, False)
+    ref = run_plan(cfg, {n: t.cpu() for n, t in zip(names, state)}, c["x"], training=False)["out"]
+    assert torch.equal(out_e, ref)
+    # input gradients are produced by the eager path
+    dx = torch.empty_like(x)
+    plan.forward(x, out, True)
+    plan.backward(dout, dx=dx)
+    torch.cuda.synchronize()
+    assert torch.isfinite(dx).all() and float(dx.abs().sum()) > 0
+    assert (plan.graph_state & 0x100) == 0
