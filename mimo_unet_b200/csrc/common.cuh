@@ -140,13 +140,39 @@ __device__ __forceinline__ uint4 group_mask(int nvalid) {
 __device__ __forceinline__ uint4 and4(const uint4& a, const uint4& m) { return make_uint4(a.x & m.x, a.y & m.y, a.z & m.z, a.w & m.w); }
 // 16-byte load of an 8-channel group when the view is 16-byte aligned (VEC), generic path otherwise; channels >= nvalid
 // come back as zero either way (the vector path may over-read pad channels inside the pixel's pitch and masks them)
+// own = view channels [c, c+8), next = [c+8, c+16) (packed bf16): returns the 8 channels starting at c + e, 0 < e < 8
+__device__ __forceinline__ uint4 funnel8(const uint4& own, const uint4& next, int e) {
+  const uint32_t w[8] = {own.x, own.y, own.z, own.w, next.x, next.y, next.z, next.w};
+  uint4 r = own;
+  switch (e) {
+#define MIMO_F8(E)                                                                                                       \
+  case E:                                                                                                                \
+    r.x = __funnelshift_r(w[(E >> 1) + 0], w[(E >> 1) + 1], (E & 1) * 16);                                               \
+    r.y = __funnelshift_r(w[(E >> 1) + 1], w[(E >> 1) + 2], (E & 1) * 16);                                               \
+    r.z = __funnelshift_r(w[(E >> 1) + 2], w[(E >> 1) + 3], (E & 1) * 16);                                               \
+    r.w = __funnelshift_r(w[(E >> 1) + 3], w[(E >> 1) + 4 > 7 ? 7 : (E >> 1) + 4], (E & 1) * 16);                        \
+    break;
+    MIMO_F8(1) MIMO_F8(2) MIMO_F8(3) MIMO_F8(4) MIMO_F8(5) MIMO_F8(6) MIMO_F8(7)
+#undef MIMO_F8
+    default: break;
+  }
+  return r;
+}
+
 template <bool VEC>
 __device__ __forceinline__ uint4 load_group(const bf16* p, int nvalid, const uint4& mask) {
   if (VEC) return and4(*reinterpret_cast<const uint4*>(p), mask);
-  bf16x8 t;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) t.v[i] = (i < nvalid) ? p[i] : __float2bfloat16_rn(0.f);
-  return *reinterpret_cast<uint4*>(&t);
+  // Unaligned view (channel offset not a multiple of 8, e.g. the [21, 63) slice of the decoder concat): the one or two
+  // 16-byte words that hold the group are loaded whole and funnel-shifted. Both words contain at least one requested
+  // channel, so they lie inside the pixel (pixel pitches are multiples of 16 bytes) -- no scalar 2-byte loads.
+  if (nvalid <= 0) return make_uint4(0, 0, 0, 0);
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const int r = (int)((a & 15) >> 1);
+  const uint4* q = reinterpret_cast<const uint4*>(a & ~uintptr_t(15));
+  const uint4 lo = q[0];
+  if (r == 0) return and4(lo, mask);
+  const uint4 hi = (r + nvalid > 8) ? q[1] : make_uint4(0, 0, 0, 0);
+  return and4(funnel8(lo, hi, r), mask);
 }
 
 __device__ __forceinline__ void store8(bf16* p, int nvalid, const float in[8]) {

@@ -348,25 +348,6 @@ __global__ void upsample_kernel(ActView in, ActView o, int off_h, int off_w) {
   }
 }
 
-// own = view channels [c, c+8), next = [c+8, c+16) (packed bf16): returns the 8 channels starting at c + e, 0 < e < 8
-__device__ __forceinline__ uint4 funnel8(const uint4& own, const uint4& next, int e) {
-  const uint32_t w[8] = {own.x, own.y, own.z, own.w, next.x, next.y, next.z, next.w};
-  uint4 r = own;
-  switch (e) {
-#define MIMO_F8(E)                                                                                                       \
-  case E:                                                                                                                \
-    r.x = __funnelshift_r(w[(E >> 1) + 0], w[(E >> 1) + 1], (E & 1) * 16);                                               \
-    r.y = __funnelshift_r(w[(E >> 1) + 1], w[(E >> 1) + 2], (E & 1) * 16);                                               \
-    r.z = __funnelshift_r(w[(E >> 1) + 2], w[(E >> 1) + 3], (E & 1) * 16);                                               \
-    r.w = __funnelshift_r(w[(E >> 1) + 3], w[(E >> 1) + 4 > 7 ? 7 : (E >> 1) + 4], (E & 1) * 16);                        \
-    break;
-    MIMO_F8(1) MIMO_F8(2) MIMO_F8(3) MIMO_F8(4) MIMO_F8(5) MIMO_F8(6) MIMO_F8(7)
-#undef MIMO_F8
-    default: break;
-  }
-  return r;
-}
-
 // Fast path of the up-sampling: block = (pixel lanes) x GPP lanes per pixel (GPP = power of two >= #channel groups, so
 // the groups of a pixel never straddle a warp), row-based 32-bit indexing, 16-byte loads of the four taps. Destination
 // slices whose channel offset is NOT a multiple of 8 (decoder concat: 21 + 42 channels) are still written with 16-byte
