@@ -125,6 +125,10 @@ int mimo_bn_relu_bwd_folded(mimo_act_t dpad, mimo_act_t g_scratch, const void* y
                             int training, float* part, float* s1s2, float* dgamma, float* dbeta, float* dbias,
                             int accumulate, mimo_act_t dy, void* stream);
 
+/* nn.Dropout (element-wise; reference model.py:239 center_dropout, model.py:294 final_dropouts): a *= keep * scale in place on
+ * the interior of the view; keep = dense bf16 0/1 [N][H][W][mask_cpitch], scale = 1/(1-p). Backward = same call on the gradient. */
+int mimo_mask_mul(mimo_act_t a, const void* keep, int mask_cpitch, float scale, void* stream);
+
 /* ------------------------------------------------------------------ heads / loss / aggregation ------------ */
 /* OutConv 1x1 (components.py:123-129): out fp32 planes, element (n,k,h,w) at out[n*out_bstride + k*h*w + ...] */
 int mimo_head1x1(mimo_act_t feat, const float* w, const float* bias, int k, float* out, long long out_bstride, void* stream);
@@ -198,6 +202,11 @@ int mimo_unet_forward(mimo_unet_plan_t* plan, const float* x, const long long* g
  * not supported together with gather). Parameter gradients are WRITTEN (accumulate==0) or ADDED to grads[]. */
 int mimo_unet_backward(mimo_unet_plan_t* plan, const float* dout, const float* grad_scale, float* dx, int accumulate,
                        void* stream);
+/* Element-wise dropout for the NEXT forward/backward pair (reference model.py:239,294): keep masks as for mimo_mask_mul,
+ * center_keep [N][H/16][W/16][round_up(8*f*S, 8)] applied to the core centre, final_keep[s] [N][H][W][round_up(f, 8)] applied
+ * to the decoder features in front of head s; NULL entries = no dropout. Masks stay caller-owned until backward has run. */
+int mimo_unet_set_elementwise_dropout(mimo_unet_plan_t* plan, const void* center_keep, float center_scale,
+                                      const void* const* final_keep, float final_scale);
 /* Overlap hook for the data-parallel gradient all-reduce: events[4] are caller-owned cudaEvent_t (or NULL
  * to disable). mimo_unet_backward records events[k] on its stream as soon as the parameter gradients of stage k are
  * final: 0 = decoders + heads, 1 = core up path, 2 = core down path, 3 = encoders (end of backward). The state entries

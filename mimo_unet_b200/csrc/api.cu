@@ -135,6 +135,11 @@ int mimo_bn_relu_bwd_folded(mimo_act_t dpad, mimo_act_t g_scratch, const void* y
                        dgamma, dbeta, dbias, 1.f, accumulate, make_view(dy), (cudaStream_t)stream, &d);
 }
 
+int mimo_mask_mul(mimo_act_t a, const void* keep, int mask_cpitch, float scale, void* stream) {
+  MIMO_CHECK(a.ptr && keep, MIMO_ERR_ARG, "mask_mul: null pointer");
+  return mask_mul_launch(make_view(a), (const bf16*)keep, mask_cpitch, scale, (cudaStream_t)stream);
+}
+
 int mimo_head1x1(mimo_act_t feat, const float* w, const float* bias, int k, float* out, long long out_bstride, void* stream) {
   MIMO_CHECK(feat.ptr && w && bias && out, MIMO_ERR_ARG, "head1x1: null pointer");
   return head_fwd_launch(make_view(feat), w, bias, k, out, out_bstride, (cudaStream_t)stream);

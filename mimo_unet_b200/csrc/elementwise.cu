@@ -1092,6 +1092,40 @@ bn_bwd_bulk_kernel(const BulkArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Element-wise dropout of nn.Dropout (reference model.py:239 center_dropout on the core centre, model.py:294 final_dropouts
+// in front of the heads): a[n,h,w,c] *= keep[n,h,w,c] * scale, in place on the interior of the view. keep is a dense bf16
+// 0/1 tensor [N][H][W][mask_cp] (mask_cp multiple of 8, >= C); the 1/(1-p) scale is applied in fp32. The same kernel
+// multiplies the upstream gradient in backward.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+mask_mul_kernel(ActView a, const bf16* __restrict__ keep, int mask_cp, float scale) {
+  const int groups = (a.C + 7) >> 3;
+  const long long total = (long long)a.N * a.H * a.W * groups;
+  const bool vec = ((reinterpret_cast<uintptr_t>(a.base) & 15) == 0) && (a.cpitch & 7) == 0 && (a.c_off & 7) == 0 &&
+                   ((reinterpret_cast<uintptr_t>(keep) & 15) == 0);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    long long r = i / groups;
+    const int w = (int)(r % a.W); r /= a.W;
+    const int h = (int)(r % a.H);
+    const int n = (int)(r / a.H);
+    const int c = g * 8, nv = min(8, a.C - c);
+    bf16* px = a.base + a.pix(n, h, w) + c;
+    const bf16* mk = keep + (((long long)n * a.H + h) * a.W + w) * mask_cp + c;
+    float v[8], m[8];
+    if (vec && nv == 8) {
+      unpack8(*reinterpret_cast<const uint4*>(px), v);
+      unpack8(*reinterpret_cast<const uint4*>(mk), m);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = v[k] * m[k] * scale;
+      *reinterpret_cast<uint4*>(px) = pack8(v);
+    } else {
+      for (int k = 0; k < nv; ++k) px[k] = __float2bfloat16_rn(__bfloat162float(px[k]) * __bfloat162float(mk[k]) * scale);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Component-level up-sampling alternatives of `Up` (components.py:86-98). The reference cannot run them at
 // whole-model level, so they are plain CUDA-core kernels, not tensor-core paths.
 // ------------------------------------------------------------------------------------------------
@@ -1409,6 +1443,14 @@ int bn_bwd_launch(const ActView& G, const bf16* y, int ycp, const float* scale, 
   const int grid = rows < 8 * num_sms() ? rows : 8 * num_sms();
   if (vec) bn_bwd_apply_kernel<true><<<grid, kBlock, 0, st>>>(G, y, ycp, scale, shift, mean, invstd, drop, s1s2, C, 1.f / (float)npix, training, dy);
   else bn_bwd_apply_kernel<false><<<grid, kBlock, 0, st>>>(G, y, ycp, scale, shift, mean, invstd, drop, s1s2, C, 1.f / (float)npix, training, dy);
+  MIMO_LAUNCH_CHECK();
+  return MIMO_OK;
+}
+
+int mask_mul_launch(const ActView& a, const bf16* keep, int mask_cp, float scale, cudaStream_t st) {
+  MIMO_CHECK(keep != nullptr && mask_cp % 8 == 0 && mask_cp >= a.C, MIMO_ERR_ARG, "mask_mul: keep mask must be dense bf16 [N][H][W][cp], cp %% 8 == 0, cp >= C");
+  const long long total = (long long)a.N * a.H * a.W * ((a.C + 7) / 8);
+  mask_mul_kernel<<<grid_for(total), kBlock, 0, st>>>(a, keep, mask_cp, scale);
   MIMO_LAUNCH_CHECK();
   return MIMO_OK;
 }

@@ -108,6 +108,11 @@ struct mimo_unet_plan {
   const float* const* last_masks = nullptr;
   std::vector<const float*> masks_copy;
   int launches = 0;
+  // element-wise dropout (nn.Dropout) keep masks of the next forward/backward pair: centre of the core, one per decoder
+  const bf16* center_keep = nullptr;
+  float center_scale = 1.f;
+  std::vector<const bf16*> final_keep;
+  float final_scale = 1.f;
   int Hs[5], Ws[5];
   // optional per-launch CUDA-event profiling (bench.py roofline numbers)
   bool prof = false;
@@ -582,6 +587,8 @@ int mimo_unet_forward(mimo_unet_plan_t* P, const float* x, const long long* gath
     if ((rc = node_forward(P, P->down2, tr, mask(P->down2), st))) return rc;
     if ((rc = node_forward(P, P->down3, tr, mask(P->down3), st))) return rc;
     if ((rc = node_forward(P, P->down4, tr, mask(P->down4), st))) return rc;
+    if (P->center_keep)  // x_drop = center_dropout(x5), model.py:239
+      RUN(kOther, mask_mul_launch(view_of(P, P->x5, 0, 4 * c), P->center_keep, p8(4 * c), P->center_scale, st));
     RUN(kUpsample, upsample_launch(view_of(P, P->x5, 0, 4 * c), view_of(P, P->cat1, 4 * c, 4 * c), st));
     if ((rc = node_forward(P, P->up1, tr, mask(P->up1), st))) return rc;
     RUN(kUpsample, upsample_launch(view_of(P, P->u1, 0, 2 * c), view_of(P, P->cat2, 2 * c, 2 * c), st));
@@ -591,11 +598,15 @@ int mimo_unet_forward(mimo_unet_plan_t* P, const float* x, const long long* gath
     for (int s = 0; s < S; ++s) {
       RUN(kUpsample, upsample_launch(view_of(P, P->u3, 0, c / 2), view_of(P, P->dcat[s], f, c / 2), st));
       if ((rc = node_forward(P, P->dec[s], tr, mask(P->dec[s]), st))) return rc;
+      if (s < (int)P->final_keep.size() && P->final_keep[s])  // x_i = final_dropouts[i](x_i), model.py:294
+        RUN(kOther, mask_mul_launch(view_of(P, P->nodes[P->dec[s]].out), P->final_keep[s], p8(f), P->final_scale, st));
     }
     return MIMO_OK;
   };
   ++P->fwd_calls;
-  const bool allow = P->graph_mode != 0 && !P->graph_failed && !P->prof && drop_masks == nullptr && P->fwd_calls > 2;
+  bool elem_drop = P->center_keep != nullptr;
+  for (const bf16* m : P->final_keep) elem_drop = elem_drop || (m != nullptr);
+  const bool allow = P->graph_mode != 0 && !P->graph_failed && !P->prof && drop_masks == nullptr && !elem_drop && P->fwd_calls > 2;
   int rc = run_graphed(P, P->g_fwd, tr ? 1ull : 0ull, allow, st, body);
   if (rc) return rc;
   const int K = cfg.out_channels;
@@ -638,6 +649,8 @@ int mimo_unet_backward(mimo_unet_plan_t* P, const float* dout, const float* grad
                         grad_scale, G, fptr(P, P->head_part), (float*)P->grads[P->head_state0 + 2 * s],
                         (float*)P->grads[P->head_state0 + 2 * s + 1], accumulate, st));
     ++P->launches;
+    if (s < (int)P->final_keep.size() && P->final_keep[s])
+      RUN(kOther, mask_mul_launch(G, P->final_keep[s], p8(f), P->final_scale, st));
   }
   // packed [9][cout][cin] -> OIHW .grad of every layer of a stage in one launch, at the end of the stage
   auto flush_unpack = [&]() -> int {
@@ -695,6 +708,7 @@ int mimo_unet_backward(mimo_unet_plan_t* P, const float* dout, const float* grad
   auto stage2 = [&]() -> int {
     int rc;
     P->unpack_jobs.clear();
+    if (P->center_keep) RUN(kOther, mask_mul_launch(view_of(P, P->g_x5, 0, 4 * c), P->center_keep, p8(4 * c), P->center_scale, st));
     if ((rc = node_backward(P, P->down4, tr, mask(P->down4), accumulate, st))) return rc;
     {
       const ActView dpp = view_of(P, P->nodes[P->down4].c1.dpad, 0, 4 * c);
@@ -753,6 +767,8 @@ int mimo_unet_backward(mimo_unet_plan_t* P, const float* dout, const float* grad
   ++P->bwd_calls;
   bool has_mask = false;
   for (const float* m : P->masks_copy) has_mask = has_mask || (m != nullptr);
+  has_mask = has_mask || P->center_keep != nullptr;
+  for (const bf16* m : P->final_keep) has_mask = has_mask || (m != nullptr);
   const bool allow = P->graph_mode != 0 && !P->graph_failed && !P->prof && !has_mask && dx == nullptr && P->bwd_calls > 2;
   const unsigned long long key = (tr ? 1ull : 0ull) | (accumulate ? 2ull : 0ull);
   if ((rc = run_graphed(P, P->g_bwd[0], key, allow, st, stage0))) return rc;
@@ -763,6 +779,18 @@ int mimo_unet_backward(mimo_unet_plan_t* P, const float* dout, const float* grad
   if (P->stage_ev[2]) MIMO_CUDA(cudaEventRecord(P->stage_ev[2], st));
   if ((rc = run_graphed(P, P->g_bwd[3], key, allow, st, stage3))) return rc;
   if (P->stage_ev[3]) MIMO_CUDA(cudaEventRecord(P->stage_ev[3], st));
+  return MIMO_OK;
+}
+
+int mimo_unet_set_elementwise_dropout(mimo_unet_plan_t* P, const void* center_keep, float center_scale, const void* const* final_keep,
+                                      float final_scale) {
+  MIMO_CHECK(P, MIMO_ERR_ARG, "set_elementwise_dropout: null plan");
+  P->center_keep = (const bf16*)center_keep;
+  P->center_scale = center_scale;
+  P->final_keep.assign(P->cfg.num_subnetworks, nullptr);
+  if (final_keep)
+    for (int s = 0; s < P->cfg.num_subnetworks; ++s) P->final_keep[s] = (const bf16*)final_keep[s];
+  P->final_scale = final_scale;
   return MIMO_OK;
 }
 

@@ -46,6 +46,7 @@ int upsample_launch(const ActView& in, const ActView& o, cudaStream_t st);
 int upsample_bwd_launch(const ActView& gdst, const ActView& gsrc, int accumulate, cudaStream_t st);
 int grad_gather_launch(const ActView* dpad, const ActView* gpool, const ActView* act, const ActView& gout, int accumulate,
                        cudaStream_t st);
+int mask_mul_launch(const ActView& a, const bf16* keep, int mask_cp, float scale, cudaStream_t st);
 int maxunpool_launch(const ActView& in, const long long* idx_nchw, const ActView& o, cudaStream_t st);
 int convtranspose2x2_launch(const ActView& in, const float* wt, const float* bias, const ActView& o, cudaStream_t st);
 int unpack_nchw_launch(const ActView& in, float* out, cudaStream_t st);

@@ -86,6 +86,19 @@ class UNetPlan:
         check(self.lib.mimo_unet_backward(self.handle, dout.data_ptr(), _ptr(grad_scale), _ptr(dx), int(accumulate), stream_ptr()),
               "mimo_unet_backward")
 
+    def set_elementwise_dropout(self, center_keep: Optional[torch.Tensor], center_scale: float,
+                                final_keep: Optional[Sequence[Optional[torch.Tensor]]], final_scale: float):
+        """nn.Dropout keep masks (bf16 0/1, NHWC with the channel pitch rounded up to 8) for the next forward/backward pair;
+        None disables. See mimo_unet_set_elementwise_dropout."""
+        S = self.cfg.num_subnetworks
+        fk = None
+        if final_keep is not None:
+            assert len(final_keep) == S
+            fk = (C.c_void_p * S)(*[_ptr(m) for m in final_keep])
+        self._elem_keepalive = (center_keep, list(final_keep) if final_keep is not None else None)
+        check(self.lib.mimo_unet_set_elementwise_dropout(self.handle, _ptr(center_keep), float(center_scale), fk, float(final_scale)),
+              "mimo_unet_set_elementwise_dropout")
+
     def set_backward_events(self, events: Optional[Sequence["torch.cuda.Event"]]):
         """events: 4 torch.cuda.Event objects (already recorded once so their handles exist) or None; see
         mimo_unet_set_backward_events."""

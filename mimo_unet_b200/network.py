@@ -142,13 +142,29 @@ class NetworkRuntime:
             masks.append(((m >= p).float() / (1.0 - p)).contiguous())
         return masks
 
-    def _check_unsupported(self):
+    def _elementwise_dropout(self, plan: UNetPlan, B: int, H: int, W: int, device):
+        """nn.Dropout at the core centre (reference model.py:239) and in front of every head (model.py:294): bf16 0/1 keep
+        masks in the executor's NHWC layout, drawn with the CUDA generator; the 1/(1-p) scale is applied in fp32 in-kernel."""
         net = self.net
-        if net.core.center_dropout.training and net.core.center_dropout.p > 0.0:
-            raise NotImplementedError("center_dropout_rate > 0 in training/MC mode is not implemented on B200 yet")
+        S, f = net.num_subnetworks, net.filter_base_count
+
+        def keep(p, h, w, c):
+            cp = (c + 7) // 8 * 8
+            return (torch.rand(B, h, w, cp, device=device) >= p).to(torch.bfloat16).contiguous()
+
+        cd = net.core.center_dropout
+        center, cs = None, 1.0
+        if cd.training and cd.p > 0.0:
+            center, cs = keep(cd.p, H // 16, W // 16, 8 * f * S), 1.0 / (1.0 - cd.p) if cd.p < 1.0 else 0.0
+        finals, fs, any_final = [], 1.0, False
         for d in net.decoder.final_dropouts:
             if d.training and d.p > 0.0:
-                raise NotImplementedError("final_dropout_rate > 0 in training/MC mode is not implemented on B200 yet")
+                finals.append(keep(d.p, H, W, f))
+                fs = 1.0 / (1.0 - d.p) if d.p < 1.0 else 0.0
+                any_final = True
+            else:
+                finals.append(None)
+        plan.set_elementwise_dropout(center, cs, finals if any_final else None, fs)
 
     def __call__(self, x: torch.Tensor, gather: Optional[torch.Tensor] = None):
         net = self.net
@@ -163,7 +179,6 @@ class NetworkRuntime:
                 raise ValueError("with gather, x must be [B, C_in, H, W] and gather int64 [S, B * batch_repetitions]")
             if x.requires_grad:
                 raise NotImplementedError("input gradients are not available together with a gather table")
-        self._check_unsupported()
         params = [p for p in net.parameters()]
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params)):
             return _UNetFunction.apply(self, x, gather, *params)
@@ -190,6 +205,7 @@ class NetworkRuntime:
         # BatchNorm mode follows the BN modules (all share the module's mode; MC-dropout keeps BN in eval)
         bn_training = net.encoder.in_convs[0].double_conv[1].training
         masks = self._dropout_masks(plan, B, dev)
+        self._elementwise_dropout(plan, B, H, W, dev)
         g = None if gather is None else gather.to(device=dev, dtype=torch.int64).contiguous()
         plan.forward(x, out, bn_training, gather=g, drop_masks=masks)
         self._forward_token += 1

@@ -171,12 +171,15 @@ def mimo_unet_forward(
     new_stats: Optional[Dict[str, Tensor]] = None,
     drop_masks: Optional[Dict[str, Tensor]] = None,
     rec: Optional[Recorder] = None,
+    elem_masks: Optional[Dict[str, Tensor]] = None,
 ) -> Tensor:
     """model.py:94-117 (MimoUNet.forward), bilinear=True / use_pooling_indices=False path
     (the only one the reference scripts run, mimo_unet.py:73-74).
 
     x: [B, S, Cin, H, W] -> [B, S, Cout, H, W].
     drop_masks: optional {double_conv prefix: [N, C] scaled keep mask} for Dropout2d.
+    elem_masks: optional scaled keep masks of the element-wise nn.Dropout layers: "center" [B, C5, H/16, W/16]
+    (model.py:239, applied to x5) and "final.<i>" [B, f, H, W] (model.py:294, in front of head i).
     """
     S = num_subnetworks
     assert x.shape[1] == S
@@ -199,6 +202,9 @@ def mimo_unet_forward(
     x3 = dc(maxpool2x2(xc), "core.down2.conv.double_conv.")
     x4 = dc(maxpool2x2(x3), "core.down3.conv.double_conv.")
     x5 = dc(maxpool2x2(x4), "core.down4.conv.double_conv.")
+    em = elem_masks or {}
+    if "center" in em:  # model.py:239
+        x5 = _q(x5 * em["center"], emulate_bf16)
 
     def up(x_low, skip, prefix):  # components.py:106-120
         u = _q(upsample_bilinear2x_ac(x_low), emulate_bf16)
@@ -213,6 +219,8 @@ def mimo_unet_forward(
     outs = []
     for i in range(S):
         d = up(u, x1s[i], f"decoder.up4s.{i}.conv.double_conv.")
+        if f"final.{i}" in em:  # model.py:294
+            d = _q(d * em[f"final.{i}"], emulate_bf16)
         if rec is not None:
             rec.put(f"decoder.feat.{i}", d)
         o = F.conv2d(d, sd[f"decoder.outcs.{i}.conv.weight"], sd[f"decoder.outcs.{i}.conv.bias"])

@@ -523,3 +523,25 @@ def test_head_fwd_bwd(lib):
     assert rel_l2(get_nchw(gb, 0, 0, f), bf16r(fq.grad)) <= TOL
     assert rel_l2(dw, wq.grad) <= 1e-5 and rel_l2(db, bq.grad) <= 1e-5
     assert torch.all(gb[..., f:] == 0)
+
+
+@pytest.mark.parametrize("C_,c_off,cp,pad", [(21, 0, 24, 1), (336, 0, 336, 1), (13, 8, 32, 0), (42, 21, 64, 0)])
+def test_mask_mul_elementwise_dropout(lib, C_, c_off, cp, pad):
+    """nn.Dropout as a keep-mask multiply (reference model.py:239,294): interior scaled in fp32, everything else untouched."""
+    torch.manual_seed(21)
+    N, H, W = 2, 5, 7
+    x = bf16r(torch.randn(N, C_, H, W, device="cuda"))
+    buf = make_buffer(N, H, W, pad, cp, fill=3.0)
+    put_nchw(buf, x, pad, c_off)
+    before = buf.clone()
+    keep = (torch.rand(N, H, W, p8(C_), device="cuda") >= 0.3).to(torch.bfloat16).contiguous()
+    scale = 1.0 / 0.7
+    _lib.check(lib.mimo_mask_mul(act_of(buf, pad, c_off, C_), keep.data_ptr(), p8(C_), scale, stream()))
+    got = get_nchw(buf, pad, c_off, C_)
+    ref = bf16r(x * keep[..., :C_].permute(0, 3, 1, 2).float() * scale)
+    assert torch.equal(got, ref)
+    # channels outside the view and the halo are untouched
+    after = buf.clone()
+    o = 1 if pad == 1 else 0
+    after[:, o:o + H, o:o + W, c_off:c_off + C_] = before[:, o:o + H, o:o + W, c_off:c_off + C_]
+    assert torch.equal(after, before)

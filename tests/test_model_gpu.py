@@ -253,3 +253,51 @@ def test_graph_replay_matches_eager(cases):
     torch.cuda.synchronize()
     assert torch.isfinite(dx).all() and float(dx.abs().sum()) > 0
     assert (plan.graph_state & 0x100) == 0
+
+
+def test_elementwise_center_and_final_dropout_vs_oracle(cases):
+    """center_dropout (model.py:239) and final_dropouts (model.py:294) with explicit keep masks: train-mode forward and
+    parameter gradients against the oracle carrying the same masks."""
+    c = cases["m2_f8_32x32"]
+    cfg = c["cfg"]
+    S, f, cin = cfg["S"], cfg["f"], cfg["cin"]
+    sd = O.make_state_dict(cin, 2, S, f, cfg["seed"])
+    x = c["x"].cuda().contiguous()
+    B, _, _, H, W = x.shape
+    torch.manual_seed(5)
+    C5 = 8 * f * S
+    keep_c = (torch.rand(B, H // 16, W // 16, C5, device="cuda") >= 0.3).to(torch.bfloat16).contiguous()
+    keep_f = [(torch.rand(B, H, W, (f + 7) // 8 * 8, device="cuda") >= 0.2).to(torch.bfloat16).contiguous() for _ in range(S)]
+    sc, sf = 1.0 / 0.7, 1.0 / 0.8
+    plan = UNetPlan(cin, 2, S, f, B, H, W, torch.device("cuda"))
+    names = [n for n, _, _ in O.state_dict_spec(cin, 2, S, f)]
+    state = [sd[n].cuda().contiguous() for n in names]
+    grads = [torch.zeros_like(t) if t.dtype == torch.float32 and ("running" not in n) else None for n, t in zip(names, state)]
+    plan.bind(state, grads)
+    plan.set_elementwise_dropout(keep_c, sc, keep_f, sf)
+    out = torch.empty(B, S, 2, H, W, device="cuda")
+    plan.forward(x, out, True)
+    dout = (torch.randn(B, S, 2, H, W, device="cuda") * 1e-2).contiguous()
+    plan.backward(dout)
+    torch.cuda.synchronize()
+    em = {"center": keep_c.float().permute(0, 3, 1, 2) * sc}
+    for i in range(S):
+        em[f"final.{i}"] = keep_f[i][..., :f].float().permute(0, 3, 1, 2) * sf
+    p = {k: (v.cuda().clone().requires_grad_(True) if v.dtype == torch.float32 and "running" not in k else v.cuda().clone())
+         for k, v in sd.items()}
+    ref = O.mimo_unet_forward(x, p, S, training=True, emulate_bf16=True, elem_masks=em)
+    assert rel_l2(out, ref.detach()) <= 4e-2
+    # without the masks the result is clearly different (the masks are really applied)
+    ref_nomask = O.mimo_unet_forward(x, {k: v.detach() for k, v in p.items()}, S, training=True, emulate_bf16=True)
+    assert rel_l2(out, ref_nomask) > 4 * rel_l2(out, ref.detach())
+    ref.backward(dout)
+    # head and last decoder conv see the final mask directly; a core-centre layer sees the centre mask
+    for key in ["decoder.outcs.0.conv.weight", "decoder.up4s.1.conv.double_conv.3.weight", "core.down4.conv.double_conv.3.weight",
+                "core.up1.conv.double_conv.0.weight"]:
+        g = grads[names.index(key)]
+        assert _cos(g, p[key].grad) >= 0.97, key
+    # a pass without masks afterwards is unaffected (the masks belong to one forward/backward pair only when reset)
+    plan.set_elementwise_dropout(None, 1.0, None, 1.0)
+    out2 = torch.empty_like(out)
+    plan.forward(x, out2, True)
+    assert rel_l2(out2, ref_nomask) <= 4e-2

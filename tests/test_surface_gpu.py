@@ -242,3 +242,23 @@ def test_component_blocks_vs_golden(golden_dir):
     oc = comp.OutConv(21, 2).cuda()
     xf = torch.rand(2, 21, 9, 7, device="cuda")
     assert torch.allclose(oc(xf), F.conv2d(bf16r(xf), oc.conv.weight, oc.conv.bias), atol=1e-5, rtol=1e-5)
+
+
+def test_center_and_final_dropout_module_surface():
+    """center_dropout_rate / final_dropout_rate of the reference constructor (model.py:37-38): active in train mode and under
+    MC dropout, identity in eval mode."""
+    m = make_model(S=2, f=8, center_dropout_rate=0.3, final_dropout_rate=0.2)
+    x = torch.rand(3, 2, 3, 32, 32, device="cuda")
+    m.eval()
+    with torch.no_grad():
+        a1, _ = m(x)
+        a2, _ = m(x)
+    assert torch.equal(a1, a2)
+    m.train()
+    with torch.no_grad():
+        q1, _ = m(x)
+    p1, p2 = m(x)
+    assert not torch.equal(p1, q1)  # fresh masks every pass
+    (p1.mean() + p2.mean()).backward()
+    g = m.model.core.down4.conv.double_conv[3].weight.grad
+    assert g is not None and torch.isfinite(g).all() and float(g.abs().sum()) > 0
