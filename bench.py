@@ -28,6 +28,14 @@ import torch  # noqa: E402
 
 CFG = dict(in_channels=3, out_channels=2, num_subnetworks=2, filter_base_count=21, height=128, width=160, batch=64)
 WORKLOAD = "C2 NYUv2-shape MIMO U-Net M=2 fbc=21 3x128x160 batch 64/GPU train step (fwd+laplace_nll+loss-buffer+bwd+Adam)"
+# other BASELINE.json configs, selectable with --workload (parity-test cases; the headline line is C2)
+WORKLOADS = {
+    "C2": (CFG, WORKLOAD),
+    "C3": (dict(in_channels=2, out_channels=2, num_subnetworks=2, filter_base_count=30, height=256, width=256, batch=32),
+           "C3 SEN12TP-NDVI-shape MIMO U-Net M=2 fbc=30 2x256x256 batch 32/GPU train step (fwd+laplace_nll+loss-buffer+bwd+Adam)"),
+    "C1": (dict(in_channels=3, out_channels=2, num_subnetworks=2, filter_base_count=21, height=256, width=256, batch=8),
+           "C1 MIMO U-Net M=2 fbc=21 3x256x256 batch 8 train step (the reference's CPU-runnable case)"),
+}
 
 
 def load_peaks():
@@ -214,7 +222,7 @@ def run_gpu_arm(args):
     opt = model.configure_optimizers()["optimizer"]
     torch.manual_seed(1 + rank)
     n_host = 4  # rotating pinned host batches (synthetic, U[0,1) like the /255 datasets)
-    host = [(torch.rand(B, 3, H, W).pin_memory(), torch.rand(B, 1, H, W).pin_memory()) for _ in range(n_host)]
+    host = [(torch.rand(B, CFG["in_channels"], H, W).pin_memory(), torch.rand(B, 1, H, W).pin_memory()) for _ in range(n_host)]
     dev_batches = [(a.to(dev), b.to(dev)) for a, b in host]
     # L2 hygiene: the step touches several GB of activations (>> 126 MB L2), so the L2 is flushed by the step itself
     loss_host = torch.zeros(1).pin_memory()
@@ -233,20 +241,45 @@ def run_gpu_arm(args):
         opt.step()
         return loss
 
+    # e2e: every step's inputs travel pinned host -> device INSIDE the timed region, on a copy stream that runs one batch
+    # ahead of the compute stream (double-buffered device staging, what a prefetching data loader does); the loss is read
+    # back to pinned host memory every step
+    copy_stream = torch.cuda.Stream()
+    stage = [(torch.empty(B, CFG["in_channels"], H, W, device=dev), torch.empty(B, 1, H, W, device=dev)) for _ in range(2)]
+    staged = [torch.cuda.Event() for _ in range(2)]    # batch landed in stage[k]
+    consumed = [torch.cuda.Event() for _ in range(2)]  # the step that read stage[k] has been enqueued and finished
+
+    def prefetch(i):
+        k = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[k])
+            a, b = host[i % n_host]
+            stage[k][0].copy_(a, non_blocking=True)
+            stage[k][1].copy_(b, non_blocking=True)
+            staged[k].record(copy_stream)
+
     def timed(n_steps, from_host):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+        cur = torch.cuda.current_stream()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        if from_host:
+            for k in range(2):
+                consumed[k].record(cur)
+            prefetch(0)
         for i in range(n_steps):
             if from_host:
-                a, b = host[i % n_host]
-                image, label = a.to(dev, non_blocking=True), b.to(dev, non_blocking=True)
+                if i + 1 < n_steps:
+                    prefetch(i + 1)
+                cur.wait_event(staged[i % 2])
+                image, label = stage[i % 2]
             else:
                 image, label = dev_batches[i % n_host]
             loss = step(image, label)
             if from_host:
+                consumed[i % 2].record(cur)
                 loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
         e1.record()
         torch.cuda.synchronize()
@@ -295,7 +328,7 @@ def run_gpu_arm(args):
         achieved = (fprop_fl + dgrad_fl) / t_conv / 1e12
         traffic = None
         tp = os.path.join(ROOT, "profiles", "conv_traffic.json")  # written by tools/gpu/evidence.sh from an ncu metric pass
-        if os.path.isfile(tp):
+        if os.path.isfile(tp) and args.workload == "C2":
             try:
                 traffic = json.load(open(tp)).get("dram_bytes_per_launch")
             except Exception:
@@ -331,7 +364,7 @@ def run_gpu_arm(args):
 
     if rank == 0:
         total_images = B * world * args.steps
-        h2d = (3 + 1) * B * H * W * 4
+        h2d = (CFG["in_channels"] + 1) * B * H * W * 4
         line = {
             "metric": "train_images_per_sec", "value": total_images / (ms * 1e-3), "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -357,9 +390,12 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", type=str, default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-infer", action="store_true", help="skip the secondary inference (MPix/s) measurements")
     args = ap.parse_args()
+    global CFG, WORKLOAD
+    CFG, WORKLOAD = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference_arm(args)
     else:

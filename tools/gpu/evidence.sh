@@ -10,6 +10,9 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smok
 t "smoke rc=$?"; tail -2 gpurun_out/smoke.log
 timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/${R}_bench.json 2> gpurun_out/bench.err
 t "bench rc=$?"; tail -c 3000 gpurun_out/${R}_bench.json
+timeout 300 python bench.py --workload C3 --steps 10 --warmup 4 --no-cpu-baseline --no-infer > gpurun_out/${R}_bench_c3.json 2> gpurun_out/bench_c3.err
+t "bench C3 rc=$?"; python -c "
+import json;d=json.load(open('gpurun_out/${R}_bench_c3.json'));print('C3', d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['achieved'], d['roofline']['frac'])"
 timeout 300 python tools/profile_layers.py --cfg C2 --out gpurun_out/${R}_layers_c2.txt > gpurun_out/layers.log 2>&1
 t "layers rc=$?"; tail -3 gpurun_out/layers.log
 timeout 300 python tools/bench_loss.py > gpurun_out/${R}_loss_bw.txt 2>&1
