@@ -297,9 +297,9 @@ def run_gpu_arm(args):
     if rank == 0:
         sampler.start()
     ms = timed(args.steps, False)
-    clocks = sampler.stop() if rank == 0 else None
     timed(1, True)
     ms_e2e = timed(args.steps, True)
+    clocks = sampler.stop() if rank == 0 else None  # sampled over both timed regions (device-resident and end-to-end)
     rt = model.model._runtime
     launches_per_step = rt.last_launches[0] + rt.last_launches[1] + 3  # + fused loss (2) + gradient-seed scale (1)
 

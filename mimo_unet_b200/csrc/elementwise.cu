@@ -220,7 +220,7 @@ __global__ void bn_eval_affine_kernel(int C, const float* gamma, const float* be
 // registers) and walks rows of 2x2 cells; 16-byte loads, packed bf16 stores, the 2x2 max is taken on the packed
 // (stored) values with the NaN-propagating bf16x2 max.
 template <bool VEC_O, bool VEC_P>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 2)
 bn_relu_apply_kernel(const bf16* __restrict__ y, int ycp, const float* __restrict__ scale,
                      const float* __restrict__ shift, const float* __restrict__ drop /*[N][C] or null*/,
                      ActView o, ActView pool, int do_pool) {
