@@ -1,13 +1,20 @@
-from pathlib import Path
+"""Small host-side helpers of the reference's `mimo.utils` surface (reference: mimo/utils.py): an argparse type for
+directories and the trainable-parameter count that MimoUnetModel stores in its hyper-parameters."""
+import os
+import pathlib
 
 
-def dir_path(string) -> Path:
-    """argparse helper: the argument must name an existing directory."""
-    p = Path(string)
-    if not p.is_dir():
-        raise NotADirectoryError(string)
-    return p
+def dir_path(string) -> pathlib.Path:
+    """argparse `type=`: accepts only names of existing directories, returns them as a Path."""
+    if os.path.isdir(string):
+        return pathlib.Path(string)
+    raise NotADirectoryError(string)
 
 
 def count_trainable_parameters(model) -> int:
-    return sum(p.numel() for p in model.parameters() if p.requires_grad)
+    """Number of scalar parameters that receive gradients."""
+    total = 0
+    for param in model.parameters():
+        if param.requires_grad:
+            total += param.numel()
+    return total
