@@ -125,6 +125,12 @@ int mimo_bn_relu_bwd_folded(mimo_act_t dpad, mimo_act_t g_scratch, const void* y
                             int training, float* part, float* s1s2, float* dgamma, float* dbeta, float* dbias,
                             int accumulate, mimo_act_t dy, void* stream);
 
+/* Host-only (no device work): the stream-K schedule of the weight-gradient kernel for a layer with `cout` x `cin` channels
+ * over `positions` = N*(H+2)*(W+2) grid positions on `sms` SMs. segments == NULL: returns the grid size. Otherwise writes
+ * up to max_segments entries {co tile, first ci chunk, ci chunks (1|2), kh, first k-block, end k-block} of CTA `cta` and
+ * returns how many segments that CTA has. Every (co tile, ci chunk, kh, k-block) is covered exactly once over all CTAs. */
+int mimo_wgrad_streamk_schedule(int cout, int cin, long long positions, int sms, int cta, int* segments, int max_segments);
+
 /* nn.Dropout (element-wise; reference model.py:239 center_dropout, model.py:294 final_dropouts): a *= keep * scale in place on
  * the interior of the view; keep = dense bf16 0/1 [N][H][W][mask_cpitch], scale = 1/(1-p). Backward = same call on the gradient. */
 int mimo_mask_mul(mimo_act_t a, const void* keep, int mask_cpitch, float scale, void* stream);

@@ -69,6 +69,7 @@ SIGNATURES = {
     "mimo_bn_bwd_scratch_floats": (sz, [i32]),
     "mimo_bn_relu_bwd": (i32, [Act, vp, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, i32, Act, vp]),
     "mimo_bn_relu_bwd_folded": (i32, [Act, Act, vp, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, i32, Act, vp]),
+    "mimo_wgrad_streamk_schedule": (i32, [i32, i32, i64, i32, i32, vp, i32]),
     "mimo_mask_mul": (i32, [Act, vp, i32, f32, vp]),
     "mimo_unet_set_elementwise_dropout": (i32, [vp, vp, f32, vp, f32]),
     "mimo_head1x1": (i32, [Act, vp, vp, i32, vp, i64, vp]),

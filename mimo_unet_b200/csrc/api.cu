@@ -135,6 +135,10 @@ int mimo_bn_relu_bwd_folded(mimo_act_t dpad, mimo_act_t g_scratch, const void* y
                        dgamma, dbeta, dbias, 1.f, accumulate, make_view(dy), (cudaStream_t)stream, &d);
 }
 
+int mimo_wgrad_streamk_schedule(int cout, int cin, long long positions, int sms, int cta, int* segments, int max_segments) {
+  return conv3x3_wgrad_flatk_schedule(cout, cin, positions, sms, cta, segments, max_segments);
+}
+
 int mimo_mask_mul(mimo_act_t a, const void* keep, int mask_cpitch, float scale, void* stream) {
   MIMO_CHECK(a.ptr && keep, MIMO_ERR_ARG, "mask_mul: null pointer");
   return mask_mul_launch(make_view(a), (const bf16*)keep, mask_cpitch, scale, (cudaStream_t)stream);

@@ -60,16 +60,16 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 struct SegWalk {
   long long w, w_end;
   int kb0, kb1, nci, cot, cic0, kh;
-  __device__ SegWalk(const WgFlatKParams& p) {
-    w = cut(p, blockIdx.x);
-    w_end = cut(p, blockIdx.x + 1);
+  __host__ __device__ SegWalk(const WgFlatKParams& p, unsigned cta, unsigned grid) {
+    w = cut(p, cta, grid);
+    w_end = cut(p, cta + 1, grid);
   }
-  static __device__ long long cut(const WgFlatKParams& p, unsigned c) {
-    long long v = (long long)c * p.Wtot / (long long)gridDim.x;
+  static __host__ __device__ long long cut(const WgFlatKParams& p, unsigned c, unsigned grid) {
+    long long v = (long long)c * p.Wtot / (long long)grid;
     if (v < p.W2) v &= ~1ll;   // a k-block of a two-chunk item weighs 2: cuts fall on k-block edges
     return v;
   }
-  __device__ bool next(const WgFlatKParams& p) {
+  __host__ __device__ bool next(const WgFlatKParams& p) {
     if (w >= w_end) return false;
     long long seg_end;
     if (w < p.W2) {
@@ -100,6 +100,26 @@ struct SegWalk {
     return true;
   }
 };
+
+// shape -> schedule parameters (shared by the launcher and the host-side schedule dump used by the CPU tests)
+void plan_schedule(WgFlatKParams& p, int cout, int cin, long long total_pos) {
+  p.n_kb = (int)ceil_div_ll(total_pos, kBlockK);
+  const int co_tiles = ceil_div(cout, 128);
+  p.ci_chunks = ceil_div(cin, 64);
+  p.n_pairs = p.ci_chunks / 2;
+  p.n2_items = co_tiles * p.n_pairs * 3;
+  const int n1_items = (p.ci_chunks & 1) ? co_tiles * 3 : 0;
+  p.W2 = (long long)p.n2_items * p.n_kb * 2;
+  p.Wtot = p.W2 + (long long)n1_items * p.n_kb;
+}
+
+int plan_grid(const WgFlatKParams& p, int sms) {
+  // every CTA should own at least a few k-blocks; tiny layers use fewer CTAs
+  long long grid = p.Wtot / 4;
+  if (grid > sms) grid = sms;
+  if (grid < 1) grid = 1;
+  return (int)grid;
+}
 
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_wgrad_flatk_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x,
@@ -137,7 +157,7 @@ conv3x3_wgrad_flatk_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __
 
   if (warp == 0) {
     // ===================== TMA producer (warp-uniform loops, one elected lane issues) =====================
-    SegWalk sw(p);
+    SegWalk sw(p, blockIdx.x, gridDim.x);
     int stage = 0; uint32_t phase = 0;
     while (sw.next(p)) {
       const uint32_t tx = (uint32_t)(2 * kDyBox + sw.nci * (kDyBox + 2 * 128));
@@ -169,7 +189,7 @@ conv3x3_wgrad_flatk_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __
     // X: 64-ci block j at LBO * j = j positions further = kw tap j.
     const uint32_t a_lo0 = desc_lo(smem_u32(smem), kDyBox);
     const uint32_t b_lo0 = desc_lo(smem_u32(smem) + 2 * kDyBox, 128);
-    SegWalk sw(p);
+    SegWalk sw(p, blockIdx.x, gridDim.x);
     int stage = 0; uint32_t phase = 0;
     uint32_t n = 0;
     while (sw.next(p)) {
@@ -206,7 +226,7 @@ conv3x3_wgrad_flatk_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __
     // ===================== flush (4 warps): lane = co, column = kw * 64 + ci =====================
     const int q = warp & 3;
     const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    SegWalk sw(p);
+    SegWalk sw(p, blockIdx.x, gridDim.x);
     uint32_t n = 0;
     while (sw.next(p)) {
       mbar_wait(acc_full, n & 1u);
@@ -257,14 +277,7 @@ int conv3x3_wgrad_flatk_launch(const ActView& dy, const ActView& x, float* dw, i
   WgFlatKParams p{};
   p.wb = x.wb();
   const long long total_pos = (long long)x.N * x.hb() * x.wb();
-  p.n_kb = (int)ceil_div_ll(total_pos, kBlockK);
-  const int co_tiles = ceil_div(dy.C, 128);
-  p.ci_chunks = ceil_div(x.C, 64);
-  p.n_pairs = p.ci_chunks / 2;
-  p.n2_items = co_tiles * p.n_pairs * 3;
-  const int n1_items = (p.ci_chunks & 1) ? co_tiles * 3 : 0;
-  p.W2 = (long long)p.n2_items * p.n_kb * 2;
-  p.Wtot = p.W2 + (long long)n1_items * p.n_kb;
+  plan_schedule(p, dy.C, x.C, total_pos);
   p.cout = dy.C; p.cin_pitch = cin_pitch;
   p.dw = dw;
 
@@ -294,13 +307,31 @@ int conv3x3_wgrad_flatk_launch(const ActView& dy, const ActView& x, float* dw, i
     MIMO_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_flatk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     attr_set = true;
   }
-  // every CTA should own at least a few k-blocks; tiny layers use fewer CTAs
-  long long grid = p.Wtot / 4;
-  if (grid > num_sms()) grid = num_sms();
-  if (grid < 1) grid = 1;
-  conv3x3_wgrad_flatk_kernel<<<(int)grid, kThreads, smem_bytes, stream>>>(tm_dy, tm_x, tm_x2, p);
+  const int grid = plan_grid(p, num_sms());
+  conv3x3_wgrad_flatk_kernel<<<grid, kThreads, smem_bytes, stream>>>(tm_dy, tm_x, tm_x2, p);
   MIMO_LAUNCH_CHECK();
   return MIMO_OK;
+}
+
+// Host-side dump of the stream-K schedule (pure arithmetic, no device): segment `j` of CTA `cta` as
+// {co tile, first ci chunk, ci chunks, kh, first k-block, end k-block}; returns the number of segments of that CTA written
+// (at most max_segs), or the grid size when out == nullptr.
+int conv3x3_wgrad_flatk_schedule(int cout, int cin, long long total_pos, int sms, int cta, int* out, int max_segs) {
+  WgFlatKParams p{};
+  plan_schedule(p, cout, cin, total_pos);
+  const int grid = plan_grid(p, sms);
+  if (out == nullptr) return grid;
+  if (cta < 0 || cta >= grid) return 0;
+  SegWalk sw(p, (unsigned)cta, (unsigned)grid);
+  int n = 0;
+  while (sw.next(p)) {
+    if (n < max_segs) {
+      int* o = out + 6 * n;
+      o[0] = sw.cot; o[1] = sw.cic0; o[2] = sw.nci; o[3] = sw.kh; o[4] = sw.kb0; o[5] = sw.kb1;
+    }
+    ++n;
+  }
+  return n;
 }
 
 }  // namespace mimo

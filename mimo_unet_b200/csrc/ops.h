@@ -28,6 +28,7 @@ struct WeightPackJob { const float* w; bf16* wf; bf16* wd; int cout, cin, cin_pi
 struct WgradUnpackJob { const float* packed; float* grad; int cout, cin, cin_pitch; };
 int weight_pack_batched_launch(const WeightPackJob* jobs, int n, cudaStream_t st);
 int wgrad_unpack_batched_launch(const WgradUnpackJob* jobs, int n, float scale, int accumulate, cudaStream_t st);
+int conv3x3_wgrad_flatk_schedule(int cout, int cin, long long total_pos, int sms, int cta, int* out, int max_segs);
 int wgrad_unpack_launch(const float* packed, float* grad_oihw, int cout, int cin, int cin_pitch, float scale, int accumulate,
                         cudaStream_t stream);
 

@@ -87,3 +87,43 @@ def test_data_parallel_exchange_gloo_world2(tmp_path):
         losses.append(loss.detach())
     assert torch.allclose(r0["flat"], (flats[0] + flats[1]) / 2, rtol=1e-5, atol=1e-8)
     assert torch.allclose(r0["loss"], (losses[0] + losses[1]) / 2, rtol=1e-6)
+
+
+@pytest.mark.parametrize("cout,cin,positions,sms", [
+    (336, 672, 64 * 18 * 22, 148),    # core.up1.c1 at C2
+    (84, 168, 64 * 66 * 82, 148),     # core.up3.c1 at C2 (pair + single ci chunk)
+    (336, 336, 64 * 10 * 12, 148),    # core.down4 at C2 (tiny map)
+    (70, 100, 2 * 9 * 11, 148),       # fewer work units than SMs
+    (130, 40, 3 * 8 * 12, 148),       # single ci chunk only: no two-chunk items
+    (480, 960, 32 * 34 * 34, 148),    # C3 core (fbc 30)
+    (65, 64, 7, 5),                   # one k-block
+    (168, 84, 1428 * 64, 132),        # another SM count
+])
+def test_wgrad_streamk_schedule_covers_every_unit_once(cout, cin, positions, sms):
+    """Host-side dump of the stream-K schedule of the weight-gradient kernel (conv_wgrad_flatk.cu): every
+    (co tile, ci chunk, kh, k-block) unit is owned by exactly one CTA segment, and the CTAs' MMA counts are balanced."""
+    import ctypes as C
+    import numpy as np
+    from mimo_unet_b200 import _lib
+    lib = _lib.lib()
+    grid = lib.mimo_wgrad_streamk_schedule(cout, cin, positions, sms, 0, None, 0)
+    assert 1 <= grid <= sms
+    n_kb = -(-positions // 128)
+    co_tiles, ci_chunks = -(-cout // 128), -(-cin // 64)
+    seen = np.zeros((co_tiles, ci_chunks, 3, n_kb), dtype=np.int32)
+    weights = []
+    buf = (C.c_int * (6 * 64))()
+    for cta in range(grid):
+        n = lib.mimo_wgrad_streamk_schedule(cout, cin, positions, sms, cta, buf, 64)
+        assert 0 <= n <= 64
+        w = 0
+        for j in range(n):
+            cot, cic0, nci, kh, kb0, kb1 = (buf[6 * j + k] for k in range(6))
+            assert nci in (1, 2) and 0 <= kb0 < kb1 <= n_kb and 0 <= kh < 3
+            seen[cot, cic0:cic0 + nci, kh, kb0:kb1] += 1
+            w += nci * (kb1 - kb0)
+        weights.append(w)
+    assert int(seen.min()) == 1 and int(seen.max()) == 1
+    total = co_tiles * ci_chunks * 3 * n_kb
+    assert sum(weights) == total
+    assert max(weights) - min(weights) <= 3  # equal shares up to rounding onto k-block edges
