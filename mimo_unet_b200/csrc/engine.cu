@@ -85,7 +85,7 @@ struct mimo_unet_plan {
   // CUDA graphs of the fixed launch sequences (forward body; the four backward stages). Only launches whose arguments are
   // workspace / bound-state pointers are captured; the kernels that touch caller tensors (input packing, heads) stay eager,
   // so a graph stays valid for as long as the binding does.
-  struct GraphSlot { cudaGraphExec_t exec = nullptr; unsigned long long key = ~0ull; int launches = 0; };
+  struct GraphSlot { cudaGraphExec_t exec = nullptr; unsigned long long key = ~0ull; int launches = 0; int captures = 0; };
   GraphSlot g_fwd, g_bwd[4];
   cudaStream_t cap_stream = nullptr;   // private stream the graphs are captured on
   int graph_mode = 1;          // env MIMO_GRAPH (0 disables)
@@ -222,6 +222,9 @@ int run_graphed(mimo_unet_plan* P, mimo_unet_plan::GraphSlot& slot, unsigned lon
     return MIMO_OK;
   }
   if (slot.exec) { cudaGraphExecDestroy(slot.exec); slot.exec = nullptr; }
+  // a caller that keeps alternating keys (BatchNorm mode / accumulate flag every call) would re-capture every time, which is
+  // slower than plain launches: give up on graphs for this plan after a few dozen captures of the same sequence
+  if (++slot.captures > 32) { P->graph_failed = true; return body(); }
   // `st` is the variable the body's launches read (captured by reference). The capture runs on a private stream -- the
   // caller's stream is usually the legacy default stream, which cannot capture, and nothing executes during capture anyway
   // -- and the instantiated graph is launched on the caller's stream.
