@@ -153,3 +153,38 @@ def test_product_surface_matches_reference_names():
         assert all(sa[k].shape == sb[k].shape and sa[k].dtype == sb[k].dtype for k in sa)
     with pytest.raises(ValueError):
         MimoUNet(3, 2, 2, 8, encoder_dropout_rate=0.1, center_dropout_rate=0.1)
+
+
+@needs_ref
+def test_oracle_elementwise_dropout_placement_equals_reference_live():
+    """center_dropout (reference model.py:239) and final_dropouts (model.py:294): the keep masks the reference's nn.Dropout
+    modules actually drew are captured with forward hooks (output / input) and replayed through the oracle's `elem_masks`."""
+    ref = _refload.load()
+    S, f, H, W = 2, 8, 32, 48
+    sd = O.make_state_dict(3, 2, S, f, seed=4)
+    m = ref.model.MimoUNet(3, 2, S, f, center_dropout_rate=0.3, final_dropout_rate=0.2)
+    m.load_state_dict(sd)
+    m.train()
+    masks = {}
+
+    def grab(name):
+        def hook(mod, inp, out):
+            x = inp[0]
+            scale = 1.0 / (1.0 - mod.p)
+            keep = torch.where(x != 0, out / (x * scale), torch.ones_like(x))  # x == 0: mask irrelevant
+            masks[name] = keep.round() * scale
+        return hook
+
+    m.core.center_dropout.register_forward_hook(grab("center"))
+    for i, d in enumerate(m.decoder.final_dropouts):
+        d.register_forward_hook(grab(f"final.{i}"))
+    torch.manual_seed(3)
+    x = torch.rand(2, S, 3, H, W)
+    with torch.no_grad():
+        y_ref = m(x)
+    assert set(masks) == {"center", "final.0", "final.1"}
+    assert 0.05 < float((masks["center"] == 0).float().mean()) < 0.6
+    y = O.mimo_unet_forward(x, sd, S, training=True, elem_masks=masks)
+    assert (y - y_ref).abs().max() <= 1e-4
+    y_plain = O.mimo_unet_forward(x, sd, S, training=True)
+    assert (y_plain - y_ref).abs().max() > 1e-2  # the masks matter
