@@ -127,3 +127,17 @@ def test_wgrad_streamk_schedule_covers_every_unit_once(cout, cin, positions, sms
     total = co_tiles * ci_chunks * 3 * n_kb
     assert sum(weights) == total
     assert max(weights) - min(weights) <= 3  # equal shares up to rounding onto k-block edges
+
+
+def test_bench_flop_accounting_matches_survey():
+    """Numerator of bench.py's roofline: algorithmic 3x3-conv FLOPs with true channel counts: C2 forward is
+    9.936 GFLOP/sample including the 1x1 heads (0.0034), dgrad skips the two image convolutions."""
+    import importlib
+    bench = importlib.import_module("bench")
+    bench.CFG, bench.WORKLOAD = bench.WORKLOADS["C2"]
+    fprop, dgrad = bench.conv_flops_per_step(64)
+    heads = 2 * 2 * 21 * 2 * 128 * 160 * 64
+    assert abs((fprop + heads) / 64 / 1e9 - 9.936) < 2e-3
+    first = 2 * (2.0 * 128 * 160 * 21 * 3 * 9) * 64  # encoder.in_convs.{0,1} first conv: no input gradient in training
+    assert abs(dgrad - (fprop - first)) / fprop < 1e-9
+    assert abs((2 * fprop + dgrad + 3 * heads) / 64 / 1e9 - 29.762) < 2e-2
