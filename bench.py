@@ -199,6 +199,20 @@ def infer_throughput(dev, batch=64, mc_steps=1, steps=10, warmup=3, M=4, f=21, H
     return batch * H * W / (ms * 1e-3) / 1e6, ms
 
 
+def conv_flops_per_node(batch):
+    """Algorithmic FLOPs of ONE pass (fprop = dgrad = wgrad) of every 3x3 conv, indexed by the executor's launch tag
+    2 * node + conv, nodes in state_dict order: encoder.in_convs.*, encoder.down1s.*, core.down2..up3, decoder.up4s.*."""
+    from oracle import mimo_oracle as O
+    rows = [r for r in O.conv_layer_table(CFG["in_channels"], CFG["num_subnetworks"], CFG["filter_base_count"], CFG["height"], CFG["width"])
+            if r[6] == 3]
+    out = []
+    for c1, c2 in zip(rows[0::2], rows[1::2]):
+        for _ in range(c1[1]):  # instances (one per subnetwork for encoder / decoder blocks)
+            for (_, _, ci, co, h, w, _) in (c1, c2):
+                out.append(2.0 * h * w * co * ci * 9 * batch)
+    return out
+
+
 def run_gpu_arm(args):
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -316,11 +330,23 @@ def run_gpu_arm(args):
     if rank == 0:
         import ctypes as C
         ncls = lib.mimo_unet_profile_classes()
-        msb = (C.c_float * ncls)()
-        cnt = (C.c_int * ncls)()
-        lib.mimo_unet_profile_read(plan.handle, msb, cnt)
-        lib.mimo_unet_profile_enable(plan.handle, 0)
         names = [lib.mimo_unet_profile_class_name(i).decode() for i in range(ncls)]
+        NL = 4096
+        lms, lcls, ltag, lkid = (C.c_float * NL)(), (C.c_int * NL)(), (C.c_int * NL)(), (C.c_int * NL)()
+        nl = lib.mimo_unet_profile_read_launches_ex(plan.handle, NL, lms, lcls, ltag, lkid)
+        lib.mimo_unet_profile_enable(plan.handle, 0)
+        msb, cnt = [0.0] * ncls, [0] * ncls
+        node_fl = conv_flops_per_node(B)   # tag = 2 * node + conv  ->  algorithmic FLOPs of that layer (one of fprop/dgrad/wgrad)
+        by_kernel = {}
+        for i in range(nl):
+            msb[lcls[i]] += lms[i]
+            cnt[lcls[i]] += 1
+            if lkid[i] > 0 and 0 <= ltag[i] < len(node_fl):
+                k = lib.mimo_conv_kernel_name(lkid[i]).decode()
+                e = by_kernel.setdefault(k, {"launches": 0, "ms": 0.0, "flops": 0.0})
+                e["launches"] += 1
+                e["ms"] += lms[i]
+                e["flops"] += node_fl[ltag[i]]
         per_step = {n: (msb[i] / 3.0, cnt[i] // 3) for i, n in enumerate(names)}
         fprop_fl, dgrad_fl = conv_flops_per_step(B)
         t_conv = (per_step["conv_fprop"][0] + per_step["conv_dgrad"][0]) * 1e-3
@@ -341,7 +367,12 @@ def run_gpu_arm(args):
                 "avg_launch_us": t_conv * 1e6 / max(1, per_step["conv_fprop"][1] + per_step["conv_dgrad"][1]),
                 "breakdown_ms_per_step": {k: round(v[0], 4) for k, v in per_step.items()},
                 "breakdown_launches_per_step": {k: v[1] for k, v in per_step.items()},
-                "note": "per-class CUDA-event timing taken in 3 extra profiled steps right after the timed region"}
+                "by_kernel": {k: {"launches_per_step": v["launches"] // 3, "ms_per_step": round(v["ms"] / 3.0, 4),
+                                  "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1) if v["ms"] > 0 else None,
+                                  "frac_of_peak": round(v["flops"] / (v["ms"] * 1e-3) / 1e12 / sustained, 4) if v["ms"] > 0 else None}
+                              for k, v in sorted(by_kernel.items())},
+                "note": "per-launch CUDA-event timing taken in 3 extra profiled steps (eager launches) right after the timed region; "
+                        "by_kernel: algorithmic FLOPs (true channel counts) of the launches each tensor-core kernel served / their time"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -236,6 +236,9 @@ int mimo_unet_profile_read(mimo_unet_plan_t* plan, float* ms_by_class, int* coun
 /* per-launch variant: fills up to max_n entries (ms, class, tag = 2*double_conv_index + second_conv or -1) in
  * enqueue order and returns how many; resets the recording like mimo_unet_profile_read. */
 int mimo_unet_profile_read_launches(mimo_unet_plan_t* plan, int max_n, float* ms, int* cls, int* tag);
+/* same, plus the tensor-core kernel each conv launch dispatched to (0 = not a conv launch); names via mimo_conv_kernel_name */
+int mimo_unet_profile_read_launches_ex(mimo_unet_plan_t* plan, int max_n, float* ms, int* cls, int* tag, int* kernel);
+const char* mimo_conv_kernel_name(int id);
 /* state_dict prefix of double conv i ("core.down2", "decoder.up4s.1", ...) */
 const char* mimo_unet_node_name(const mimo_unet_plan_t* plan, int i);
 

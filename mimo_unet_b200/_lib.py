@@ -106,6 +106,8 @@ SIGNATURES = {
     "mimo_unet_profile_enable": (i32, [vp, i32]),
     "mimo_unet_profile_read": (i32, [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "mimo_unet_profile_read_launches": (i32, [vp, i32, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "mimo_unet_profile_read_launches_ex": (i32, [vp, i32, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "mimo_conv_kernel_name": (C.c_char_p, [i32]),
     "mimo_unet_node_name": (C.c_char_p, [vp, i32]),
 }
 

@@ -54,6 +54,11 @@ static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 
 
 int num_sms();
 
+// conv launchers record which kernel they dispatched to: 1 flat, 2 flatk, 3 igemm (4-D), 4 wgrad_flat, 5 wgrad_flatk, 6 wgrad (4-D)
+void note_kernel(int id);
+int last_kernel();
+const char* conv_kernel_name(int id);
+
 // ---------------------------------------------------------------------------------------------
 // Activation view: NHWC bf16 with an optional halo and an optional channel slice.
 //   pad == 0: dense [N][H][W]

@@ -379,6 +379,7 @@ bool conv3x3_flat_ok(const ActView& in, int mode, int cout) {
 
 int conv3x3_flat_launch(const ActView& in, int mode, const bf16* wpacked, int cout, int cin_pitch, bf16* out, int out_cpitch,
                         float* stat_sum, float* stat_sq, const float* bias, int relu, cudaStream_t stream) {
+  note_kernel(1);
   FlatParams p{};
   const int block_n = round_up(cout, 16);
   const int sets = block_n <= 48 ? 2 : 1;   // 8 epilogue warps unless the per-thread statistics registers do not fit

@@ -300,6 +300,7 @@ bool conv3x3_flatk_ok(const ActView& in, int mode, int cout) {
 
 int conv3x3_flatk_launch(const ActView& in, int mode, const bf16* wpacked, int cout, int cin_pitch, bf16* out, int out_cpitch,
                          float* stat_sum, float* stat_sq, const float* bias, int relu, cudaStream_t stream) {
+  note_kernel(2);
   FlatKParams p{};
   p.wb = in.wb();
   p.img_pix = in.hb() * in.wb();

@@ -246,6 +246,7 @@ int conv3x3_launch(const ActView& in, int mode, const bf16* wpacked, int cout, i
   if (conv3x3_flatk_ok(in, mode, cout))
     return conv3x3_flatk_launch(in, mode, wpacked, cout, cin_pitch, out, out_cpitch, stat_sum, stat_sq, bias, relu, stream);
 
+  note_kernel(3);
   ConvParams p{};
   p.n_img = in.N;
   p.out_h = in.H + (mode == 1 ? 2 : 0);

@@ -220,6 +220,7 @@ int conv3x3_wgrad_launch(const ActView& dy, const ActView& x, float* dw, int cin
   MIMO_CHECK(cin_pitch % 4 == 0 && cin_pitch >= x.C, MIMO_ERR_ALIGN, "wgrad: cin_pitch %d invalid", cin_pitch);
   if (conv3x3_wgrad_flat_ok(dy, x)) return conv3x3_wgrad_flat_launch(dy, x, dw, cin_pitch, stream, pre_zeroed);
   if (conv3x3_wgrad_flatk_ok(dy, x)) return conv3x3_wgrad_flatk_launch(dy, x, dw, cin_pitch, stream, pre_zeroed);
+  note_kernel(6);
   WgradParams p{};
   p.n_img = dy.N; p.H = dy.H; p.W = dy.W;
   pick_tile64(p.W, p.H, p.n_img, &p.tw, &p.th, &p.tn);

@@ -215,6 +215,7 @@ bool conv3x3_wgrad_flat_ok(const ActView& dy, const ActView& x) {
 }
 
 int conv3x3_wgrad_flat_launch(const ActView& dy, const ActView& x, float* dw, int cin_pitch, cudaStream_t stream, bool pre_zeroed) {
+  note_kernel(4);
   WgFlatParams p{};
   p.wb = x.wb();
   const long long total_pos = (long long)x.N * x.hb() * x.wb();

@@ -274,6 +274,7 @@ bool conv3x3_wgrad_flatk_ok(const ActView& dy, const ActView& x) {
 
 // dy: zero-tail view (pad == 2), x: haloed view (pad == 1), both with c_off % 8 == 0; cin_pitch % 4 == 0
 int conv3x3_wgrad_flatk_launch(const ActView& dy, const ActView& x, float* dw, int cin_pitch, cudaStream_t stream, bool pre_zeroed) {
+  note_kernel(5);
   WgFlatKParams p{};
   p.wb = x.wb();
   const long long total_pos = (long long)x.N * x.hb() * x.wb();

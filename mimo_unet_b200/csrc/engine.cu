@@ -117,7 +117,7 @@ struct mimo_unet_plan {
   // optional per-launch CUDA-event profiling (bench.py roofline numbers)
   bool prof = false;
   std::vector<cudaEvent_t> ev;   // pairs
-  std::vector<int> ev_cls, ev_tag;
+  std::vector<int> ev_cls, ev_tag, ev_kid;   // class, 2*node+conv tag, tensor-core kernel id (common.cuh note_kernel)
   int ev_used = 0;
   int cur_tag = -1;              // 2*node + (second conv) of the launch being enqueued, -1 outside a DoubleConv
 };
@@ -188,10 +188,12 @@ inline void prof_begin(mimo_unet_plan* P, int cls, cudaStream_t st) {
   cudaEventRecord(P->ev[2 * P->ev_used], st);
   P->ev_cls[P->ev_used] = cls;
   P->ev_tag[P->ev_used] = P->cur_tag;
+  note_kernel(0);
 }
 inline void prof_end(mimo_unet_plan* P, cudaStream_t st) {
   if (!P->prof || (size_t)(2 * P->ev_used + 1) >= P->ev.size()) return;
   cudaEventRecord(P->ev[2 * P->ev_used + 1], st);
+  P->ev_kid[P->ev_used] = last_kernel();
   ++P->ev_used;
 }
 
@@ -498,6 +500,7 @@ int mimo_unet_profile_enable(mimo_unet_plan_t* P, int on) {
     P->ev.resize(2 * 4096);
     P->ev_cls.assign(4096, 0);
     P->ev_tag.assign(4096, -1);
+    P->ev_kid.assign(4096, 0);
     for (auto& e : P->ev) MIMO_CUDA(cudaEventCreate(&e));
   }
   P->prof = on != 0;
@@ -531,6 +534,19 @@ int mimo_unet_profile_read_launches(mimo_unet_plan_t* P, int max_n, float* ms, i
   P->ev_used = 0;
   return n;
 }
+int mimo_unet_profile_read_launches_ex(mimo_unet_plan_t* P, int max_n, float* ms, int* cls, int* tag, int* kernel) {
+  MIMO_CHECK(P && ms && cls && tag && kernel, MIMO_ERR_ARG, "profile_read_launches_ex: null argument");
+  MIMO_CUDA(cudaDeviceSynchronize());
+  int n = P->ev_used < max_n ? P->ev_used : max_n;
+  for (int i = 0; i < n; ++i) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, P->ev[2 * i], P->ev[2 * i + 1]);
+    ms[i] = t; cls[i] = P->ev_cls[i]; tag[i] = P->ev_tag[i]; kernel[i] = P->ev_kid[i];
+  }
+  P->ev_used = 0;
+  return n;
+}
+const char* mimo_conv_kernel_name(int id) { return conv_kernel_name(id); }
 const char* mimo_unet_node_name(const mimo_unet_plan_t* P, int i) {
   return (P && i >= 0 && i < (int)P->nodes.size()) ? P->nodes[i].name.c_str() : "";
 }

@@ -16,6 +16,16 @@ void set_error(const char* fmt, ...) {
 }
 const char* last_error() { return g_err; }
 
+// which tensor-core kernel the last conv launcher of this thread dispatched to (read by the executor's per-launch profiler)
+static thread_local int g_last_kernel = 0;
+void note_kernel(int id) { g_last_kernel = id; }
+int last_kernel() { return g_last_kernel; }
+const char* conv_kernel_name(int id) {
+  static const char* names[] = {"", "conv3x3_flat_kernel", "conv3x3_flatk_kernel", "conv3x3_igemm_kernel", "conv3x3_wgrad_flat_kernel",
+                                "conv3x3_wgrad_flatk_kernel", "conv3x3_wgrad_kernel"};
+  return (id >= 0 && id < 7) ? names[id] : "";
+}
+
 int num_sms() {
   static int sms = 0;
   if (sms == 0) {

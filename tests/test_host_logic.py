@@ -141,3 +141,37 @@ def test_bench_flop_accounting_matches_survey():
     first = 2 * (2.0 * 128 * 160 * 21 * 3 * 9) * 64  # encoder.in_convs.{0,1} first conv: no input gradient in training
     assert abs(dgrad - (fprop - first)) / fprop < 1e-9
     assert abs((2 * fprop + dgrad + 3 * heads) / 64 / 1e9 - 29.762) < 2e-2
+
+
+def test_bench_per_node_flops_follow_the_executor_node_order():
+    """bench.py attributes per-launch times to layers through the executor's tag = 2 * node + conv: the FLOP table must follow
+    the plan's node order (host-only plan creation, no device needed) and sum to the per-step total."""
+    import ctypes as C
+    import importlib
+    from mimo_unet_b200 import _lib
+    from mimo_unet_b200.engine import UnetConfig
+    bench = importlib.import_module("bench")
+    for wl in ("C2", "C3"):
+        bench.CFG, bench.WORKLOAD = bench.WORKLOADS[wl]
+        cfg = bench.CFG
+        lib = _lib.lib()
+        h = C.c_void_p()
+        c = UnetConfig(cfg["in_channels"], cfg["out_channels"], cfg["num_subnetworks"], cfg["filter_base_count"], cfg["batch"],
+                       cfg["height"], cfg["width"])
+        _lib.check(lib.mimo_unet_plan_create(C.byref(c), C.byref(h)), "plan_create")
+        try:
+            n = lib.mimo_unet_num_double_convs(h)
+            names = [lib.mimo_unet_node_name(h, i).decode() for i in range(n)]
+        finally:
+            lib.mimo_unet_plan_destroy(h)
+        S = cfg["num_subnetworks"]
+        expect = [f"encoder.in_convs.{s}" for s in range(S)] + [f"encoder.down1s.{s}" for s in range(S)] + \
+                 ["core.down2", "core.down3", "core.down4", "core.up1", "core.up2", "core.up3"] + [f"decoder.up4s.{s}" for s in range(S)]
+        assert names == expect
+        node_fl = bench.conv_flops_per_node(cfg["batch"])
+        assert len(node_fl) == 2 * n
+        fprop, _ = bench.conv_flops_per_step(cfg["batch"])
+        assert abs(sum(node_fl) - fprop) / fprop < 1e-12
+        # first conv of encoder 0: Cin -> f at full resolution
+        assert node_fl[0] == 2.0 * cfg["height"] * cfg["width"] * cfg["filter_base_count"] * cfg["in_channels"] * 9 * cfg["batch"]
+    bench.CFG, bench.WORKLOAD = bench.WORKLOADS["C2"]
