@@ -55,6 +55,7 @@ class NetworkRuntime:
         self._forward_token = 0
         self._flat_grads: Optional[torch.Tensor] = None
         self._grad_views: List[Optional[torch.Tensor]] = []
+        self._views_of: Optional[torch.Tensor] = None  # the flat buffer the cached views slice
         self._learnable_idx: List[int] = []
         self.last_launches = (0, 0)
         self.grad_sync = None  # OverlappedGradientSynchronizer when data-parallel training is enabled
@@ -109,6 +110,9 @@ class NetworkRuntime:
         if self._flat_grads is None or self._flat_grads.numel() != total or self._flat_grads.device != dev or learn != self._learnable_idx:
             self._flat_grads = torch.zeros(total, dtype=torch.float32, device=dev)
             self._learnable_idx = learn
+        elif len(self._grad_views) == len(state) and self._views_of is self._flat_grads:
+            return  # same buffer, same layout: the cached views (they only feed data_ptr() to bind) are still right
+        self._views_of = self._flat_grads
         views: List[Optional[torch.Tensor]] = [None] * len(state)
         off = 0
         for i in learn:

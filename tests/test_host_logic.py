@@ -175,3 +175,32 @@ def test_bench_per_node_flops_follow_the_executor_node_order():
         # first conv of encoder 0: Cin -> f at full resolution
         assert node_fl[0] == 2.0 * cfg["height"] * cfg["width"] * cfg["filter_base_count"] * cfg["in_channels"] * 9 * cfg["batch"]
     bench.CFG, bench.WORKLOAD = bench.WORKLOADS["C2"]
+
+
+def test_runtime_grad_buffer_views_are_cached_and_rebuilt():
+    """NetworkRuntime._ensure_grad_buffer: one flat fp32 buffer in state order; the per-parameter views are rebuilt only when the
+    buffer is (re)created or the set of trainable tensors changes (host logic, CPU tensors)."""
+    from mimo.models.mimo_components.model import MimoUNet
+    from mimo_unet_b200.network import NetworkRuntime, _state_entries
+    net = MimoUNet(3, 2, 2, 8)
+    rt = NetworkRuntime(net)
+    st = _state_entries(net)
+    rt._ensure_grad_buffer(st)
+    flat, views = rt.flat_grads, rt._grad_views
+    n_learn = sum(1 for t in st if t.dtype == torch.float32 and t.requires_grad)
+    assert flat.numel() == sum(t.numel() for t in st if t.dtype == torch.float32 and t.requires_grad)
+    assert sum(v is not None for v in views) == n_learn == len(list(net.parameters()))
+    off = 0
+    for t, v in zip(st, views):  # contiguous slices in state order
+        if v is not None:
+            assert v.shape == t.shape and v.data_ptr() == flat.data_ptr() + 4 * off
+            off += t.numel()
+    rt._ensure_grad_buffer(st)
+    assert rt.flat_grads is flat and rt._grad_views is views          # cached
+    net.decoder.outcs[0].conv.bias.requires_grad_(False)              # the trainable set changed -> new buffer + views
+    rt._ensure_grad_buffer(_state_entries(net))
+    assert rt.flat_grads is not flat and rt._grad_views is not views
+    assert rt.flat_grads.numel() == flat.numel() - 2
+    rt._flat_grads = None                                            # private-buffer path of the backward
+    rt._ensure_grad_buffer(_state_entries(net))
+    assert rt.flat_grads is not None and rt._views_of is rt.flat_grads
