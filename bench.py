@@ -146,15 +146,30 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def conv_shape_table():
+    """(name, instances, Cin, Cout, H, W) of every 3x3 convolution of the bilinear MIMO U-Net for the current workload, in
+    state_dict order (channel arithmetic of reference model.py:133-148,190-230,262-283). Pure shape arithmetic: the GPU arm
+    must not touch oracle/ (tests/test_host_logic.py checks this table against the oracle's)."""
+    cin, S, f, H, W = CFG["in_channels"], CFG["num_subnetworks"], CFG["filter_base_count"], CFG["height"], CFG["width"]
+    c = 2 * f * S
+    d = c // 2 + f
+    lv = [(H >> l, W >> l) for l in range(5)]
+    blocks = [("encoder.in_convs", S, cin, f, f, 0), ("encoder.down1s", S, f, 2 * f, 2 * f, 1),
+              ("core.down2", 1, c, 2 * c, 2 * c, 2), ("core.down3", 1, 2 * c, 4 * c, 4 * c, 3), ("core.down4", 1, 4 * c, 4 * c, 4 * c, 4),
+              ("core.up1", 1, 8 * c, 4 * c, 2 * c, 3), ("core.up2", 1, 4 * c, 2 * c, c, 2), ("core.up3", 1, 2 * c, c, c // 2, 1),
+              ("decoder.up4s", S, d, d // 2, f, 0)]
+    rows = []
+    for name, inst, ci, cm, co, l in blocks:
+        rows.append((name + ".0", inst, ci, cm, lv[l][0], lv[l][1]))
+        rows.append((name + ".3", inst, cm, co, lv[l][0], lv[l][1]))
+    return rows
+
+
 def conv_flops_per_step(batch):
     """Algorithmic FLOPs (true channel counts) executed by the tcgen05 conv kernel per training step:
     fprop of all 3x3 convs + dgrad of all but the two image convs."""
-    from oracle import mimo_oracle as O
     fprop = dgrad = 0.0
-    for name, inst, ci, co, h, w, k in O.conv_layer_table(CFG["in_channels"], CFG["num_subnetworks"], CFG["filter_base_count"],
-                                                           CFG["height"], CFG["width"]):
-        if k != 3:
-            continue
+    for name, inst, ci, co, h, w in conv_shape_table():
         fl = 2.0 * h * w * co * ci * 9 * inst * batch
         fprop += fl
         if name != "encoder.in_convs.0":
@@ -202,13 +217,11 @@ def infer_throughput(dev, batch=64, mc_steps=1, steps=10, warmup=3, M=4, f=21, H
 def conv_flops_per_node(batch):
     """Algorithmic FLOPs of ONE pass (fprop = dgrad = wgrad) of every 3x3 conv, indexed by the executor's launch tag
     2 * node + conv, nodes in state_dict order: encoder.in_convs.*, encoder.down1s.*, core.down2..up3, decoder.up4s.*."""
-    from oracle import mimo_oracle as O
-    rows = [r for r in O.conv_layer_table(CFG["in_channels"], CFG["num_subnetworks"], CFG["filter_base_count"], CFG["height"], CFG["width"])
-            if r[6] == 3]
+    rows = conv_shape_table()
     out = []
     for c1, c2 in zip(rows[0::2], rows[1::2]):
         for _ in range(c1[1]):  # instances (one per subnetwork for encoder / decoder blocks)
-            for (_, _, ci, co, h, w, _) in (c1, c2):
+            for (_, _, ci, co, h, w) in (c1, c2):
                 out.append(2.0 * h * w * co * ci * 9 * batch)
     return out
 

@@ -204,3 +204,17 @@ def test_runtime_grad_buffer_views_are_cached_and_rebuilt():
     rt._flat_grads = None                                            # private-buffer path of the backward
     rt._ensure_grad_buffer(_state_entries(net))
     assert rt.flat_grads is not None and rt._views_of is rt.flat_grads
+
+
+def test_bench_shape_table_equals_the_oracle_table():
+    """bench.py carries its own conv shape table (its GPU arm may not import oracle/): same rows as the oracle's."""
+    import importlib
+    from oracle import mimo_oracle as O
+    bench = importlib.import_module("bench")
+    for wl in ("C1", "C2", "C3"):
+        bench.CFG, bench.WORKLOAD = bench.WORKLOADS[wl]
+        cfg = bench.CFG
+        ref = [r[:6] for r in O.conv_layer_table(cfg["in_channels"], cfg["num_subnetworks"], cfg["filter_base_count"], cfg["height"],
+                                                  cfg["width"]) if r[6] == 3]
+        assert bench.conv_shape_table() == ref
+    bench.CFG, bench.WORKLOAD = bench.WORKLOADS["C2"]
