@@ -1,5 +1,5 @@
 """GPU diagnostic: whole-model forward/backward of the executor vs the oracle (fp32 and bf16-emulating) run on
-the same GPU with autograd. Prints per-tensor errors. Usage: python tools/diag_model.py [S f H W B cin]"""
+the same GPU with autograd. Prints per-tensor errors. Usage: python tests/diag_model_vs_oracle.py [S f H W B cin]"""
 import os
 import sys
 

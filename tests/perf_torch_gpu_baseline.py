@@ -1,7 +1,7 @@
 """Second baseline (SURVEY 8d "GPU reference timing"): the reference's algorithm through stock PyTorch on the SAME B200 --
 the oracle's functional restatement (F.conv2d / batch_norm / max_pool / interpolate = cuDNN + ATen kernels), fp32 and
 torch.autocast(bf16), eager; C2 training step (forward + Laplace NLL + loss-buffer weights + backward + fused Adam).
-Test/measurement infrastructure only (imports oracle/). Usage: python tools/bench_torch_gpu.py [--steps 10]"""
+Test/measurement infrastructure only (imports oracle/). Lives under tests/ because only test infrastructure may execute oracle/. Usage: python tests/perf_torch_gpu_baseline.py [--steps 10]"""
 import argparse
 import json
 import os
@@ -9,7 +9,7 @@ import sys
 
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # repo root
 from oracle import mimo_oracle as O  # noqa: E402
 
 
