@@ -218,3 +218,39 @@ def test_bench_shape_table_equals_the_oracle_table():
                                                   cfg["width"]) if r[6] == 3]
         assert bench.conv_shape_table() == ref
     bench.CFG, bench.WORKLOAD = bench.WORKLOADS["C2"]
+
+
+REFERENCE_ROOT = "/root/reference"
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE_ROOT), reason="reference checkout not present (GPU box)")
+def test_reference_scripts_resolve_every_mimo_module_with_this_repo_first():
+    """INTEGRATION.md option A: PYTHONPATH=<this repo>:<reference>. Every `mimo.*` module the reference's train/test scripts
+    import must resolve -- the hot-path modules to THIS repo, the host I/O / logging glue (tasks, datasets, visualization) to
+    the reference checkout through pkgutil.extend_path. Run in a subprocess so sys.path / sys.modules stay clean."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r"""
+import importlib.util, os, sys
+ours = {"mimo.utils", "mimo.losses", "mimo.metrics", "mimo.models.mimo_unet", "mimo.models.ensemble", "mimo.models.evidential_unet",
+        "mimo.models.utils", "mimo.models.mimo_components.model", "mimo.models.mimo_components.components",
+        "mimo.models.mimo_components.loss_buffer"}
+theirs = {"mimo.visualization", "mimo.regularization", "mimo.datasets.nyuv2", "mimo.datasets.muad", "mimo.datasets.make3d",
+          "mimo.tasks.depth.nyuv2_datamodule", "mimo.tasks.depth.callbacks", "mimo.tasks.sen12tp.sen12tp_datamodule",
+          "mimo.tasks.sen12tp.callbacks"}
+root, ref = sys.argv[1], sys.argv[2]
+for name in sorted(ours | theirs):
+    # walk the package chain by hand: find_spec imports the parents (ours: importable), not the leaf (may need lightning)
+    spec = importlib.util.find_spec(name)
+    assert spec is not None and spec.origin, name
+    want = root if name in ours else ref
+    assert os.path.abspath(spec.origin).startswith(want + os.sep), (name, spec.origin)
+import mimo.losses, mimo.models.mimo_unet, mimo.models.ensemble, mimo.models.evidential_unet  # the ones scripts construct
+from mimo.losses import UncertaintyLoss, EvidentialLoss
+from mimo.utils import dir_path, count_trainable_parameters
+print("ok")
+"""
+    env = dict(os.environ, PYTHONPATH=root + os.pathsep + REFERENCE_ROOT)
+    r = subprocess.run([sys.executable, "-c", code, root, REFERENCE_ROOT], capture_output=True, text=True, env=env, cwd="/tmp")
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
