@@ -16,6 +16,9 @@ int conv3x3_launch(const ActView& in, int mode, const bf16* wpacked, int cout, i
 bool conv3x3_flatk_ok(const ActView& in, int mode, int cout);
 int conv3x3_flatk_launch(const ActView& in, int mode, const bf16* wpacked, int cout, int cin_pitch, bf16* out, int out_cpitch,
                          float* stat_sum, float* stat_sq, const float* bias, int relu, cudaStream_t stream);
+bool conv3x3_c2_ok(const ActView& in, int mode, int cout);
+int conv3x3_c2_launch(const ActView& in, int mode, const bf16* wpacked, int cout, int cin_pitch, bf16* out, int out_cpitch,
+                      float* stat_sum, float* stat_sq, const float* bias, int relu, cudaStream_t stream);
 // pre_zeroed: the caller has already cleared dw_packed on `stream` (the executor clears all layers with one memset)
 int conv3x3_wgrad_launch(const ActView& dy, const ActView& x, float* dw_packed, int cin_pitch, cudaStream_t stream, bool pre_zeroed = false);
 bool conv3x3_wgrad_flat_ok(const ActView& dy, const ActView& x);

@@ -11,26 +11,6 @@
 
 using namespace mimo;
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void umma2_bf16_w(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
-                                             uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-      "mov.b64 da, {%1, %2};\n\t"
-      "mov.b64 db, {%3, %4};\n\t"
-      "setp.ne.b32 p, %6, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}"
-      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 __device__ __forceinline__ void umma_ts_bf16_w(uint32_t tmem_d, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
@@ -190,6 +170,83 @@ __global__ void __launch_bounds__(256, 1) tmem_ld_probe_kernel(int warps, int re
   if (threadIdx.x == 0) out[blockIdx.x] = (unsigned long long)(t1 - t0);
 }
 
+
+// Cost of tcgen05.commit in the issue stream: `reps` iterations of { n_mma MMAs (N = 64); commit -> sink barrier }, then one
+// final commit + wait. mode 0: cta_group::1 local, 1: cta_group::2 local barrier, 2: cta_group::2 multicast to both CTAs.
+template <int GROUP>
+__global__ void __launch_bounds__(128, 1) commit_probe_kernel(int n_mma, int mode, int reps, unsigned long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar, sink[4];
+  __shared__ uint32_t tmem_ptr;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t rank = GROUP == 2 ? cluster_ctarank() : 0;
+  for (int i = threadIdx.x; i < 64 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u + (i & 0xff);
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&sink[i], 100000);
+    fence_barrier_init();
+  }
+  fence_proxy_async();
+  if (warp == 0) {
+    if constexpr (GROUP == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_ptr)), "r"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      tmem_alloc(&tmem_ptr, 512);
+      tmem_relinquish();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if constexpr (GROUP == 2) cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_ptr;
+  long long t0 = 0, t1 = 0;
+  if (warp == 0 && rank == 0) {
+    const uint32_t idesc = make_idesc_bf16(GROUP == 2 ? 256 : 128, 64, 0, 0);
+    constexpr uint32_t hi = desc_hi(1024, kLayoutSW128);
+    const uint32_t a_lo = desc_lo(smem_u32(smem), 16);
+    const uint32_t b_lo = desc_lo(smem_u32(smem + 32 * 1024), 16);
+    __syncwarp();
+    t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+      if (elect_one()) {
+        for (int k = 0; k < n_mma; ++k) {
+          if constexpr (GROUP == 2) umma2_bf16_w(tmem_base, a_lo + 2 * (k & 3), hi, b_lo + 2 * (k & 3), hi, idesc, 1);
+          else umma_bf16_w(tmem_base, a_lo + 2 * (k & 3), hi, b_lo + 2 * (k & 3), hi, idesc, 1);
+        }
+        if constexpr (GROUP == 2) {
+          if (mode == 2)
+            asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                             smem_u32(&sink[r & 3])), "h"((uint16_t)3) : "memory");
+          else umma_commit2_local(&sink[r & 3]);
+        } else {
+          umma_commit(&sink[r & 3]);
+        }
+      }
+      __syncwarp();
+    }
+    if (elect_one()) {
+      if constexpr (GROUP == 2) umma_commit2_local(&bar);
+      else umma_commit(&bar);
+    }
+    __syncwarp();
+    mbar_wait(&bar, 0);
+    t1 = clock64();
+    tc_fence_after();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if constexpr (GROUP == 2) cluster_sync_all();
+  if (warp == 0) {
+    tc_fence_after();
+    if constexpr (GROUP == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    else tmem_dealloc(tmem_base, 512);
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = (unsigned long long)(t1 - t0);
+}
+
 static double median(std::vector<unsigned long long> v) {
   std::sort(v.begin(), v.end());
   return (double)v[v.size() / 2];
@@ -250,6 +307,33 @@ int main() {
     const double math = per_sm_m * c.N * 16 * 2 / 8192.0;
     printf("%d %3d %3d %s %d %d | %7.1f | %6.1f | %7.0f\n", c.group, c.M, c.N, c.a_tmem ? "tmem" : "smem", c.amn, c.bmn, cyc, math,
            per_sm_m * c.N * 32.0 / cyc);
+  }
+  printf("# commit cost: cycles per iteration of { n MMAs (N=64); tcgen05.commit } ; group/mode: 1/0 local, 2/1 local, 2/2 multicast\n");
+  cudaFuncSetAttribute(commit_probe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(commit_probe_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  for (int gm = 0; gm < 3; ++gm) {
+    const int group = gm == 0 ? 1 : 2, mode = gm;
+    for (int n_mma : {0, 1, 4, 12}) {
+      const int r3 = 1024;
+      cudaLaunchConfig_t lc = {};
+      lc.gridDim = dim3(group == 2 ? (sms / 2) * 2 : sms);
+      lc.blockDim = dim3(128);
+      lc.dynamicSmemBytes = smem;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = group; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      lc.attrs = at;
+      lc.numAttrs = group == 2 ? 1 : 0;
+      cudaMemset(out, 0, sizeof(unsigned long long) * sms);
+      cudaError_t e = group == 2 ? cudaLaunchKernelEx(&lc, commit_probe_kernel<2>, n_mma, mode, r3, out)
+                                 : cudaLaunchKernelEx(&lc, commit_probe_kernel<1>, n_mma, mode, r3, out);
+      if (e == cudaSuccess) e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("commit probe failed: %s\n", cudaGetErrorString(e)); return 1; }
+      cudaMemcpy(h.data(), out, sizeof(unsigned long long) * sms, cudaMemcpyDeviceToHost);
+      std::vector<unsigned long long> v;
+      for (int i = 0; i < (int)lc.gridDim.x; ++i) if (h[i]) v.push_back(h[i]);
+      printf("group %d mode %d n_mma %2d | %7.1f cycles/iteration\n", group, mode, n_mma, median(v) / r3);
+    }
   }
   printf("# tcgen05.ld 32x32b: cycles per instruction per warp (all warps concurrently), bytes/cycle/SM\n");
   for (int warps : {4, 8}) {
