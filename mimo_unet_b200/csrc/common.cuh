@@ -215,12 +215,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.b32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)   // suspend-time hint (as CUTLASS's ClusterBarrier::wait): without it a
+      : "memory");                                         // waiting warp re-issues try_wait every few cycles and starves the
+  return ok != 0;                                          // working warps of its SM sub-partition of issue slots (measured)
 }
 // Bounded spin: a protocol bug turns into a trap (reported as a CUDA error) instead of a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
@@ -228,6 +228,29 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > (1u << 26)) {
       printf("mimo_b200: mbarrier wait timeout (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+      __trap();
+    }
+  }
+}
+
+// Polling wait (mbarrier.test_wait never suspends the thread): for barriers whose arrivals come from ANOTHER SM (remote
+// arrives of the peer CTA, multicast tcgen05.commit): a thread suspended in try_wait is not woken promptly by those.
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_poll(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_test_wait(bar, parity)) {
+    if (++spins > (1u << 28)) {
+      printf("mimo_b200: mbarrier poll timeout (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
       __trap();
     }
   }
@@ -382,8 +405,11 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t smem_addr, uint32_t ran
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
   return r;
 }
+// Default semantics (release at CTA scope), as CUTLASS's ClusterBarrier::arrive(cta_id) issues it. An explicit
+// .release.cluster compiles to MEMBAR.ALL.GPU in front of the arrive: measured ~900 cycles per arrive, and in the epilogue
+// warps it also waits for every global store of the previous tile to be acknowledged (profiles/r02_findings.md).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA loads whose completion is signalled on an mbarrier of EITHER CTA of the pair (shared::cluster address)
 __device__ __forceinline__ void tma_load_2d_cg2(const CUtensorMap* m, uint32_t bar_cluster, void* dst, int c0, int c1) {

@@ -241,6 +241,8 @@ int conv3x3_launch(const ActView& in, int mode, const bf16* wpacked, int cout, i
   MIMO_CHECK(((uintptr_t)in.base % 16) == 0 && ((uintptr_t)wpacked % 16) == 0 && ((uintptr_t)out % 16) == 0, MIMO_ERR_ALIGN,
              "conv3x3: pointers must be 16-byte aligned");
   MIMO_CHECK(in.H >= 2 && in.W >= 2, MIMO_ERR_ARG, "conv3x3: reflect padding needs H,W >= 2");
+  if (conv3x3_flat2_ok(in, mode, cout))
+    return conv3x3_flat2_launch(in, mode, wpacked, cout, cin_pitch, out, out_cpitch, stat_sum, stat_sq, bias, relu, stream);
   if (conv3x3_flat_ok(in, mode, cout))
     return conv3x3_flat_launch(in, mode, wpacked, cout, cin_pitch, out, out_cpitch, stat_sum, stat_sq, bias, relu, stream);
   if (conv3x3_c2_ok(in, mode, cout))

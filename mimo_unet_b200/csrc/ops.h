@@ -16,6 +16,9 @@ int conv3x3_launch(const ActView& in, int mode, const bf16* wpacked, int cout, i
 bool conv3x3_flatk_ok(const ActView& in, int mode, int cout);
 int conv3x3_flatk_launch(const ActView& in, int mode, const bf16* wpacked, int cout, int cin_pitch, bf16* out, int out_cpitch,
                          float* stat_sum, float* stat_sq, const float* bias, int relu, cudaStream_t stream);
+bool conv3x3_flat2_ok(const ActView& in, int mode, int cout);
+int conv3x3_flat2_launch(const ActView& in, int mode, const bf16* wpacked, int cout, int cin_pitch, bf16* out, int out_cpitch,
+                         float* stat_sum, float* stat_sq, const float* bias, int relu, cudaStream_t stream);
 bool conv3x3_c2_ok(const ActView& in, int mode, int cout);
 int conv3x3_c2_launch(const ActView& in, int mode, const bf16* wpacked, int cout, int cin_pitch, bf16* out, int out_cpitch,
                       float* stat_sum, float* stat_sq, const float* bias, int relu, cudaStream_t stream);

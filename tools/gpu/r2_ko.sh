@@ -1,11 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_kernels_gpu.py -q -m gpu -p no:cacheprovider -x -k "conv" 2>&1 | tail -3
-for t in 0 1 2 4; do
-  echo "== MIMO_C2_T=$t"
-  MIMO_C2_T=$t timeout 200 python tools/bench_conv.py --set half,core --reps 20 2>&1 | grep -E "\(64, (168|84|336|672)"
+timeout 600 python -m pytest tests/test_kernels_gpu.py -q -m gpu -p no:cacheprovider -x -k "conv" 2>&1 | tail -4
+echo "== flat2"
+timeout 300 python tools/bench_conv.py --set full,half --reps 20 2>&1 | grep -E "\(64, (3|21|63|31|42),"
+for ko in 2 4 7; do
+  echo "== MIMO_FLAT2_KO=$ko"
+  MIMO_FLAT2_KO=$ko timeout 200 python tools/bench_conv.py --set full --fprop-only --reps 20 2>&1 | grep -E "\(64, "
 done
-for ko in 57 63; do
-  echo "== MIMO_C2_KO=$ko"
-  MIMO_C2_KO=$ko timeout 200 python tools/bench_conv.py --set half,core --fprop-only --reps 20 2>&1 | grep -E "\(64, (168|84|336|672)"
-done
+MIMO_FLAT2_TRACE=1 timeout 200 python tools/bench_conv.py --set probe --fprop-only --reps 1 2>&1 | grep -E "^ (2[0-9]) \|"

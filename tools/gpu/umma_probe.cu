@@ -31,6 +31,7 @@ struct ProbeArgs {
   int reps;
   int b_mn_major;  // B operand MN-major (wgrad-style) instead of K-major
   int a_mn_major;
+  int a_row_off;   // A window starts this many 128-byte rows past the 1024-byte swizzle atom (row-shifted conv tap windows)
 };
 
 template <int GROUP>
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(ProbeArgs p, unsigne
   if (warp == 0 && rank == 0) {
     const uint32_t idesc = make_idesc_bf16(p.M, p.N, p.a_mn_major, p.b_mn_major);
     constexpr uint32_t hi = desc_hi(1024, kLayoutSW128);
-    const uint32_t a_lo = desc_lo(smem_u32(smem_a), p.a_mn_major ? 128 : 16);
+    const uint32_t a_lo = desc_lo(smem_u32(smem_a) + 128u * (uint32_t)p.a_row_off, p.a_mn_major ? 128 : 16);
     const uint32_t b_lo = desc_lo(smem_u32(smem_b), p.b_mn_major ? 128 : 16);
     const uint32_t d = tmem_base;             // accumulator columns [0, N)
     const uint32_t a_t = tmem_base + 256;     // A operand in TMEM (columns 256..)
@@ -267,18 +268,20 @@ int main() {
   const int reps = 2048;
   printf("# tcgen05.mma kind::f16 (bf16 in, fp32 acc), K = 16 per instruction, %d back-to-back MMAs, %d SMs busy\n", reps, sms);
   printf("# group M N a_src a_major b_major | cycles/MMA | dense-math cycles (M*N*16*2/8192 per SM) | flops/cycle/SM\n");
-  struct Cfg { int M, N, group, a_tmem, amn, bmn; };
+  struct Cfg { int M, N, group, a_tmem, amn, bmn, aoff; };
   std::vector<Cfg> cfgs;
-  for (int N : {16, 32, 48, 64, 96, 128, 192, 256}) cfgs.push_back({128, N, 1, 0, 0, 0});
-  for (int N : {32, 64, 128, 256}) cfgs.push_back({64, N, 1, 0, 0, 0});
-  for (int N : {32, 64, 128, 256}) cfgs.push_back({128, N, 1, 1, 0, 0});
-  for (int N : {32, 64, 128, 256}) cfgs.push_back({64, N, 1, 1, 0, 0});
-  for (int N : {32, 64, 96, 128, 192, 256}) cfgs.push_back({256, N, 2, 0, 0, 0});
-  for (int N : {64, 128, 256}) cfgs.push_back({128, N, 2, 0, 0, 0});
-  for (int N : {64, 128, 192, 256}) cfgs.push_back({128, N, 1, 0, 1, 1});   // both MN-major (wgrad)
-  for (int N : {128, 192, 256}) cfgs.push_back({256, N, 2, 0, 1, 1});
+  for (int N : {16, 32, 48, 64, 96, 128, 192, 256}) cfgs.push_back({128, N, 1, 0, 0, 0, 0});
+  for (int N : {32, 64, 128, 256}) cfgs.push_back({64, N, 1, 0, 0, 0, 0});
+  for (int N : {32, 64, 128, 256}) cfgs.push_back({128, N, 1, 1, 0, 0, 0});
+  for (int N : {32, 64, 128, 256}) cfgs.push_back({64, N, 1, 1, 0, 0, 0});
+  for (int N : {32, 64, 96, 128, 192, 256}) cfgs.push_back({256, N, 2, 0, 0, 0, 0});
+  for (int N : {64, 128, 256}) cfgs.push_back({128, N, 2, 0, 0, 0, 0});
+  for (int N : {64, 128, 192, 256}) cfgs.push_back({128, N, 1, 0, 1, 1, 0});   // both MN-major (wgrad)
+  for (int N : {128, 192, 256}) cfgs.push_back({256, N, 2, 0, 1, 1, 0});
+  for (int off : {1, 3, 4}) for (int N : {32, 64, 96, 176}) cfgs.push_back({256, N, 2, 0, 0, 0, off});   // row-shifted A windows
+  for (int off : {1, 3}) for (int N : {32, 64}) cfgs.push_back({128, N, 1, 0, 0, 0, off});
   for (const Cfg& c : cfgs) {
-    ProbeArgs a{c.M, c.N, c.group, c.a_tmem, reps, c.bmn, c.amn};
+    ProbeArgs a{c.M, c.N, c.group, c.a_tmem, reps, c.bmn, c.amn, c.aoff};
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3(c.group == 2 ? (sms / 2) * 2 : sms);
     lc.blockDim = dim3(128);
@@ -305,7 +308,7 @@ int main() {
     const double cyc = median(v) / reps;
     const double per_sm_m = c.group == 2 ? c.M / 2.0 : c.M;
     const double math = per_sm_m * c.N * 16 * 2 / 8192.0;
-    printf("%d %3d %3d %s %d %d | %7.1f | %6.1f | %7.0f\n", c.group, c.M, c.N, c.a_tmem ? "tmem" : "smem", c.amn, c.bmn, cyc, math,
+    printf("%d %3d %3d %s %d %d off%d | %7.1f | %6.1f | %7.0f\n", c.group, c.M, c.N, c.a_tmem ? "tmem" : "smem", c.amn, c.bmn, c.aoff, cyc, math,
            per_sm_m * c.N * 32.0 / cyc);
   }
   printf("# commit cost: cycles per iteration of { n MMAs (N=64); tcgen05.commit } ; group/mode: 1/0 local, 2/1 local, 2/2 multicast\n");
