@@ -33,6 +33,9 @@ WORKLOADS = {
     "C2": (CFG, WORKLOAD),
     "C3": (dict(in_channels=2, out_channels=2, num_subnetworks=2, filter_base_count=30, height=256, width=256, batch=32),
            "C3 SEN12TP-NDVI-shape MIMO U-Net M=2 fbc=30 2x256x256 batch 32/GPU train step (fwd+laplace_nll+loss-buffer+bwd+Adam)"),
+    "C4": (dict(in_channels=3, out_channels=2, num_subnetworks=4, filter_base_count=21, height=128, width=160, batch=256),
+           "C4 MIMO U-Net M=4 fbc=21 dropout 0.1 with MC dropout active, 3x128x160, batch 256: EnsembleModule.forward = 4 members + fused "
+           "aggregation (mean, aleatoric 2b^2, epistemic variance)"),
     "C1": (dict(in_channels=3, out_channels=2, num_subnetworks=2, filter_base_count=21, height=256, width=256, batch=8),
            "C1 MIMO U-Net M=2 fbc=21 3x256x256 batch 8 train step (the reference's CPU-runnable case)"),
 }
@@ -83,25 +86,135 @@ def cpu_training_step_time(batch, steps, warmup, threads):
     return statistics.median(times)
 
 
+def reference_training_step_time(batch, steps, warmup, threads, budget_s=None):
+    """The REAL reference modules (MimoUNet, apply_input_transform, LaplaceNLL, LossBuffer; loaded by oracle/_refload.py from
+    /root/reference or from the copy oracle/stage_reference.py staged into the git-ignored oracle/_ref/) in the reference's own
+    Lightning-free training loop (MIMO_U_Net_NYUv2_depth.ipynb cell 13-14 == mimo_unet.py:115-144 + Adam). fp32, train mode.
+    Returns (median seconds per step, timed steps actually run)."""
+    from oracle import _refload
+    R = _refload.load()
+    torch.set_num_threads(threads)
+    S, f, cin = CFG["num_subnetworks"], CFG["filter_base_count"], CFG["in_channels"]
+    H, W = CFG["height"], CFG["width"]
+    torch.manual_seed(1)
+    net = R.model.MimoUNet(in_channels=cin, out_channels=2, num_subnetworks=S, filter_base_count=f)
+    net.train()
+    loss_fn = R.losses.LaplaceNLL()
+    lb = R.loss_buffer.LossBuffer(subnetworks=S, temperature=0.3, buffer_size=10)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    x, y = torch.rand(batch, cin, H, W), torch.rand(batch, 1, H, W)
+    times, t_start = [], time.perf_counter()
+    it = 0
+    while it < warmup + steps:
+        t0 = time.perf_counter()
+        image_t, label_t, _ = R.utils.apply_input_transform(x, y, None, num_subnetworks=S, input_repetition_probability=0.0,
+                                                            batch_repetitions=1)
+        out = net(image_t)
+        loss = loss_fn.forward(out[:, :, :1], out[:, :, 1:], label_t, reduce_mean=False).mean(dim=(0, 2, 3, 4))
+        w = lb.get_weights()
+        lb.add(loss.detach())
+        opt.zero_grad(set_to_none=True)
+        (loss * w).mean().backward()
+        opt.step()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+        it += 1
+        # bounded sample: stop early (after at least 2 timed steps) when the whole run would exceed the budget
+        if budget_s is not None and len(times) >= 2 and (time.perf_counter() - t_start) + dt > budget_s:
+            break
+    return statistics.median(times), len(times)
+
+
+def cpu_arm(batch, steps, warmup, threads, budget_s):
+    """(seconds per step, timed steps, kind): the real reference when it is available, else the oracle port."""
+    try:
+        from oracle import _refload
+        if _refload.reference_available():
+            t, n = reference_training_step_time(batch, steps, warmup, threads, budget_s)
+            return t, n, "reference"
+    except Exception as e:  # pragma: no cover - falls back to the port, loudly
+        print(f"bench.py: reference modules unusable ({e}); timing the oracle port instead", file=sys.stderr)
+    return cpu_training_step_time(batch, steps, warmup, threads), steps, "port"
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sample_b = 16
-    t = cpu_training_step_time(sample_b, max(1, args.steps), max(0, min(args.warmup, 1)), threads)
-    val = sample_b / t
+    B = CFG["batch"]
+    warm = max(0, args.warmup)
+    t, n, kind = cpu_arm(B, max(1, args.steps), warm, threads, budget_s=240.0)
+    val = B / t
+    what = ("reference's own modules (MimoUNet + apply_input_transform + LaplaceNLL + LossBuffer + Adam, notebook loop)" if kind == "reference"
+            else "oracle port of the reference algorithm")
     line = {
         "impl": "reference", "metric": "train_images_per_sec", "value": val, "unit": "images/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+        "steps": n, "warmup": warm, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": f"batch {sample_b} of the same shape per step (bounded CPU sample)"},
-        "cpu_baseline": {"value": val, "unit": "images/s", "cores": threads, "kind": "port",
-                         "sample": f"oracle port of the reference algorithm, fp32, batch {sample_b} x 3x128x160, full train step incl. Adam"},
+        "config": {"workload": WORKLOAD, "global_batch": B, "parallelism": "cpu",
+                   "sample": f"full batch {B} per step; {n} timed steps after {warm} warm-up (the run is bounded to ~4 minutes)"},
+        "cpu_baseline": {"value": val, "unit": "images/s", "cores": threads, "kind": kind,
+                         "sample": f"{what}, fp32, batch {B} x {CFG['in_channels']}x{CFG['height']}x{CFG['width']}, full train step incl. Adam, "
+                                   f"median of {n} steps"},
         "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def parity_guard(dev, steps=3, batch=16):
+    """Outside every timed region (rank 0, N=1): a `steps`-step training trajectory of the product on the GPU against the CPU oracle
+    (bf16-emulating) at the benchmarked shape with a smaller batch: per-subnetwork loss and loss-buffer weights every step.
+    Same weights, same data, shuffles disabled (input_repetition_probability = 1 -> aligned indices)."""
+    from mimo.models.mimo_unet import MimoUnetModel
+    from oracle import mimo_oracle as O
+    S, f, cin, H, W = CFG["num_subnetworks"], CFG["filter_base_count"], CFG["in_channels"], CFG["height"], CFG["width"]
+    torch.manual_seed(7)
+    sd = O.make_state_dict(cin, 2, S, f, seed=5)
+    model = MimoUnetModel(in_channels=cin, out_channels=2, num_subnetworks=S, filter_base_count=f, center_dropout_rate=0.0,
+                          final_dropout_rate=0.0, encoder_dropout_rate=0.0, core_dropout_rate=0.0, decoder_dropout_rate=0.0,
+                          loss="laplace_nll", weight_decay=0.0, learning_rate=1e-3, seed=1, loss_buffer_size=10,
+                          loss_buffer_temperature=0.3, input_repetition_probability=1.0).to(dev)
+    model.model.load_state_dict(sd)
+    model.train()
+    opt = model.configure_optimizers()["optimizer"]
+    params = {k: (v.clone().requires_grad_(True) if v.dtype == torch.float32 and "running" not in k else v.clone()) for k, v in sd.items()}
+    opt_ref = torch.optim.Adam([p for p in params.values() if p.requires_grad], lr=1e-3)
+    lb = O.LossBufferOracle(S, 0.3, 10)
+    worst_loss = worst_w = 0.0
+    for it in range(steps):
+        x, y = torch.rand(batch, cin, H, W), torch.rand(batch, 1, H, W)
+        xs, ys = torch.stack([x] * S, dim=1), torch.stack([y] * S, dim=1)
+        p1, p2 = model(xs.to(dev))
+        loss, loss_w, w = model._calculate_train_loss(p1, p2, y_true=ys.to(dev))
+        opt.zero_grad(set_to_none=True)
+        loss_w.mean().backward()
+        opt.step()
+        ns = {}
+        out = O.mimo_unet_forward(xs, params, S, training=True, emulate_bf16=True, new_stats=ns)
+        w_ref = lb.get_weights()
+        l_ref, total = O.train_loss(out, ys, None, w_ref)
+        lb.add(l_ref)
+        opt_ref.zero_grad(set_to_none=True)
+        total.backward()
+        opt_ref.step()
+        for k, v in ns.items():
+            if k in params:
+                params[k] = v
+        l = loss.detach().cpu()
+        if not torch.isfinite(l).all():
+            raise RuntimeError(f"bench.py parity guard: non-finite loss {l.tolist()} at step {it}")
+        worst_loss = max(worst_loss, float((l - l_ref.detach()).abs().max() / l_ref.detach().abs().max()))
+        worst_w = max(worst_w, float((w.detach().cpu() - w_ref).abs().max()))
+    ok = worst_loss <= 5e-3 and worst_w <= 5e-3
+    res = {"steps": steps, "batch": batch, "loss_rel_max": worst_loss, "weight_abs_max": worst_w, "ok": ok,
+           "tolerance": "per-subnetwork loss rel <= 5e-3 and loss-buffer weights abs <= 5e-3 over the trajectory (bf16 weight updates drift apart; "
+                        "step 0 is <= 1e-3, see tests/test_fullshape_gpu.py for the per-kernel 1e-3 gates)"}
+    if not ok:
+        raise RuntimeError(f"bench.py parity guard failed: {res}")
+    return res
 
 
 # ------------------------------------------------------------------------------------------------
@@ -319,14 +432,16 @@ def run_gpu_arm(args):
             ms = float(t.item())
         return ms
 
-    timed(args.warmup, False)
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start()   # before the warm-up: nvidia-smi needs ~1 s for its first row, and the short timed region must be covered
+    timed(args.warmup, False)
     ms = timed(args.steps, False)
     timed(1, True)
     ms_e2e = timed(args.steps, True)
-    clocks = sampler.stop() if rank == 0 else None  # sampled over both timed regions (device-resident and end-to-end)
+    clocks = sampler.stop() if rank == 0 else None  # sampled over warm-up and both timed regions (device-resident and end-to-end)
+    if not bool(torch.isfinite(loss_host).all()):
+        raise RuntimeError(f"bench.py: non-finite training loss {loss_host.tolist()} after the timed steps")
     rt = model.model._runtime
     launches_per_step = rt.last_launches[0] + rt.last_launches[1] + 3  # + fused loss (2) + gradient-seed scale (1)
 
@@ -362,9 +477,11 @@ def run_gpu_arm(args):
                 e["flops"] += node_fl[ltag[i]]
         per_step = {n: (msb[i] / 3.0, cnt[i] // 3) for i, n in enumerate(names)}
         fprop_fl, dgrad_fl = conv_flops_per_step(B)
-        t_conv = (per_step["conv_fprop"][0] + per_step["conv_dgrad"][0]) * 1e-3
+        wgrad_fl = fprop_fl   # every 3x3 conv has a weight gradient of the same FLOP count as its forward
+        t_conv = (per_step["conv_fprop"][0] + per_step["conv_dgrad"][0] + per_step["conv_wgrad"][0]) * 1e-3
+        n_conv = per_step["conv_fprop"][1] + per_step["conv_dgrad"][1] + per_step["conv_wgrad"][1]
         sustained, burst, hbm, src = load_peaks()
-        achieved = (fprop_fl + dgrad_fl) / t_conv / 1e12
+        achieved = (fprop_fl + dgrad_fl + wgrad_fl) / t_conv / 1e12
         traffic = None
         tp = os.path.join(ROOT, "profiles", "conv_traffic.json")  # written by tools/gpu/evidence.sh from an ncu metric pass
         if os.path.isfile(tp) and args.workload == "C2":
@@ -372,12 +489,13 @@ def run_gpu_arm(args):
                 traffic = json.load(open(tp)).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        roof = {"bound": "tensor", "kernel": "conv3x3_flat_kernel + conv3x3_igemm_kernel (all fprop+dgrad launches of a step)", "achieved": achieved, "peak": sustained,
+        roof = {"bound": "tensor", "kernel": " + ".join(sorted(by_kernel)) + " (ALL fprop + dgrad + wgrad launches of a step)", "achieved": achieved, "peak": sustained,
                 "unit": "TFLOP/s", "frac": achieved / sustained, "traffic": traffic,
-                "traffic_note": "mean DRAM bytes (read+write) per conv fprop/dgrad launch, ncu metric pass committed as profiles/conv_traffic.json",
+                "traffic_note": "mean DRAM bytes (read+write) per conv launch, ncu metric pass committed as profiles/conv_traffic.json",
                 "peak_source": f"bf16_tflops_sustained of {src} MEASURED_PEAKS.json (kernel timed inside a long step)",
-                "launches_per_step": per_step["conv_fprop"][1] + per_step["conv_dgrad"][1],
-                "avg_launch_us": t_conv * 1e6 / max(1, per_step["conv_fprop"][1] + per_step["conv_dgrad"][1]),
+                "launches_per_step": n_conv,
+                "avg_launch_us": t_conv * 1e6 / max(1, n_conv),
+                "algorithmic_tflop_per_step": (fprop_fl + dgrad_fl + wgrad_fl) / 1e12,
                 "breakdown_ms_per_step": {k: round(v[0], 4) for k, v in per_step.items()},
                 "breakdown_launches_per_step": {k: v[1] for k, v in per_step.items()},
                 "by_kernel": {k: {"launches_per_step": v["launches"] // 3, "ms_per_step": round(v["ms"] / 3.0, 4),
@@ -387,13 +505,14 @@ def run_gpu_arm(args):
                 "note": "per-launch CUDA-event timing taken in 3 extra profiled steps (eager launches) right after the timed region; "
                         "by_kernel: algorithmic FLOPs (true channel counts) of the launches each tensor-core kernel served / their time"}
 
-    cpu = None
+    cpu = guard = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        sb = 16
-        t = cpu_training_step_time(sb, 2, 1, threads)
-        cpu = {"value": sb / t, "unit": "images/s", "cores": threads, "kind": "port",
-               "sample": f"oracle port (fp32, train step incl. Adam) on batch {sb} x 3x128x160, 1 warm-up + 2 timed steps, median"}
+        t, n, kind = cpu_arm(B, 2, 1, threads, budget_s=40.0)
+        cpu = {"value": B / t, "unit": "images/s", "cores": threads, "kind": kind,
+               "sample": f"{'reference modules' if kind == 'reference' else 'oracle port'} (fp32, train step incl. Adam) on the full batch {B} x "
+                         f"{CFG['in_channels']}x{H}x{W}, 1 warm-up + {n} timed steps, median"}
+        guard = parity_guard(dev)
 
     infer = None
     if rank == 0 and world == 1 and not args.no_infer:
@@ -421,11 +540,81 @@ def run_gpu_arm(args):
             "clocks": clocks,
             "roofline": roof,
             "cpu_baseline": cpu,
+            "parity_guard": guard,
             "infer": infer,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+
+def run_infer_arm(args):
+    """--workload C4 (BASELINE.json configs[3]): inference MPix/s of the M=4 MC-dropout ensemble on one GPU (replicas only: the
+    path has no exchange step). value = device-resident inputs, e2e = pinned-host inputs H2D + the three result maps D2H
+    inside the timed region, roofline = the tcgen05 conv kernels of the forward pass against the sustained bf16 peak."""
+    import ctypes as C
+    from mimo_unet_b200 import _lib
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    _lib.check(_lib.lib().mimo_check_device(), "mimo_check_device")
+    B, H, W, M, f = CFG["batch"], CFG["height"], CFG["width"], CFG["num_subnetworks"], CFG["filter_base_count"]
+    sampler = ClockSampler(local)
+    sampler.start()
+    cases = []
+    for (b, mc) in ((B, 1), (64, 1), (64, 8)):
+        v, t = infer_throughput(dev, batch=b, mc_steps=mc, steps=args.steps, warmup=args.warmup, M=M, f=f, H=H, W=W)
+        ve, te = infer_throughput(dev, batch=b, mc_steps=mc, steps=args.steps, warmup=args.warmup, M=M, f=f, H=H, W=W, from_host=True)
+        cases.append({"batch": b, "mc_steps": mc, "members": M * mc, "value": v, "ms_per_batch": t, "e2e_value": ve, "e2e_ms_per_batch": te})
+    clocks = sampler.stop()
+    # roofline: per-launch CUDA events of the forward convolutions at the headline case (profiled eager passes outside the timed region)
+    from mimo.models.ensemble import EnsembleModule
+    from mimo.models.mimo_unet import MimoUnetModel
+    torch.manual_seed(1)
+    m = MimoUnetModel(in_channels=3, out_channels=2, num_subnetworks=M, filter_base_count=f, center_dropout_rate=0.0, final_dropout_rate=0.0,
+                      encoder_dropout_rate=0.1, core_dropout_rate=0.1, decoder_dropout_rate=0.1, loss="laplace_nll", weight_decay=0.0,
+                      learning_rate=1e-3, seed=1, loss_buffer_size=10, loss_buffer_temperature=0.3).to(dev)
+    ens = EnsembleModule([], monte_carlo_steps=1, models=[m])
+    x = torch.rand(B, 3, H, W, device=dev)
+    with torch.no_grad():
+        mean, alea, epi = ens(x)
+        if not all(bool(torch.isfinite(t).all()) for t in (mean, alea, epi)):
+            raise RuntimeError("bench.py: non-finite ensemble outputs")
+        lib = _lib.lib()
+        plan = next(iter(m.model._runtime.plans.values()))
+        lib.mimo_unet_profile_enable(plan.handle, 1)
+        for _ in range(3):
+            ens(x)
+        torch.cuda.synchronize()
+    ncls = lib.mimo_unet_profile_classes()
+    names = [lib.mimo_unet_profile_class_name(i).decode() for i in range(ncls)]
+    msb, cnt = (C.c_float * ncls)(), (C.c_int * ncls)()
+    lib.mimo_unet_profile_read(plan.handle, msb, cnt)
+    lib.mimo_unet_profile_enable(plan.handle, 0)
+    per = {n: msb[i] / 3.0 for i, n in enumerate(names)}
+    fprop_fl, _ = conv_flops_per_step(B)
+    sustained, burst, hbm, src = load_peaks()
+    t_conv = per["conv_fprop"] * 1e-3
+    head = cases[0]
+    line = {
+        "metric": "infer_mpix_per_sec", "value": head["value"], "unit": "MPix/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": head["ms_per_batch"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch": B, "parallelism": "dp1", "members": M, "mc_steps": 1,
+                   "l2": "activations of one forward (> 1 GB) exceed the 126 MB L2; no explicit flush needed"},
+        "e2e": {"value": head["e2e_value"], "unit": "MPix/s", "h2d_bytes_per_step": B * 3 * H * W * 4, "d2h_bytes_per_step": 3 * B * H * W * 4,
+                "ms_per_step": head["e2e_ms_per_batch"]},
+        "gpu_launches": int(m.model._runtime.last_launches[0] + 1) * args.steps,
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "all conv fprop launches of one forward (conv3x3_c2_kernel + conv3x3_flat_kernel)",
+                     "achieved": fprop_fl / t_conv / 1e12, "peak": sustained, "unit": "TFLOP/s", "frac": fprop_fl / t_conv / 1e12 / sustained,
+                     "traffic": None, "peak_source": f"bf16_tflops_sustained of {src} MEASURED_PEAKS.json",
+                     "breakdown_ms_per_forward": {k: round(v, 4) for k, v in per.items() if v > 0}},
+        "cases": cases,
+    }
+    print(json.dumps(line), flush=True)
 
 
 def main():
@@ -442,6 +631,10 @@ def main():
     CFG, WORKLOAD = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.workload == "C4":
+        if args.warmup < 3:
+            args.warmup = 3
+        run_infer_arm(args)
     else:
         if args.warmup < 3:
             args.warmup = 3

@@ -172,6 +172,41 @@ int mimo_laplace_nll_train(const float* out, const float* y, long long y_bs, lon
                            long long hw, float eps_min, float eps_max, void* lb_state, const float* fixed_w,
                            int update_buffer, float* dout, float* part, float* loss, float* weights, float* weighted,
                            void* stream);
+/* Same pass, plus the per-step regression metrics the reference computes with four torchmetrics reductions
+ * (mimo/metrics.py:22-34, called from mimo/models/mimo_unet.py:135,172): metrics[4] = {mae, mse, rmse, r2} of the
+ * location channels (mu vs y) over all B*S*C*H*W elements; the mask does not enter (as in the reference).
+ * `part` must hold mimo_laplace_train_metrics_scratch_floats() floats. */
+size_t mimo_laplace_train_metrics_scratch_floats(int batch, int subnetworks, int c, long long hw);
+int mimo_laplace_nll_train_metrics(const float* out, const float* y, long long y_bs, long long y_ss, const float* mask,
+                                   long long m_bs, long long m_ss, const long long* gather, int batch, int subnetworks, int c,
+                                   long long hw, float eps_min, float eps_max, void* lb_state, const float* fixed_w,
+                                   int update_buffer, float* dout, float* part, float* loss, float* weights, float* weighted,
+                                   float* metrics, void* stream);
+/* GaussianNLL (mimo/losses.py:39-79; selected by UncertaintyLoss.from_name("gaussian_nll"), mimo/losses.py:29-36):
+ * log(v) + (mu - y)^2 / v with v = clamp(exp(log_var), eps_min, eps_max), same clamp-gradient semantics and the same
+ * argument meaning as the mimo_laplace_nll_* entry points. */
+int mimo_gaussian_nll_fwd(const float* mu, long long mu_rs, const float* log_var, long long lv_rs, const float* y, long long y_rs,
+                          const float* mask, long long m_rs, long long rows, long long cols, float eps_min, float eps_max,
+                          float* out_elem, float* part, float* out_mean, void* stream);
+int mimo_gaussian_nll_bwd(const float* mu, long long mu_rs, const float* log_var, long long lv_rs, const float* y, long long y_rs,
+                          const float* mask, long long m_rs, long long rows, long long cols, float eps_min, float eps_max,
+                          const float* upstream, int upstream_is_scalar, float upstream_scale, float* g_mu, float* g_log_var,
+                          void* stream);
+int mimo_gaussian_nll_train_metrics(const float* out, const float* y, long long y_bs, long long y_ss, const float* mask,
+                                    long long m_bs, long long m_ss, const long long* gather, int batch, int subnetworks, int c,
+                                    long long hw, float eps_min, float eps_max, void* lb_state, const float* fixed_w,
+                                    int update_buffer, float* dout, float* part, float* loss, float* weights, float* weighted,
+                                    float* metrics, void* stream);
+/* Deep evidential regression baseline (M = 1, out_channels = 4): the softplus head of EvidentialUnetModel.forward
+ * (mimo/models/evidential_unet.py:85-96: raw (mu, log v, log alpha, log beta) -> (mu, v, alpha, beta)) and EvidentialLoss
+ * (mimo/losses.py:195-271), each one elementwise pass forward and backward. raw/out/params/g_*: fp32 [batch][4][hw];
+ * y, mask, out_elem: fp32 [batch][hw]; upstream as in mimo_laplace_nll_bwd; part: mimo_laplace_scratch_floats() floats. */
+int mimo_evidential_head(const float* raw, float* out, long long batch, long long hw, void* stream);
+int mimo_evidential_head_bwd(const float* raw, const float* g_out, float* g_raw, long long batch, long long hw, void* stream);
+int mimo_evidential_loss_fwd(const float* params, const float* y, const float* mask, long long batch, long long hw,
+                             float* out_elem, float* part, float* out_mean, void* stream);
+int mimo_evidential_loss_bwd(const float* params, const float* y, const float* mask, long long batch, long long hw,
+                             const float* upstream, int upstream_is_scalar, float upstream_scale, float* g_params, void* stream);
 int mimo_scale_by_scalar(float* x, long long n, const float* scalar, void* stream);
 
 /* compute_uncertainties (mimo/models/utils.py:76-101): element (b,s,j) at p[b*bs + s*ss + j], j < inner */

@@ -8,7 +8,7 @@ from typing import Any, Dict, Literal, Tuple
 
 import torch
 
-from mimo.losses import LaplaceNLL, UncertaintyLoss
+from mimo.losses import GaussianNLL, LaplaceNLL, UncertaintyLoss
 from mimo.metrics import compute_regression_metrics
 from mimo.utils import count_trainable_parameters
 from ._lightning_compat import LightningModule
@@ -84,9 +84,10 @@ class MimoUnetModel(LightningModule):
         mask_t = None if mask is None else torch.stack([mask.index_select(0, i) for i in idx], dim=1)
         y_pred = self.loss_fn.mode(p1, p2)
         aleatoric_std = self.loss_fn.std(p1, p2)
-        loss, loss_weighted, weights = self._calculate_train_loss(p1, p2, y_true=label_t, mask=mask_t, _out=out)
+        self._fused_metrics = None
+        loss, loss_weighted, weights = self._calculate_train_loss(p1, p2, y_true=label_t, mask=mask_t, _out=out, _metrics=True)
         self._log_train_loss_and_weights(loss, weights)
-        self._log_metrics(y_pred=y_pred, y_true=label_t, stage="train")
+        self._log_metrics(y_pred=y_pred, y_true=label_t, stage="train", precomputed=self._fused_metrics)
         return {
             "loss": loss_weighted.mean() if loss_weighted.dim() else loss_weighted,
             "label": flatten_subnetwork_dimension(label_t),
@@ -135,22 +136,32 @@ class MimoUnetModel(LightningModule):
         return (torch.sum((y_hat - y_hat.mean(dim=1, keepdim=True)) ** 2, dim=1) / (S - 1)) ** 0.5
 
     def _calculate_train_loss(self, p1: torch.Tensor, p2: torch.Tensor, y_true: torch.Tensor, mask: torch.Tensor = None,
-                              _out: torch.Tensor = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+                              _out: torch.Tensor = None, _metrics: bool = False) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         """Returns (loss[S], loss*weights [S], weights[S]). Weights are read from the loss buffer BEFORE the new
         loss is added (reference mimo_unet.py:243-245). On the GPU with the Laplace loss everything -- NLL,
         per-subnetwork means, buffer read, buffer update and the gradient seed -- is one fused kernel pass."""
-        if isinstance(self.loss_fn, LaplaceNLL) and p1.is_cuda:
+        if isinstance(self.loss_fn, (LaplaceNLL, GaussianNLL)) and p1.is_cuda:
             from mimo_unet_b200 import functional as Fn
             out = _out if _out is not None else torch.cat([p1, p2], dim=2)
             dev_buf = self.loss_buffer.device_state(p1.device)
             from mimo_unet_b200 import parallel as Par
             dp = Par.world_size() > 1
+            sync = getattr(self.model, "_runtime", None) and self.model._runtime.grad_sync
+            if dp and sync is not None:
+                sync.join_loss_exchange()   # the previous step's buffer update (side stream) before this step reads the weights
             # data parallel: every rank's loss buffer receives the MEAN per-subnetwork loss over ranks, so the softmax
             # weights stay identical everywhere (the reference defines no multi-GPU behaviour; SURVEY 8e)
-            total, loss, weights = Fn.laplace_train_loss(out, y_true, mask=mask, loss_buffer=dev_buf, update_buffer=not dp,
-                                                         eps_min=self.loss_fn.eps_min, eps_max=self.loss_fn.eps_max)
+            res = Fn.laplace_train_loss(out, y_true, mask=mask, loss_buffer=dev_buf, update_buffer=not dp,
+                                        eps_min=self.loss_fn.eps_min, eps_max=self.loss_fn.eps_max, with_metrics=_metrics,
+                                        gaussian=isinstance(self.loss_fn, GaussianNLL))
+            total, loss, weights = res[:3]
+            # r2/mae/mse/rmse of (mode, label) out of the same kernel pass (reference: compute_regression_metrics, 4 reductions)
+            self._fused_metrics = res[3] if _metrics else None
             if dp:
-                dev_buf.add(Par.allreduce_mean_(loss.detach().clone()))
+                if sync is not None:
+                    sync.exchange_loss(loss, dev_buf)     # all-reduce + buffer update on the side stream, joined next step
+                else:
+                    dev_buf.add(Par.allreduce_mean_(loss.detach().clone()))
             # `total` (= mean_s w_s loss_s) carries the autograd graph; expose it through the reference's
             # (loss, loss*weights, weights) triple so that loss_weighted.mean() == total, value and gradient
             loss_weighted = loss * weights + (total - (loss * weights).mean())
@@ -169,8 +180,10 @@ class MimoUnetModel(LightningModule):
             self.log(f"train_loss_{i}", loss[i], batch_size=bs)
             self.log(f"train_weight_{i}", weights[i], batch_size=bs)
 
-    def _log_metrics(self, y_pred: torch.Tensor, y_true: torch.Tensor, stage: Literal["train", "val"] = "train") -> None:
-        for name, value in compute_regression_metrics(y_pred.flatten(), y_true.flatten()).items():
+    def _log_metrics(self, y_pred: torch.Tensor, y_true: torch.Tensor, stage: Literal["train", "val"] = "train",
+                     precomputed: Dict[str, torch.Tensor] = None) -> None:
+        metrics = precomputed if precomputed is not None else compute_regression_metrics(y_pred.flatten(), y_true.flatten())
+        for name, value in metrics.items():
             self.log(f"metric_{stage}/{name}", value, on_step=(stage == "train"), on_epoch=True, metric_attribute=name,
                      batch_size=self._batch_size())
 

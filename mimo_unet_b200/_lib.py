@@ -85,6 +85,17 @@ SIGNATURES = {
     "mimo_laplace_train_scratch_floats": (sz, [i32, i32, i32, i64]),
     "mimo_laplace_nll_train": (i32, [vp, vp, i64, i64, vp, i64, i64, vp, i32, i32, i32, i64, f32, f32, vp, vp, i32,
                                      vp, vp, vp, vp, vp, vp]),
+    "mimo_laplace_train_metrics_scratch_floats": (sz, [i32, i32, i32, i64]),
+    "mimo_laplace_nll_train_metrics": (i32, [vp, vp, i64, i64, vp, i64, i64, vp, i32, i32, i32, i64, f32, f32, vp, vp, i32,
+                                             vp, vp, vp, vp, vp, vp, vp]),
+    "mimo_gaussian_nll_fwd": (i32, [vp, i64, vp, i64, vp, i64, vp, i64, i64, i64, f32, f32, vp, vp, vp, vp]),
+    "mimo_gaussian_nll_bwd": (i32, [vp, i64, vp, i64, vp, i64, vp, i64, i64, i64, f32, f32, vp, i32, f32, vp, vp, vp]),
+    "mimo_gaussian_nll_train_metrics": (i32, [vp, vp, i64, i64, vp, i64, i64, vp, i32, i32, i32, i64, f32, f32, vp, vp, i32,
+                                              vp, vp, vp, vp, vp, vp, vp]),
+    "mimo_evidential_head": (i32, [vp, vp, i64, i64, vp]),
+    "mimo_evidential_head_bwd": (i32, [vp, vp, vp, i64, i64, vp]),
+    "mimo_evidential_loss_fwd": (i32, [vp, vp, vp, i64, i64, vp, vp, vp, vp]),
+    "mimo_evidential_loss_bwd": (i32, [vp, vp, vp, i64, i64, vp, i32, f32, vp, vp]),
     "mimo_scale_by_scalar": (i32, [vp, i64, vp, vp]),
     "mimo_ensemble_aggregate": (i32, [vp, i64, i64, vp, i64, i64, i32, i32, i64, vp, vp, vp, vp]),
     "mimo_unet_plan_create": (i32, [C.POINTER(UnetConfig), C.POINTER(vp)]),

@@ -179,6 +179,47 @@ int mimo_laplace_nll_bwd(const float* mu, long long mu_rs, const float* log_s, l
                             upstream_scale, g_mu, g_log_s, (cudaStream_t)stream);
 }
 
+int mimo_gaussian_nll_fwd(const float* mu, long long mu_rs, const float* log_var, long long lv_rs, const float* y, long long y_rs,
+                          const float* mask, long long m_rs, long long rows, long long cols, float eps_min, float eps_max,
+                          float* out_elem, float* part, float* out_mean, void* stream) {
+  MIMO_CHECK(mu && log_var && y && (out_elem || out_mean), MIMO_ERR_ARG, "gaussian_nll_fwd: null pointer");
+  if (rows * cols == 0) return MIMO_OK;
+  return laplace_fwd_launch(mu, mu_rs, log_var, lv_rs, y, y_rs, mask, m_rs, rows, cols, eps_min, eps_max, out_elem, part, out_mean,
+                            (cudaStream_t)stream, 1);
+}
+int mimo_gaussian_nll_bwd(const float* mu, long long mu_rs, const float* log_var, long long lv_rs, const float* y, long long y_rs,
+                          const float* mask, long long m_rs, long long rows, long long cols, float eps_min, float eps_max,
+                          const float* upstream, int upstream_is_scalar, float upstream_scale, float* g_mu, float* g_log_var,
+                          void* stream) {
+  MIMO_CHECK(mu && log_var && y && upstream && g_mu && g_log_var, MIMO_ERR_ARG, "gaussian_nll_bwd: null pointer");
+  if (rows * cols == 0) return MIMO_OK;
+  return laplace_bwd_launch(mu, mu_rs, log_var, lv_rs, y, y_rs, mask, m_rs, rows, cols, eps_min, eps_max, upstream, upstream_is_scalar,
+                            upstream_scale, g_mu, g_log_var, (cudaStream_t)stream, 1);
+}
+
+int mimo_evidential_head(const float* raw, float* out, long long batch, long long hw, void* stream) {
+  MIMO_CHECK(raw && out, MIMO_ERR_ARG, "evidential_head: null pointer");
+  if (batch * hw == 0) return MIMO_OK;
+  return evidential_head_launch(raw, out, batch, hw, (cudaStream_t)stream);
+}
+int mimo_evidential_head_bwd(const float* raw, const float* g_out, float* g_raw, long long batch, long long hw, void* stream) {
+  MIMO_CHECK(raw && g_out && g_raw, MIMO_ERR_ARG, "evidential_head_bwd: null pointer");
+  if (batch * hw == 0) return MIMO_OK;
+  return evidential_head_bwd_launch(raw, g_out, g_raw, batch, hw, (cudaStream_t)stream);
+}
+int mimo_evidential_loss_fwd(const float* params, const float* y, const float* mask, long long batch, long long hw, float* out_elem,
+                             float* part, float* out_mean, void* stream) {
+  MIMO_CHECK(params && y && (out_elem || out_mean), MIMO_ERR_ARG, "evidential_loss_fwd: null pointer");
+  if (batch * hw == 0) return MIMO_OK;
+  return evidential_loss_fwd_launch(params, y, mask, batch, hw, out_elem, part, out_mean, (cudaStream_t)stream);
+}
+int mimo_evidential_loss_bwd(const float* params, const float* y, const float* mask, long long batch, long long hw,
+                             const float* upstream, int upstream_is_scalar, float upstream_scale, float* g_params, void* stream) {
+  MIMO_CHECK(params && y && upstream && g_params, MIMO_ERR_ARG, "evidential_loss_bwd: null pointer");
+  if (batch * hw == 0) return MIMO_OK;
+  return evidential_loss_bwd_launch(params, y, mask, batch, hw, upstream, upstream_is_scalar, upstream_scale, g_params, (cudaStream_t)stream);
+}
+
 size_t mimo_lossbuffer_bytes(int subnetworks, int buffer_size) { return lossbuffer_bytes(subnetworks, buffer_size); }
 int mimo_lossbuffer_init(void* state, int subnetworks, int buffer_size, float temperature, void* stream) {
   MIMO_CHECK(state, MIMO_ERR_ARG, "lossbuffer_init: null pointer");
@@ -204,6 +245,29 @@ int mimo_laplace_nll_train(const float* out, const float* y, long long y_bs, lon
   MIMO_CHECK(out && y && part && loss, MIMO_ERR_ARG, "laplace_nll_train: null pointer");
   return laplace_train_launch(out, y, y_bs, y_ss, mask, m_bs, m_ss, gather, batch, subnetworks, c, hw, eps_min, eps_max, lb_state,
                               fixed_w, update_buffer, dout, part, loss, weights, weighted, (cudaStream_t)stream);
+}
+
+int mimo_laplace_nll_train_metrics(const float* out, const float* y, long long y_bs, long long y_ss, const float* mask, long long m_bs,
+                                   long long m_ss, const long long* gather, int batch, int subnetworks, int c, long long hw,
+                                   float eps_min, float eps_max, void* lb_state, const float* fixed_w, int update_buffer, float* dout,
+                                   float* part, float* loss, float* weights, float* weighted, float* metrics, void* stream) {
+  MIMO_CHECK(out && y && part && loss && metrics, MIMO_ERR_ARG, "laplace_nll_train_metrics: null pointer");
+  // scratch: [B*S*nblk] loss partials followed by [B*S*nblk][4] metric partials (mimo_laplace_train_metrics_scratch_floats)
+  float* mpart = part + mimo_laplace_train_scratch_floats(batch, subnetworks, c, hw);
+  return laplace_train_launch(out, y, y_bs, y_ss, mask, m_bs, m_ss, gather, batch, subnetworks, c, hw, eps_min, eps_max, lb_state,
+                              fixed_w, update_buffer, dout, part, loss, weights, weighted, (cudaStream_t)stream, mpart, metrics);
+}
+size_t mimo_laplace_train_metrics_scratch_floats(int batch, int subnetworks, int c, long long hw) {
+  return 5 * mimo_laplace_train_scratch_floats(batch, subnetworks, c, hw);
+}
+int mimo_gaussian_nll_train_metrics(const float* out, const float* y, long long y_bs, long long y_ss, const float* mask, long long m_bs,
+                                    long long m_ss, const long long* gather, int batch, int subnetworks, int c, long long hw,
+                                    float eps_min, float eps_max, void* lb_state, const float* fixed_w, int update_buffer, float* dout,
+                                    float* part, float* loss, float* weights, float* weighted, float* metrics, void* stream) {
+  MIMO_CHECK(out && y && part && loss && metrics, MIMO_ERR_ARG, "gaussian_nll_train_metrics: null pointer");
+  float* mpart = part + mimo_laplace_train_scratch_floats(batch, subnetworks, c, hw);
+  return laplace_train_launch(out, y, y_bs, y_ss, mask, m_bs, m_ss, gather, batch, subnetworks, c, hw, eps_min, eps_max, lb_state,
+                              fixed_w, update_buffer, dout, part, loss, weights, weighted, (cudaStream_t)stream, mpart, metrics, 1);
 }
 
 int mimo_scale_by_scalar(float* x, long long n, const float* scalar, void* stream) {

@@ -272,23 +272,35 @@ __global__ void head_bwd_finalize_kernel(const float* __restrict__ part, int npa
 // ------------------------------------------------------------------------------------------------
 // Laplace NLL element math
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void laplace_elem(float mu, float ls, float y, float m, float eps_min, float eps_max, float* loss,
-                                             float* g_mu, float* g_ls) {
+// kind 0: LaplaceNLL (mimo/losses.py:132-164)   log(s) + |d| / s,   s = clamp(exp(log_s))
+// kind 1: GaussianNLL (mimo/losses.py:48-79)    log(v) + d^2 / v,   v = clamp(exp(log_var))
+// In both the clamp is applied in place under no_grad on a clone, i.e. it changes the VALUE the loss is evaluated at but is
+// invisible to autograd: d/d log_p = dloss/dp (at the clamped value) * p_raw.
+__device__ __forceinline__ void nll_elem(int kind, float mu, float ls, float y, float m, float eps_min, float eps_max, float* loss,
+                                         float* g_mu, float* g_ls) {
   const float d = mu - y;
   const float s_raw = expf(ls);
   const float s_c = fminf(fmaxf(s_raw, eps_min), eps_max);
   const float inv = 1.f / s_c;
-  const float ad = fabsf(d);
-  *loss = (logf(s_c) + ad * inv) * m;
-  *g_mu = ((d > 0.f) ? inv : ((d < 0.f) ? -inv : 0.f)) * m;
-  *g_ls = (inv - ad * inv * inv) * s_raw * m;
+  if (kind == 0) {
+    const float ad = fabsf(d);
+    *loss = (logf(s_c) + ad * inv) * m;
+    *g_mu = ((d > 0.f) ? inv : ((d < 0.f) ? -inv : 0.f)) * m;
+    *g_ls = (inv - ad * inv * inv) * s_raw * m;
+  } else {
+    const float dd = d * d;
+    *loss = (logf(s_c) + dd * inv) * m;
+    *g_mu = 2.f * d * inv * m;
+    *g_ls = (inv - dd * inv * inv) * s_raw * m;
+  }
 }
+#define laplace_elem(...) nll_elem(kind, __VA_ARGS__)
 
 // generic elementwise forward over [rows][cols] with per-tensor row strides (covers the strided p1/p2 views)
 __global__ void laplace_fwd_kernel(const float* __restrict__ mu, long long mu_rs, const float* __restrict__ ls, long long ls_rs,
                                    const float* __restrict__ y, long long y_rs, const float* __restrict__ mask, long long m_rs,
                                    long long rows, long long cols, float eps_min, float eps_max, float* __restrict__ out_elem,
-                                   float* __restrict__ part /*[gridDim.x] or null*/) {
+                                   float* __restrict__ part /*[gridDim.x] or null*/, int kind) {
   __shared__ float sh[32];
   const long long total = rows * cols;
   float acc = 0.f;
@@ -318,7 +330,7 @@ __global__ void sum_partials_kernel(const float* __restrict__ part, int n, float
 __global__ void laplace_bwd_kernel(const float* __restrict__ mu, long long mu_rs, const float* __restrict__ ls, long long ls_rs,
                                    const float* __restrict__ y, long long y_rs, const float* __restrict__ mask, long long m_rs,
                                    long long rows, long long cols, float eps_min, float eps_max, const float* __restrict__ up,
-                                   int up_is_scalar, float up_scale, float* __restrict__ g_mu, float* __restrict__ g_ls) {
+                                   int up_is_scalar, float up_scale, float* __restrict__ g_mu, float* __restrict__ g_ls, int kind) {
   const long long total = rows * cols;
   const float us = up_is_scalar ? (*up) * up_scale : 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -328,6 +340,91 @@ __global__ void laplace_bwd_kernel(const float* __restrict__ mu, long long mu_rs
     const float u = up_is_scalar ? us : up[i];
     g_mu[i] = a * u;
     g_ls[i] = b * u;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Deep evidential regression head + loss (reference mimo/models/evidential_unet.py:74-96, mimo/losses.py:195-271) for the
+// M = 1, out_channels = 4 network: raw = (mu, log v, log alpha, log beta) per pixel.
+//   head:  v = softplus(raw1), alpha = softplus(raw2) + 1, beta = softplus(raw3)          (nn.Softplus: threshold 20)
+//   loss:  L = G(alpha - 1/2) / (4 G(alpha) v sqrt(beta)) * (2 beta (1 + v) + (2 alpha - 1) v d^2) + d^2 (2 alpha + v),  d = y - mu
+// All tensors [B][4][HW] / [B][HW] fp32, contiguous. One elementwise pass each way.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
+// digamma for x > 0: recurrence up to x >= 6, then the asymptotic series
+__device__ __forceinline__ float digamma_f(float x) {
+  float r = 0.f;
+  while (x < 6.f) { r -= 1.f / x; x += 1.f; }
+  const float i = 1.f / x, i2 = i * i;
+  return r + logf(x) - 0.5f * i - i2 * (1.f / 12.f - i2 * (1.f / 120.f - i2 * (1.f / 252.f)));
+}
+
+__global__ void evidential_head_kernel(const float* __restrict__ raw, float* __restrict__ out, long long B, long long HW) {
+  const long long total = B * HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / HW, p = i - b * HW;
+    const float* r = raw + b * 4 * HW + p;
+    float* o = out + b * 4 * HW + p;
+    o[0] = r[0];
+    o[HW] = softplus_f(r[HW]);
+    o[2 * HW] = softplus_f(r[2 * HW]) + 1.f;
+    o[3 * HW] = softplus_f(r[3 * HW]);
+  }
+}
+__global__ void evidential_head_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ g_out, float* __restrict__ g_raw,
+                                           long long B, long long HW) {
+  const long long total = B * HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / HW, p = i - b * HW;
+    const long long o = b * 4 * HW + p;
+    g_raw[o] = g_out[o];
+#pragma unroll
+    for (int c = 1; c < 4; ++c) {
+      const float x = raw[o + c * HW];
+      g_raw[o + c * HW] = g_out[o + c * HW] * (x > 20.f ? 1.f : sigmoid_f(x));
+    }
+  }
+}
+
+__device__ __forceinline__ void evidential_elem(float mu, float v, float alpha, float beta, float y, float m, float* loss, float g[4]) {
+  const float d = y - mu, dd = d * d;
+  const float R = expf(lgammaf(alpha - 0.5f)) / expf(lgammaf(alpha));   // as the reference: Gamma(x) = exp(lgamma(x))
+  const float coeff = R / (4.f * v * sqrtf(beta));
+  const float second = 2.f * beta * (1.f + v) + (2.f * alpha - 1.f) * v * dd;
+  *loss = (coeff * second + dd * (2.f * alpha + v)) * m;
+  g[0] = (coeff * (2.f * alpha - 1.f) * v + (2.f * alpha + v)) * (-2.f * d) * m;
+  g[1] = (-coeff / v * second + coeff * (2.f * beta + (2.f * alpha - 1.f) * dd) + dd) * m;
+  g[2] = (coeff * (digamma_f(alpha - 0.5f) - digamma_f(alpha)) * second + coeff * 2.f * v * dd + 2.f * dd) * m;
+  g[3] = (-coeff / (2.f * beta) * second + coeff * 2.f * (1.f + v)) * m;
+}
+
+// mode 0: elementwise loss (and, if part, per-block sums for the mean); mode 1: gradients w.r.t. the four parameters,
+// scaled by up[i] (elementwise upstream) or *up * up_scale (mean)
+__global__ void evidential_loss_kernel(const float* __restrict__ par, const float* __restrict__ y, const float* __restrict__ mask,
+                                       long long B, long long HW, int mode, float* __restrict__ out_elem, float* __restrict__ part,
+                                       const float* __restrict__ up, int up_is_scalar, float up_scale, float* __restrict__ g_par) {
+  __shared__ float sh[32];
+  const long long total = B * HW;
+  const float us = (mode == 1 && up_is_scalar) ? (*up) * up_scale : 0.f;
+  float acc = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / HW, p = i - b * HW;
+    const long long o = b * 4 * HW + p;
+    float l, g[4];
+    evidential_elem(par[o], par[o + HW], par[o + 2 * HW], par[o + 3 * HW], y[i], mask ? mask[i] : 1.f, &l, g);
+    if (mode == 0) {
+      if (out_elem) out_elem[i] = l;
+      acc += l;
+    } else {
+      const float u = up_is_scalar ? us : up[i];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) g_par[o + c * HW] = g[c] * u;
+    }
+  }
+  if (mode == 0 && part) {
+    const float sres = block_sum(acc, sh);
+    if (threadIdx.x == 0) part[blockIdx.x] = sres;
   }
 }
 
@@ -372,7 +469,7 @@ laplace_train_kernel(const float* __restrict__ out, const float* __restrict__ y,
                      const long long* __restrict__ gather /*[S][B] or null*/, int B, int S, int C, long long HW,
                      float eps_min, float eps_max, const LossBufferState* __restrict__ lb,
                      const float* __restrict__ fixed_w /*[S] or null*/, float* __restrict__ dout,
-                     float* __restrict__ part /*[B*S][nblk]*/, int nblk) {
+                     float* __restrict__ part /*[B*S][nblk]*/, int nblk, float* __restrict__ mpart /*[B*S][nblk][4] or null*/, int kind) {
   __shared__ float sh[32];
   __shared__ float sw[64];
   if (threadIdx.x == 0) {
@@ -396,6 +493,15 @@ laplace_train_kernel(const float* __restrict__ out, const float* __restrict__ y,
     float* gmu = dout ? dout + (long long)row * 2 * n : nullptr;
     float* gls = dout ? gmu + n : nullptr;
     float acc = 0.f;
+    // regression metrics of the location channel (reference mimo/metrics.py:22-34, called every step from
+    // mimo_unet.py:135): sum |e|, sum e^2, sum y, sum y^2 with e = mu - y; the mask does not enter (as in the reference)
+    float m_ae = 0.f, m_se = 0.f, m_y = 0.f, m_yy = 0.f;
+#define MIMO_METRIC(MU, Y)                                   \
+  {                                                          \
+    const float e_ = (MU) - (Y);                             \
+    m_ae += fabsf(e_); m_se = fmaf(e_, e_, m_se);            \
+    m_y += (Y); m_yy = fmaf((Y), (Y), m_yy);                 \
+  }
     const bool vec = ((n & 3) == 0) && ((reinterpret_cast<uintptr_t>(mu) & 15) == 0) && ((reinterpret_cast<uintptr_t>(yy) & 15) == 0) &&
                      (!mm || (reinterpret_cast<uintptr_t>(mm) & 15) == 0) && (!dout || (reinterpret_cast<uintptr_t>(gmu) & 15) == 0);
     if (vec) {
@@ -423,6 +529,7 @@ laplace_train_kernel(const float* __restrict__ out, const float* __restrict__ y,
         laplace_elem(a0.y, l0.y, t0.y, m0.y, eps_min, eps_max, &l, &ga.y, &gl.y); acc += l;
         laplace_elem(a0.z, l0.z, t0.z, m0.z, eps_min, eps_max, &l, &ga.z, &gl.z); acc += l;
         laplace_elem(a0.w, l0.w, t0.w, m0.w, eps_min, eps_max, &l, &ga.w, &gl.w); acc += l;
+        if (mpart) { MIMO_METRIC(a0.x, t0.x) MIMO_METRIC(a0.y, t0.y) MIMO_METRIC(a0.z, t0.z) MIMO_METRIC(a0.w, t0.w) }
         if (dout) {
           ga.x *= coef; ga.y *= coef; ga.z *= coef; ga.w *= coef;
           gl.x *= coef; gl.y *= coef; gl.z *= coef; gl.w *= coef;
@@ -434,6 +541,7 @@ laplace_train_kernel(const float* __restrict__ out, const float* __restrict__ y,
           laplace_elem(a1.y, l1.y, t1.y, m1.y, eps_min, eps_max, &l, &ga.y, &gl.y); acc += l;
           laplace_elem(a1.z, l1.z, t1.z, m1.z, eps_min, eps_max, &l, &ga.z, &gl.z); acc += l;
           laplace_elem(a1.w, l1.w, t1.w, m1.w, eps_min, eps_max, &l, &ga.w, &gl.w); acc += l;
+          if (mpart) { MIMO_METRIC(a1.x, t1.x) MIMO_METRIC(a1.y, t1.y) MIMO_METRIC(a1.z, t1.z) MIMO_METRIC(a1.w, t1.w) }
           if (dout) {
             ga.x *= coef; ga.y *= coef; ga.z *= coef; ga.w *= coef;
             gl.x *= coef; gl.y *= coef; gl.z *= coef; gl.w *= coef;
@@ -449,11 +557,20 @@ laplace_train_kernel(const float* __restrict__ out, const float* __restrict__ y,
         float l, ga, gl;
         laplace_elem(mu[i], ls[i], yy[i], mm ? mm[i] : 1.f, eps_min, eps_max, &l, &ga, &gl);
         acc += l;
+        if (mpart) MIMO_METRIC(mu[i], yy[i])
         if (dout) { gmu[i] = ga * coef; gls[i] = gl * coef; }
       }
     }
+#undef MIMO_METRIC
     const float sres = block_sum(acc, sh);
     if (threadIdx.x == 0) part[(size_t)row * nblk + chunk] = sres;
+    if (mpart) {
+      const float r0 = block_sum(m_ae, sh), r1 = block_sum(m_se, sh), r2 = block_sum(m_y, sh), r3 = block_sum(m_yy, sh);
+      if (threadIdx.x == 0) {
+        float* mp = mpart + ((size_t)row * nblk + chunk) * 4;
+        mp[0] = r0; mp[1] = r1; mp[2] = r2; mp[3] = r3;
+      }
+    }
   }
 }
 
@@ -461,8 +578,10 @@ laplace_train_kernel(const float* __restrict__ out, const float* __restrict__ y,
 __global__ void laplace_train_finalize_kernel(const float* __restrict__ part, int nblk, int B, int S, double count,
                                               LossBufferState* lb, const float* __restrict__ fixed_w, int update_buffer,
                                               float* __restrict__ loss /*[S]*/, float* __restrict__ weights /*[S]*/,
-                                              float* __restrict__ weighted /*[1]*/) {
+                                              float* __restrict__ weighted /*[1]*/, const float* __restrict__ mpart,
+                                              float* __restrict__ metrics /*[4]: mae, mse, rmse, r2*/) {
   __shared__ float sl[64];
+  __shared__ double sm[8][4];
   // one warp per subnetwork (fixed lane-strided order + butterfly: deterministic), all subnetworks in parallel
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   for (int s = warp; s < S; s += nwarps) {
@@ -475,7 +594,33 @@ __global__ void laplace_train_finalize_kernel(const float* __restrict__ part, in
     for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
     if (lane == 0) sl[s] = (float)(a / count);
   }
+  if (mpart && metrics) {
+    // fixed thread-strided order + butterfly + fixed warp order: deterministic
+    double a[4] = {0.0, 0.0, 0.0, 0.0};
+    const int total = B * S * nblk;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) a[k] += (double)mpart[(size_t)i * 4 + k];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a[k] += __shfl_xor_sync(0xffffffffu, a[k], o);
+      if (lane == 0 && warp < 8) sm[warp][k] = a[k];
+    }
+  }
   __syncthreads();
+  if (threadIdx.x == 0 && mpart && metrics) {
+    double t[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int w2 = 0; w2 < nwarps && w2 < 8; ++w2)
+      for (int k = 0; k < 4; ++k) t[k] += sm[w2][k];
+    const double nn = count * (double)S;   // all B*S*C*H*W elements
+    const double mse = t[1] / nn;
+    metrics[0] = (float)(t[0] / nn);
+    metrics[1] = (float)mse;
+    metrics[2] = (float)sqrt(mse);
+    metrics[3] = (float)(1.0 - t[1] / (t[3] - t[2] * t[2] / nn));   // r2 = 1 - SS_res / SS_tot
+  }
   if (threadIdx.x == 0) {
     float w[64];
     float* buf = lb ? reinterpret_cast<float*>(lb + 1) : nullptr;
@@ -728,12 +873,43 @@ int head_bwd_launch(const ActView& f, const float* W, int K, const float* dout, 
 
 int laplace_parts() { return num_sms() * 8; }
 
+int evidential_head_launch(const float* raw, float* out, long long B, long long HW, cudaStream_t st) {
+  evidential_head_kernel<<<grid_for(B * HW, 4), kBlock, 0, st>>>(raw, out, B, HW);
+  MIMO_LAUNCH_CHECK();
+  return MIMO_OK;
+}
+int evidential_head_bwd_launch(const float* raw, const float* g_out, float* g_raw, long long B, long long HW, cudaStream_t st) {
+  evidential_head_bwd_kernel<<<grid_for(B * HW, 4), kBlock, 0, st>>>(raw, g_out, g_raw, B, HW);
+  MIMO_LAUNCH_CHECK();
+  return MIMO_OK;
+}
+int evidential_loss_fwd_launch(const float* par, const float* y, const float* mask, long long B, long long HW, float* out_elem,
+                               float* part, float* out_mean, cudaStream_t st) {
+  const int grid = grid_for(B * HW, 4);
+  evidential_loss_kernel<<<grid, kBlock, 0, st>>>(par, y, mask, B, HW, 0, out_elem, out_mean ? part : nullptr, nullptr, 0, 0.f, nullptr);
+  MIMO_LAUNCH_CHECK();
+  if (out_mean) {
+    MIMO_CHECK(part != nullptr, MIMO_ERR_ARG, "evidential_loss_fwd: partial buffer required for the mean");
+    sum_partials_kernel<<<1, kBlock, 0, st>>>(part, grid, (float)(1.0 / (double)(B * HW)), out_mean);
+    MIMO_LAUNCH_CHECK();
+  }
+  return MIMO_OK;
+}
+int evidential_loss_bwd_launch(const float* par, const float* y, const float* mask, long long B, long long HW, const float* up,
+                               int up_is_scalar, float up_scale, float* g_par, cudaStream_t st) {
+  evidential_loss_kernel<<<grid_for(B * HW, 4), kBlock, 0, st>>>(par, y, mask, B, HW, 1, nullptr, nullptr, up, up_is_scalar, up_scale, g_par);
+  MIMO_LAUNCH_CHECK();
+  return MIMO_OK;
+}
+
+
+
 int laplace_fwd_launch(const float* mu, long long mu_rs, const float* ls, long long ls_rs, const float* y, long long y_rs,
                        const float* mask, long long m_rs, long long rows, long long cols, float eps_min, float eps_max,
-                       float* out_elem, float* part, float* out_mean, cudaStream_t st) {
+                       float* out_elem, float* part, float* out_mean, cudaStream_t st, int kind) {
   const int grid = grid_for(rows * cols, 4);
   laplace_fwd_kernel<<<grid, kBlock, 0, st>>>(mu, mu_rs, ls, ls_rs, y, y_rs, mask, m_rs, rows, cols, eps_min, eps_max, out_elem,
-                                              out_mean ? part : nullptr);
+                                              out_mean ? part : nullptr, kind);
   MIMO_LAUNCH_CHECK();
   if (out_mean) {
     MIMO_CHECK(part != nullptr, MIMO_ERR_ARG, "laplace_fwd: partial buffer required for the mean");
@@ -745,9 +921,9 @@ int laplace_fwd_launch(const float* mu, long long mu_rs, const float* ls, long l
 
 int laplace_bwd_launch(const float* mu, long long mu_rs, const float* ls, long long ls_rs, const float* y, long long y_rs,
                        const float* mask, long long m_rs, long long rows, long long cols, float eps_min, float eps_max,
-                       const float* up, int up_is_scalar, float up_scale, float* g_mu, float* g_ls, cudaStream_t st) {
+                       const float* up, int up_is_scalar, float up_scale, float* g_mu, float* g_ls, cudaStream_t st, int kind) {
   laplace_bwd_kernel<<<grid_for(rows * cols, 4), kBlock, 0, st>>>(mu, mu_rs, ls, ls_rs, y, y_rs, mask, m_rs, rows, cols, eps_min,
-                                                                 eps_max, up, up_is_scalar, up_scale, g_mu, g_ls);
+                                                                 eps_max, up, up_is_scalar, up_scale, g_mu, g_ls, kind);
   MIMO_LAUNCH_CHECK();
   return MIMO_OK;
 }
@@ -782,8 +958,9 @@ int laplace_train_blocks(long long n) {
 int laplace_train_launch(const float* out, const float* y, long long y_bs, long long y_ss, const float* mask, long long m_bs,
                          long long m_ss, const long long* gather, int B, int S, int C, long long HW, float eps_min, float eps_max,
                          void* lb_state, const float* fixed_w, int update_buffer, float* dout, float* part, float* loss,
-                         float* weights, float* weighted, cudaStream_t st) {
+                         float* weights, float* weighted, cudaStream_t st, float* mpart, float* metrics, int kind) {
   MIMO_CHECK(S >= 1 && S <= 64, MIMO_ERR_ARG, "laplace_train: 1..64 subnetworks supported");
+  MIMO_CHECK((mpart == nullptr) == (metrics == nullptr), MIMO_ERR_ARG, "laplace_train: metrics need both the scratch and the output");
   const long long n = (long long)C * HW;
   const int nblk = laplace_train_blocks(n);
   const long long items = (long long)B * S * nblk;
@@ -791,10 +968,10 @@ int laplace_train_launch(const float* out, const float* y, long long y_bs, long 
   int grid = 4 * num_sms();
   if (grid > items) grid = (int)items;
   laplace_train_kernel<<<grid, kBlock, 0, st>>>(out, y, y_bs, y_ss, mask, m_bs, m_ss, gather, B, S, C, HW, eps_min, eps_max,
-                                                (const LossBufferState*)lb_state, fixed_w, dout, part, nblk);
+                                                (const LossBufferState*)lb_state, fixed_w, dout, part, nblk, mpart, kind);
   MIMO_LAUNCH_CHECK();
   laplace_train_finalize_kernel<<<1, kBlock, 0, st>>>(part, nblk, B, S, (double)B * (double)n, (LossBufferState*)lb_state, fixed_w,
-                                                      update_buffer, loss, weights, weighted);
+                                                      update_buffer, loss, weights, weighted, mpart, metrics);
   MIMO_LAUNCH_CHECK();
   return MIMO_OK;
 }

@@ -72,10 +72,16 @@ int head_bwd_launch(const ActView& f, const float* W, int K, const float* dout, 
 int laplace_parts();
 int laplace_fwd_launch(const float* mu, long long mu_rs, const float* ls, long long ls_rs, const float* y, long long y_rs,
                        const float* mask, long long m_rs, long long rows, long long cols, float eps_min, float eps_max,
-                       float* out_elem, float* part, float* out_mean, cudaStream_t st);
+                       float* out_elem, float* part, float* out_mean, cudaStream_t st, int kind = 0 /* 0 Laplace, 1 Gaussian */);
 int laplace_bwd_launch(const float* mu, long long mu_rs, const float* ls, long long ls_rs, const float* y, long long y_rs,
                        const float* mask, long long m_rs, long long rows, long long cols, float eps_min, float eps_max,
-                       const float* up, int up_is_scalar, float up_scale, float* g_mu, float* g_ls, cudaStream_t st);
+                       const float* up, int up_is_scalar, float up_scale, float* g_mu, float* g_ls, cudaStream_t st, int kind = 0);
+int evidential_head_launch(const float* raw, float* out, long long B, long long HW, cudaStream_t st);
+int evidential_head_bwd_launch(const float* raw, const float* g_out, float* g_raw, long long B, long long HW, cudaStream_t st);
+int evidential_loss_fwd_launch(const float* par, const float* y, const float* mask, long long B, long long HW, float* out_elem,
+                               float* part, float* out_mean, cudaStream_t st);
+int evidential_loss_bwd_launch(const float* par, const float* y, const float* mask, long long B, long long HW, const float* up,
+                               int up_is_scalar, float up_scale, float* g_par, cudaStream_t st);
 size_t lossbuffer_bytes(int S, int size);
 int lossbuffer_init_launch(void* state, int S, int size, float T, cudaStream_t st);
 int lossbuffer_weights_launch(const void* state, float* w, cudaStream_t st);
@@ -84,7 +90,7 @@ int laplace_train_blocks(long long n);
 int laplace_train_launch(const float* out, const float* y, long long y_bs, long long y_ss, const float* mask, long long m_bs,
                          long long m_ss, const long long* gather, int B, int S, int C, long long HW, float eps_min, float eps_max,
                          void* lb_state, const float* fixed_w, int update_buffer, float* dout, float* part, float* loss,
-                         float* weights, float* weighted, cudaStream_t st);
+                         float* weights, float* weighted, cudaStream_t st, float* mpart = nullptr, float* metrics = nullptr, int kind = 0);
 int scale_by_scalar_launch(float* x, long long n, const float* s, cudaStream_t st);
 int aggregate_launch(const float* p1, long long p1_bs, long long p1_ss, const float* p2, long long p2_bs, long long p2_ss, int B,
                      int S, long long inner, float* mean, float* alea, float* epi, cudaStream_t st);

@@ -74,7 +74,7 @@ class _LaplaceNLLFn(torch.autograd.Function):
     """LaplaceNLL.forward (reference mimo/losses.py:132-164) on the GPU, elementwise or mean."""
 
     @staticmethod
-    def forward(ctx, y_hat, log_scale, y, mask, reduce_mean: bool, eps_min: float, eps_max: float):
+    def forward(ctx, y_hat, log_scale, y, mask, reduce_mean: bool, eps_min: float, eps_max: float, gaussian: bool = False):
         _need_cuda(y_hat, log_scale, y, mask)
         shape = torch.broadcast_shapes(y_hat.shape, log_scale.shape, y.shape, *( [mask.shape] if mask is not None else []))
         ops = [y_hat.detach(), log_scale.detach(), y.detach()] + ([mask.detach()] if mask is not None else [])
@@ -83,20 +83,22 @@ class _LaplaceNLLFn(torch.autograd.Function):
         mu_rs, ls_rs, y_rs = rss[0], rss[1], rss[2]
         mm, m_rs = (ts[3], rss[3]) if mask is not None else (None, 0)
         lib = _lib.lib()
+        fwd = lib.mimo_gaussian_nll_fwd if gaussian else lib.mimo_laplace_nll_fwd
         dev = mu.device
         n = rows * cols
         if reduce_mean:
             out = torch.empty((), dtype=torch.float32, device=dev)
             part = torch.empty(int(lib.mimo_laplace_scratch_floats()), dtype=torch.float32, device=dev)
-            check(lib.mimo_laplace_nll_fwd(mu.data_ptr(), mu_rs, ls.data_ptr(), ls_rs, yy.data_ptr(), y_rs, _ptr(mm), m_rs, rows, cols,
-                                           eps_min, eps_max, None, part.data_ptr(), out.data_ptr(), stream_ptr()), "mimo_laplace_nll_fwd")
+            check(fwd(mu.data_ptr(), mu_rs, ls.data_ptr(), ls_rs, yy.data_ptr(), y_rs, _ptr(mm), m_rs, rows, cols,
+                      eps_min, eps_max, None, part.data_ptr(), out.data_ptr(), stream_ptr()), "mimo_*_nll_fwd")
         else:
             out = torch.empty(shape, dtype=torch.float32, device=dev)
-            check(lib.mimo_laplace_nll_fwd(mu.data_ptr(), mu_rs, ls.data_ptr(), ls_rs, yy.data_ptr(), y_rs, _ptr(mm), m_rs, rows, cols,
-                                           eps_min, eps_max, out.data_ptr(), None, None, stream_ptr()), "mimo_laplace_nll_fwd")
+            check(fwd(mu.data_ptr(), mu_rs, ls.data_ptr(), ls_rs, yy.data_ptr(), y_rs, _ptr(mm), m_rs, rows, cols,
+                      eps_min, eps_max, out.data_ptr(), None, None, stream_ptr()), "mimo_*_nll_fwd")
         ctx.save_for_backward(mu, ls, yy, mm if mm is not None else torch.empty(0, device=dev))
         ctx.geom = (rows, cols, mu_rs, ls_rs, y_rs, m_rs, mm is not None, reduce_mean, eps_min, eps_max, shape,
                     tuple(y_hat.shape), tuple(log_scale.shape))
+        ctx.gaussian = gaussian
         return out
 
     @staticmethod
@@ -107,19 +109,25 @@ class _LaplaceNLLFn(torch.autograd.Function):
         g_mu = torch.empty(shape, dtype=torch.float32, device=mu.device)
         g_ls = torch.empty(shape, dtype=torch.float32, device=mu.device)
         g = g.contiguous().float()
-        check(lib.mimo_laplace_nll_bwd(mu.data_ptr(), mu_rs, ls.data_ptr(), ls_rs, yy.data_ptr(), y_rs, mm.data_ptr() if has_mask else None,
-                                       m_rs, rows, cols, eps_min, eps_max, g.data_ptr(), int(reduce_mean),
-                                       1.0 / float(rows * cols) if reduce_mean else 1.0, g_mu.data_ptr(), g_ls.data_ptr(), stream_ptr()),
-              "mimo_laplace_nll_bwd")
+        bwd = lib.mimo_gaussian_nll_bwd if ctx.gaussian else lib.mimo_laplace_nll_bwd
+        check(bwd(mu.data_ptr(), mu_rs, ls.data_ptr(), ls_rs, yy.data_ptr(), y_rs, mm.data_ptr() if has_mask else None,
+                  m_rs, rows, cols, eps_min, eps_max, g.data_ptr(), int(reduce_mean),
+                  1.0 / float(rows * cols) if reduce_mean else 1.0, g_mu.data_ptr(), g_ls.data_ptr(), stream_ptr()),
+              "mimo_*_nll_bwd")
         if tuple(shape) != s_mu:
             g_mu = g_mu.sum_to_size(s_mu)
         if tuple(shape) != s_ls:
             g_ls = g_ls.sum_to_size(s_ls)
-        return g_mu, g_ls, None, None, None, None, None
+        return g_mu, g_ls, None, None, None, None, None, None
 
 
 def laplace_nll(y_hat, log_scale, y, mask=None, reduce_mean=True, eps_min=1e-5, eps_max=1e3):
-    return _LaplaceNLLFn.apply(y_hat, log_scale, y, mask, bool(reduce_mean), float(eps_min), float(eps_max))
+    return _LaplaceNLLFn.apply(y_hat, log_scale, y, mask, bool(reduce_mean), float(eps_min), float(eps_max), False)
+
+
+def gaussian_nll(y_hat, log_variance, y, mask=None, reduce_mean=True, eps_min=1e-5, eps_max=1e3):
+    """GaussianNLL.forward (reference mimo/losses.py:48-79): same kernels, Gaussian element math."""
+    return _LaplaceNLLFn.apply(y_hat, log_variance, y, mask, bool(reduce_mean), float(eps_min), float(eps_max), True)
 
 
 class DeviceLossBuffer:
@@ -156,7 +164,8 @@ class _TrainLossFn(torch.autograd.Function):
     the seed of backward: one pass produces loss[S], weights[S], the scalar weighted loss and d/d out."""
 
     @staticmethod
-    def forward(ctx, out, y, mask, gather, lb_state, fixed_w, update_buffer: bool, eps_min: float, eps_max: float):
+    def forward(ctx, out, y, mask, gather, lb_state, fixed_w, update_buffer: bool, eps_min: float, eps_max: float,
+                want_metrics: bool = False, gaussian: bool = False):
         _need_cuda(out, y, mask)
         lib = _lib.lib()
         B, S, C2, H, W = out.shape
@@ -186,33 +195,116 @@ class _TrainLossFn(torch.autograd.Function):
         dev = outc.device
         need_grad = out.requires_grad
         dout = torch.empty_like(outc) if need_grad else None
-        part = torch.empty(int(lib.mimo_laplace_train_scratch_floats(B, S, C, HW)), dtype=torch.float32, device=dev)
-        res = torch.empty(2 * S + 1, dtype=torch.float32, device=dev)
-        loss, weights, weighted = res[:S], res[S:2 * S], res[2 * S:]
-        check(lib.mimo_laplace_nll_train(outc.data_ptr(), yc.data_ptr(), y_bs, y_ss, _ptr(mc), m_bs, m_ss, _ptr(gather), B, S, C, HW,
-                                         eps_min, eps_max, _ptr(lb_state), _ptr(fixed_w), int(update_buffer), _ptr(dout),
-                                         part.data_ptr(), loss.data_ptr(), weights.data_ptr(), weighted.data_ptr(), stream_ptr()),
-              "mimo_laplace_nll_train")
+        res = torch.empty(2 * S + 1 + 4, dtype=torch.float32, device=dev)
+        loss, weights, weighted, metrics = res[:S], res[S:2 * S], res[2 * S:2 * S + 1], res[2 * S + 1:]
+        if want_metrics or gaussian:
+            # r2 / mae / mse / rmse of (mu, y) come out of the same pass (reference mimo/metrics.py: four more reductions)
+            part = torch.empty(int(lib.mimo_laplace_train_metrics_scratch_floats(B, S, C, HW)), dtype=torch.float32, device=dev)
+            fn = lib.mimo_gaussian_nll_train_metrics if gaussian else lib.mimo_laplace_nll_train_metrics
+            check(fn(outc.data_ptr(), yc.data_ptr(), y_bs, y_ss, _ptr(mc), m_bs, m_ss, _ptr(gather), B, S, C,
+                     HW, eps_min, eps_max, _ptr(lb_state), _ptr(fixed_w), int(update_buffer), _ptr(dout),
+                     part.data_ptr(), loss.data_ptr(), weights.data_ptr(), weighted.data_ptr(),
+                     metrics.data_ptr(), stream_ptr()), "mimo_*_nll_train_metrics")
+        else:
+            part = torch.empty(int(lib.mimo_laplace_train_scratch_floats(B, S, C, HW)), dtype=torch.float32, device=dev)
+            check(lib.mimo_laplace_nll_train(outc.data_ptr(), yc.data_ptr(), y_bs, y_ss, _ptr(mc), m_bs, m_ss, _ptr(gather), B, S, C, HW,
+                                             eps_min, eps_max, _ptr(lb_state), _ptr(fixed_w), int(update_buffer), _ptr(dout),
+                                             part.data_ptr(), loss.data_ptr(), weights.data_ptr(), weighted.data_ptr(), stream_ptr()),
+                  "mimo_laplace_nll_train")
         ctx.dout = dout
-        ctx.mark_non_differentiable(loss, weights)
-        return weighted.reshape(()), loss, weights
+        ctx.mark_non_differentiable(loss, weights, metrics)
+        return weighted.reshape(()), loss, weights, metrics
 
     @staticmethod
-    def backward(ctx, g_weighted, g_loss, g_weights):
+    def backward(ctx, g_weighted, g_loss, g_weights, g_metrics):
         dout = ctx.dout
         ctx.dout = None
         if dout is None:
-            return (None,) * 9
+            return (None,) * 11
         g = g_weighted.detach().reshape(1).float().contiguous()
         check(_lib.lib().mimo_scale_by_scalar(dout.data_ptr(), dout.numel(), g.data_ptr(), stream_ptr()), "mimo_scale_by_scalar")
-        return (dout,) + (None,) * 8
+        return (dout,) + (None,) * 10
 
 
 def laplace_train_loss(out, y, mask=None, gather=None, loss_buffer: Optional[DeviceLossBuffer] = None, fixed_weights=None,
-                       update_buffer=True, eps_min=1e-5, eps_max=1e3):
-    """Returns (weighted_mean_loss scalar [differentiable], loss[S], weights[S])."""
-    return _TrainLossFn.apply(out, y, mask, gather, None if loss_buffer is None else loss_buffer.state, fixed_weights,
-                              bool(update_buffer), float(eps_min), float(eps_max))
+                       update_buffer=True, eps_min=1e-5, eps_max=1e3, with_metrics=False, gaussian=False):
+    """Returns (weighted_mean_loss scalar [differentiable], loss[S], weights[S]); with_metrics appends the regression metrics
+    {"mae", "mse", "rmse", "r2"} of (mu, y) as 0-d tensors (reference mimo/metrics.py:22-34), produced by the same kernel pass."""
+    total, loss, weights, metrics = _TrainLossFn.apply(out, y, mask, gather, None if loss_buffer is None else loss_buffer.state,
+                                                       fixed_weights, bool(update_buffer), float(eps_min), float(eps_max), bool(with_metrics), bool(gaussian))
+    if with_metrics:
+        return total, loss, weights, {"r2": metrics[3], "mae": metrics[0], "mse": metrics[1], "rmse": metrics[2]}
+    return total, loss, weights
+
+
+class _EvidentialHeadFn(torch.autograd.Function):
+    """(mu, log v, log alpha, log beta) -> (mu, softplus, softplus + 1, softplus): reference evidential_unet.py:85-96."""
+
+    @staticmethod
+    def forward(ctx, raw):
+        _need_cuda(raw)
+        r = raw.detach().contiguous().float()
+        B, C, H, W = r.shape
+        assert C == 4, "the evidential head needs 4 output channels (mu, v, alpha, beta)"
+        out = torch.empty_like(r)
+        check(_lib.lib().mimo_evidential_head(r.data_ptr(), out.data_ptr(), B, H * W, stream_ptr()), "mimo_evidential_head")
+        ctx.save_for_backward(r)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (r,) = ctx.saved_tensors
+        B, _, H, W = r.shape
+        g = g.contiguous().float()
+        g_raw = torch.empty_like(r)
+        check(_lib.lib().mimo_evidential_head_bwd(r.data_ptr(), g.data_ptr(), g_raw.data_ptr(), B, H * W, stream_ptr()), "mimo_evidential_head_bwd")
+        return g_raw
+
+
+def evidential_head(raw: torch.Tensor) -> torch.Tensor:
+    return _EvidentialHeadFn.apply(raw)
+
+
+class _EvidentialLossFn(torch.autograd.Function):
+    """EvidentialLoss.forward (reference mimo/losses.py:203-256), elementwise [B,H,W] or mean."""
+
+    @staticmethod
+    def forward(ctx, params, y, mask, reduce_mean: bool):
+        _need_cuda(params, y, mask)
+        p = params.detach().contiguous().float()
+        B, C, H, W = p.shape
+        assert C == 4
+        yy = y.detach().float().reshape(B, H * W).contiguous()
+        mm = None if mask is None else mask.detach().float().expand(B, *mask.shape[1:]).reshape(B, H * W).contiguous()
+        lib = _lib.lib()
+        if reduce_mean:
+            out = torch.empty((), dtype=torch.float32, device=p.device)
+            part = torch.empty(int(lib.mimo_laplace_scratch_floats()), dtype=torch.float32, device=p.device)
+            check(lib.mimo_evidential_loss_fwd(p.data_ptr(), yy.data_ptr(), _ptr(mm), B, H * W, None, part.data_ptr(), out.data_ptr(),
+                                               stream_ptr()), "mimo_evidential_loss_fwd")
+        else:
+            out = torch.empty(B, H, W, dtype=torch.float32, device=p.device)
+            check(lib.mimo_evidential_loss_fwd(p.data_ptr(), yy.data_ptr(), _ptr(mm), B, H * W, out.data_ptr(), None, None, stream_ptr()),
+                  "mimo_evidential_loss_fwd")
+        ctx.save_for_backward(p, yy, mm if mm is not None else torch.empty(0, device=p.device))
+        ctx.meta = (mm is not None, reduce_mean)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        p, yy, mm = ctx.saved_tensors
+        has_mask, reduce_mean = ctx.meta
+        B, _, H, W = p.shape
+        g = g.contiguous().float()
+        gp = torch.empty_like(p)
+        check(_lib.lib().mimo_evidential_loss_bwd(p.data_ptr(), yy.data_ptr(), mm.data_ptr() if has_mask else None, B, H * W, g.data_ptr(),
+                                                  int(reduce_mean), 1.0 / float(B * H * W) if reduce_mean else 1.0, gp.data_ptr(),
+                                                  stream_ptr()), "mimo_evidential_loss_bwd")
+        return gp, None, None, None
+
+
+def evidential_loss(params, y, mask=None, reduce_mean=False):
+    return _EvidentialLossFn.apply(params, y, mask, bool(reduce_mean))
 
 
 def ensemble_aggregate(p1: torch.Tensor, p2: torch.Tensor):

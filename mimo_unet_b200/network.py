@@ -121,6 +121,23 @@ class NetworkRuntime:
             off += n
         self._grad_views = views
 
+    def _assert_grads_aliased(self):
+        """Run by grad_sync.wait(): the overlapped all-reduce averages the flat buffer IN PLACE on a side stream, which is only
+        correct if every parameter's .grad is a view of that buffer (autograd adopts the returned views when .grad was None).
+        If autograd cloned or accumulated instead (a pre-existing non-aliased .grad, hooks), the optimizer would step on
+        un-reduced gradients and the ranks would diverge silently: fail loudly instead."""
+        if self._flat_grads is None:
+            return
+        lo = self._flat_grads.data_ptr()
+        hi = lo + self._flat_grads.numel() * 4
+        state = _state_entries(self.net)
+        bad = [i for i in self._learnable_idx if state[i].grad is not None and not (lo <= state[i].grad.data_ptr() < hi)]
+        if bad:
+            raise _lib.MimoError(f"data-parallel gradient sync: {len(bad)} parameter gradients are not views of the flat gradient buffer "
+                                 "(a .grad tensor existed before backward and autograd accumulated into it). Call "
+                                 "optimizer.zero_grad(set_to_none=True) before the step (or keep the .grad tensors returned by this "
+                                 "module), otherwise the all-reduced values never reach the optimizer.")
+
     @property
     def flat_grads(self) -> Optional[torch.Tensor]:
         """One contiguous fp32 tensor holding every parameter gradient (bucket for the data-parallel all-reduce)."""
@@ -223,9 +240,15 @@ class NetworkRuntime:
         lo = self._flat_grads.data_ptr()
         hi = lo + self._flat_grads.numel() * 4
         aliased = [i for i in self._learnable_idx if state[i].grad is not None and lo <= state[i].grad.data_ptr() < hi]
+        sync = self.grad_sync
         if aliased and len(aliased) == len(self._learnable_idx):
-            # the user kept .grad from the previous step (gradient accumulation): add in place, hand nothing to autograd
+            # the user kept .grad from the previous step (gradient accumulation, or zero_grad(set_to_none=False)): add in place,
+            # hand nothing to autograd. Data parallel: the accumulated buffer is averaged again -- the part that was already
+            # averaged is identical on every rank, so mean(previous mean + local) = previous mean + mean(local).
+            plan.set_backward_events(sync.events if sync is not None else None)
             plan.backward(dout, dx=dx, accumulate=True)
+            if sync is not None:
+                sync.launch(self._flat_grads, self._stage_bounds(plan, state))
             grads = [None] * len(state)
         else:
             if aliased:  # mixed case: do not clobber live .grad tensors, use a private buffer for this pass
@@ -233,11 +256,11 @@ class NetworkRuntime:
                 self._ensure_grad_buffer(state)
                 plan._bound_sig = None
                 plan.bind([t.detach() for t in state], self._grad_views)
-            sync = self.grad_sync
             plan.set_backward_events(sync.events if sync is not None else None)
             plan.backward(dout, dx=dx, accumulate=False)
             if sync is not None:
                 sync.launch(self._flat_grads, self._stage_bounds(plan, state))
+                sync._after_wait = self._assert_grads_aliased
             # fresh view objects so autograd can adopt them as .grad without a copy
             grads, off = [None] * len(state), 0
             for i in self._learnable_idx:

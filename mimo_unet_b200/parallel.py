@@ -76,6 +76,7 @@ class OverlappedGradientSynchronizer:
             e.record()  # torch creates the cudaEvent_t lazily on the first record
         self.side = torch.cuda.Stream()
         self._work: List = []
+        self._after_wait = None   # callable run by wait() once the buckets have been joined (gradient-aliasing check)
 
     def launch(self, flat: torch.Tensor, bounds):
         """bounds[k] = (start, end) element range of stage k inside `flat`."""
@@ -93,6 +94,33 @@ class OverlappedGradientSynchronizer:
         for w in self._work:
             w.wait()
         self._work = []
+        if self._after_wait is not None:
+            cb, self._after_wait = self._after_wait, None
+            cb()
+
+    def exchange_loss(self, loss: torch.Tensor, loss_buffer) -> None:
+        """Data-parallel loss-buffer update OFF the compute stream: the [S] per-subnetwork loss is averaged over ranks and
+        added to the device loss buffer on the side stream; the next step's loss kernel waits for `loss_event` before it reads
+        the buffer. (The result is not needed before the next step, so nothing on the compute stream blocks on NCCL.)"""
+        cur = torch.cuda.current_stream()
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        loss.record_stream(self.side)
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(ready)
+            l = loss.detach().clone()
+            allreduce_mean_(l, self.group)
+            loss_buffer.add(l)
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+        self.loss_event = ev
+
+    loss_event = None
+
+    def join_loss_exchange(self) -> None:
+        if self.loss_event is not None:
+            torch.cuda.current_stream().wait_event(self.loss_event)
+            self.loss_event = None
 
 
 def allreduce_mean_(t: torch.Tensor, group=None) -> torch.Tensor:

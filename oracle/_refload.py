@@ -1,19 +1,35 @@
 """Loads the reference's torch-only modules from /root/reference under the alias ``_refmimo``
 so they never collide with this repo's own ``mimo`` package.  TEST INFRASTRUCTURE ONLY.
 
-Only works in the build container (the GPU box has no /root/reference); callers must check
-``reference_available()`` first.
+Sources, in order: $MIMO_REFERENCE_ROOT, /root/reference (build container), oracle/_ref (staged copy of the five torch-only
+files, git-ignored, shipped to the GPU box by gpurun). Callers must check ``reference_available()`` first.
 """
 import importlib
 import importlib.util
 import os
 import sys
 
-REF_ROOT = os.environ.get("MIMO_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def _has_reference(root: str) -> bool:
+    return os.path.isfile(os.path.join(root, "mimo", "models", "mimo_components", "model.py"))
+
+
+def _pick_root() -> str:
+    """The live checkout in the build container, else the copy oracle/stage_reference.py staged into the git-ignored
+    oracle/_ref/ (that copy travels to the GPU box with the gpurun snapshot)."""
+    for root in (os.environ.get("MIMO_REFERENCE_ROOT"), "/root/reference", _STAGED):
+        if root and _has_reference(root):
+            return root
+    return "/root/reference"
+
+
+REF_ROOT = _pick_root()
 
 
 def reference_available() -> bool:
-    return os.path.isfile(os.path.join(REF_ROOT, "mimo", "models", "mimo_components", "model.py"))
+    return _has_reference(REF_ROOT)
 
 
 def load():

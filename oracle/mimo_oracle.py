@@ -255,6 +255,37 @@ def laplace_nll_grads(mu: Tensor, log_s: Tensor, y: Tensor, mask: Optional[Tenso
     return g_mu, g_ls
 
 
+def gaussian_nll_elementwise(mu: Tensor, log_var: Tensor, y: Tensor, mask: Optional[Tensor] = None,
+                             eps_min: float = 1e-5, eps_max: float = 1e3) -> Tensor:
+    """losses.py:48-79 (GaussianNLL.forward).  l = log(clamp(exp(log_var))) + (mu - y)^2 / clamp(exp(log_var)); the clamp is
+    applied in place under no_grad on a clone, i.e. it is invisible to autograd."""
+    v_raw = torch.exp(log_var)
+    v_c = v_raw + (v_raw.detach().clamp(eps_min, eps_max) - v_raw.detach())
+    loss = torch.log(v_c) + (mu - y) ** 2 / v_c
+    if mask is not None:
+        loss = loss * mask
+    return loss
+
+
+def evidential_head(raw: Tensor) -> Tensor:
+    """evidential_unet.py:85-96: raw [B,4,H,W] = (mu, log v, log alpha, log beta) -> (mu, softplus, softplus + 1, softplus)."""
+    mu, logv, loga, logb = torch.unbind(raw, dim=1)
+    return torch.stack([mu, F.softplus(logv), F.softplus(loga) + 1, F.softplus(logb)], dim=1)
+
+
+def evidential_loss_elementwise(params: Tensor, y: Tensor, mask: Optional[Tensor] = None) -> Tensor:
+    """losses.py:203-256 (EvidentialLoss.evidential_loss + forward): params [B,4,H,W] = (gamma, v, alpha, beta), y [B,1,H,W]
+    -> [B,H,W].  Gamma(x) = exp(lgamma(x)) as in the reference."""
+    mu, v, alpha, beta = torch.unbind(params, dim=1)
+    t = y.squeeze(dim=1)
+    coeff = torch.exp(torch.lgamma(alpha - 0.5)) / (4 * torch.exp(torch.lgamma(alpha)) * v * torch.sqrt(beta))
+    second = 2 * beta * (1 + v) + (2 * alpha - 1) * v * (t - mu) ** 2
+    loss = coeff * second + (t - mu) ** 2 * (2 * alpha + v)
+    if mask is not None:
+        loss = loss * mask
+    return loss
+
+
 def laplace_std(log_s: Tensor) -> Tensor:
     """losses.py:166-167."""
     return torch.exp(log_s) * math.sqrt(2.0)

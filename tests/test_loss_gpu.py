@@ -122,3 +122,94 @@ def test_ensemble_aggregate_golden(ops):
     m, a, e = Fn.ensemble_aggregate(out[:, :, :1], out[:, :, 1:])
     mr, ar, er = O.compute_uncertainties(out[:, :, :1].cpu(), out[:, :, 1:].cpu())
     assert torch.allclose(m.cpu(), mr, atol=1e-6) and torch.allclose(a.cpu(), ar, rtol=1e-5) and torch.allclose(e.cpu(), er, rtol=1e-4, atol=1e-6)
+
+
+def test_fused_regression_metrics_match_torch_formulas():
+    """r2 / mae / mse / rmse of (mu, y) from the fused loss pass (reference mimo/metrics.py:22-34 computes them with four
+    torchmetrics reductions per step) against the plain torch formulas in fp64; with a mask (which must not enter) and a gather."""
+    from mimo_unet_b200 import functional as Fn
+    torch.manual_seed(11)
+    B, S, H, W = 6, 3, 37, 45
+    out = torch.randn(B, S, 2, H, W, device="cuda", requires_grad=True)
+    y = torch.rand(B, 1, H, W, device="cuda") * 3 + 0.5
+    mask = (torch.rand(B, 1, H, W, device="cuda") > 0.3).float()
+    gather = torch.stack([torch.randperm(B, device="cuda") for _ in range(S)])
+    total, loss, weights, m = Fn.laplace_train_loss(out, y, mask=mask, gather=gather, with_metrics=True)
+    total.backward()
+    yt = torch.stack([y[g] for g in gather], dim=1).double()        # [B,S,1,H,W]
+    mu = out.detach()[:, :, :1].double()
+    e = mu - yt
+    mse = (e * e).mean()
+    ref = {"mae": e.abs().mean(), "mse": mse, "rmse": mse.sqrt(), "r2": 1 - (e * e).sum() / ((yt - yt.mean()) ** 2).sum()}
+    assert list(m.keys()) == ["r2", "mae", "mse", "rmse"]           # the reference's logging order
+    for k, v in ref.items():
+        assert abs(float(m[k]) - float(v)) <= 1e-5 * max(1.0, abs(float(v))), (k, float(m[k]), float(v))
+    # the loss itself is unchanged by the extra accumulators
+    total2, loss2, _ = Fn.laplace_train_loss(out.detach(), y, mask=mask, gather=gather)
+    assert torch.equal(loss, loss2) and torch.equal(total.detach(), total2)
+
+
+def test_gaussian_nll_vs_oracle_values_and_gradients():
+    """GaussianNLL on the GPU (same kernels as the Laplace loss, Gaussian element math) against the oracle's autograd, incl. the
+    clamp edge cases (the clamp changes the value the loss is evaluated at but is invisible to autograd), masks, mean and
+    elementwise reductions, and the fused training pass (per-subnetwork means + gradient seed)."""
+    from mimo.losses import GaussianNLL, UncertaintyLoss
+    from mimo_unet_b200 import functional as Fn
+    torch.manual_seed(4)
+    crit = UncertaintyLoss.from_name("gaussian_nll")
+    assert isinstance(crit, GaussianNLL)
+    mu = torch.randn(4, 3, 1, 9, 11, device="cuda", requires_grad=True)
+    lv = (torch.randn(4, 3, 1, 9, 11, device="cuda") * 5).requires_grad_(True)
+    with torch.no_grad():
+        lv.view(-1)[:5] = torch.tensor([-20.0, -11.6, 0.0, 6.9, 10.0], device="cuda")
+    y = torch.randn(4, 3, 1, 9, 11, device="cuda")
+    mask = (torch.rand(4, 3, 1, 9, 11, device="cuda") > 0.25).float()
+    for reduce_mean in (False, True):
+        mu_o, lv_o = mu.detach().double().requires_grad_(True), lv.detach().double().requires_grad_(True)
+        ref = O.gaussian_nll_elementwise(mu_o, lv_o, y.double(), mask.double())
+        got = crit(mu, lv, y, mask=mask, reduce_mean=reduce_mean)
+        if reduce_mean:
+            ref = ref.mean()
+        assert rel_l2(got.detach(), ref.detach()) <= 1e-5
+        mu.grad = lv.grad = None
+        (got.sum() * 1.5).backward()
+        (ref.sum() * 1.5).backward()
+        assert rel_l2(mu.grad, mu_o.grad) <= 1e-5 and rel_l2(lv.grad, lv_o.grad) <= 1e-5
+    # fused training pass with the Gaussian element math
+    out = torch.randn(4, 3, 2, 9, 11, device="cuda", requires_grad=True)
+    total, loss, w = Fn.laplace_train_loss(out, y, gaussian=True)
+    total.backward()
+    o2 = out.detach().double().requires_grad_(True)
+    l_ref = O.gaussian_nll_elementwise(o2[:, :, :1], o2[:, :, 1:], y.double()).mean(dim=(0, 2, 3, 4))
+    l_ref.mean().backward()
+    assert rel_l2(loss, l_ref.detach()) <= 1e-5 and rel_l2(out.grad, o2.grad) <= 1e-5
+
+
+def test_evidential_head_and_loss_vs_oracle():
+    """Softplus head (evidential_unet.py:85-96) and EvidentialLoss (losses.py:195-271) fused kernels against the oracle in fp64:
+    values, gradients w.r.t. the raw network output, mask, mean / elementwise."""
+    from mimo.losses import EvidentialLoss
+    from mimo_unet_b200 import functional as Fn
+    torch.manual_seed(5)
+    raw = (torch.randn(3, 4, 13, 17, device="cuda") * 1.5).requires_grad_(True)
+    with torch.no_grad():
+        raw[0, 1, 0, :3] = torch.tensor([25.0, -15.0, 0.0], device="cuda")   # softplus threshold / tiny evidence
+    y = torch.rand(3, 1, 13, 17, device="cuda")
+    mask = (torch.rand(3, 1, 13, 17, device="cuda") > 0.3).float()
+    crit = EvidentialLoss(coeff=1.0)
+    for reduce_mean in (False, True):
+        par = Fn.evidential_head(raw)
+        got = crit(par, y, mask=mask, reduce_mean=reduce_mean)
+        r64 = raw.detach().double().requires_grad_(True)
+        p64 = O.evidential_head(r64)
+        ref = O.evidential_loss_elementwise(p64, y.double(), mask.double().squeeze(1))
+        if reduce_mean:
+            ref = ref.mean()
+        assert rel_l2(par.detach(), p64.detach()) <= 1e-6
+        assert rel_l2(got.detach(), ref.detach()) <= 2e-5
+        raw.grad = None
+        got.sum().backward()
+        ref.sum().backward()
+        assert rel_l2(raw.grad, r64.grad) <= 2e-4    # digamma series + fp32 lgamma against fp64
+    assert torch.equal(crit.mode(par), par[:, 0])
+    assert rel_l2(crit.aleatoric_var(par), par[:, 3] / (par[:, 2] - 1)) == 0.0

@@ -142,6 +142,33 @@ def test_oracle_equals_reference_live(S, f, H, W):
 
 
 @needs_ref
+def test_gaussian_and_evidential_oracle_equal_reference_live():
+    """GaussianNLL (losses.py:39-121) and EvidentialLoss (losses.py:195-271): oracle restatement vs the reference classes,
+    values and autograd gradients, including the clamp edge cases of the Gaussian variance."""
+    ref = _refload.load()
+    torch.manual_seed(3)
+    mu = torch.randn(200, requires_grad=True)
+    lv = torch.cat([torch.randn(180) * 4, torch.tensor([-20.0, -11.6, 0.0, 6.9, 10.0] * 4)]).requires_grad_(True)
+    y = torch.randn(200)
+    mask = (torch.rand(200) > 0.3).float()
+    a = ref.losses.GaussianNLL().forward(mu, lv, y, mask=mask, reduce_mean=False)
+    mu2, lv2 = mu.detach().clone().requires_grad_(True), lv.detach().clone().requires_grad_(True)
+    b = O.gaussian_nll_elementwise(mu2, lv2, y, mask)
+    assert torch.allclose(a, b, rtol=1e-6, atol=1e-7)
+    a.sum().backward()
+    b.sum().backward()
+    assert torch.allclose(mu.grad, mu2.grad, rtol=1e-6, atol=1e-7) and torch.allclose(lv.grad, lv2.grad, rtol=1e-5, atol=1e-6)
+    raw = torch.randn(3, 4, 5, 6, requires_grad=True)
+    yy = torch.rand(3, 1, 5, 6)
+    par = O.evidential_head(raw)
+    mu_, logv, loga, logb = torch.unbind(raw, dim=1)
+    sp = torch.nn.Softplus()
+    assert torch.equal(par, torch.stack([mu_, sp(logv), sp(loga) + 1, sp(logb)], dim=1))   # evidential_unet.py:90-96
+    la = ref.losses.EvidentialLoss(coeff=1.0).forward(par, yy, reduce_mean=False)
+    assert torch.allclose(la, O.evidential_loss_elementwise(par, yy), rtol=1e-6, atol=1e-7)
+
+
+@needs_ref
 def test_product_surface_matches_reference_names():
     """state_dict layout and constructor surface of the product module vs the live reference."""
     ref = _refload.load()

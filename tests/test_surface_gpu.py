@@ -262,3 +262,33 @@ def test_center_and_final_dropout_module_surface():
     (p1.mean() + p2.mean()).backward()
     g = m.model.core.down4.conv.double_conv[3].weight.grad
     assert g is not None and torch.isfinite(g).all() and float(g.abs().sum()) > 0
+
+
+def test_evidential_unet_module_steps():
+    """EvidentialUnetModel (reference mimo/models/evidential_unet.py): M = 1, four output channels, softplus head, EvidentialLoss.
+    One training and one validation step run through the CUDA executor and the fused head / loss kernels; the head output equals
+    the oracle's restatement applied to the raw network output, gradients reach every parameter."""
+    from mimo.models.evidential_unet import EvidentialUnetModel
+    torch.manual_seed(0)
+    m = EvidentialUnetModel(3, 4, 8, 0.0, 0.0, 0.0, 0.0, 0.0, weight_decay=0.0, learning_rate=1e-3, seed=1).cuda()
+    m.train()
+    x = torch.rand(3, 3, 32, 48, device="cuda")
+    y = torch.rand(3, 1, 32, 48, device="cuda")
+    out = m(x)
+    assert out.shape == (3, 4, 32, 48)
+    assert float(out[:, 1].min()) > 0 and float(out[:, 2].min()) > 1 and float(out[:, 3].min()) > 0
+    step = m.training_step({"image": x, "label": y}, 0)
+    assert set(step) == {"loss", "label", "preds", "aleatoric_std_map", "err_map", "mask"}
+    step["loss"].backward()
+    for n, p in m.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), n
+    assert float(m.model.decoder.outcs[0].conv.weight.grad.abs().sum()) > 0
+    # loss value against the oracle evaluated on the module's own head output
+    ref = O.evidential_loss_elementwise(out.detach().double(), y.double()).mean()
+    assert abs(float(step["loss"]) - float(ref)) <= 2e-5 * max(1.0, abs(float(ref)))
+    m.eval()
+    val = m.validation_step({"image": x, "label": y}, 0)
+    assert set(val) == {"loss", "label", "preds", "aleatoric_std_map", "epistemic_std_map", "err_map", "mask"}
+    assert torch.isfinite(val["epistemic_std_map"]).all()
+    opt = m.configure_optimizers()
+    assert opt["monitor"] == "val_loss"
