@@ -351,11 +351,7 @@ int plan_slots(int block_n, int sets, int nc, size_t* smem_bytes) {
 
 template <int BN, int SETS>
 int launch_flat(const CUtensorMap& tm_in, const CUtensorMap& tm_w, const FlatParams& p, size_t smem_bytes, int grid, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    MIMO_CUDA(cudaFuncSetAttribute(conv3x3_flat_kernel<BN, SETS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  MIMO_CUDA(cudaFuncSetAttribute(conv3x3_flat_kernel<BN, SETS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));   // per launch: the attribute is per DEVICE, a process-wide "done" flag would skip the other GPUs
   conv3x3_flat_kernel<BN, SETS><<<grid, 64 + 128 * SETS, smem_bytes, stream>>>(tm_in, tm_w, p);
   MIMO_LAUNCH_CHECK();
   return MIMO_OK;

@@ -350,11 +350,7 @@ int conv3x3_flatk_launch(const ActView& in, int mode, const bf16* wpacked, int c
     int rc = encode_tmap_bf16(&tm_w, wpacked, 3, dims, strides, box, 1);
     if (rc) return rc;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    MIMO_CUDA(cudaFuncSetAttribute(conv3x3_flatk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  MIMO_CUDA(cudaFuncSetAttribute(conv3x3_flatk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));   // per launch: the attribute is per DEVICE, a process-wide "done" flag would skip the other GPUs
   const int items = p.n_pairs * p.n_tiles_n;
   const int grid = items < num_sms() ? items : num_sms();
   conv3x3_flatk_kernel<<<grid, kThreads, smem_bytes, stream>>>(tm_a, tm_a2, tm_w, p);

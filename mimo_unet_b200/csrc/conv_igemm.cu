@@ -312,11 +312,7 @@ int conv3x3_launch(const ActView& in, int mode, const bf16* wpacked, int cout, i
     if (rc) return rc;
   }
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    MIMO_CUDA(cudaFuncSetAttribute(conv3x3_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  MIMO_CUDA(cudaFuncSetAttribute(conv3x3_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));   // per launch: the attribute is per DEVICE, a process-wide "done" flag would skip the other GPUs
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   conv3x3_igemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(tm_in, tm_w, p);

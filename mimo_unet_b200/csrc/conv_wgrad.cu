@@ -257,12 +257,8 @@ int conv3x3_wgrad_launch(const ActView& dy, const ActView& x, float* dw, int cin
     if (rc) return rc;
   }
   if (!pre_zeroed) MIMO_CUDA(cudaMemsetAsync(dw, 0, (size_t)9 * p.cout * cin_pitch * sizeof(float), stream));
-  static bool attr_set = false;
   const size_t smem_bytes = (size_t)kStages * kStageBytes + (2 * kStages + 1) * 8 + 16 + 1024;
-  if (!attr_set) {
-    MIMO_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-    attr_set = true;
-  }
+  MIMO_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));   // per device -> per launch
   const int grid = base_items * p.ksplit;
   conv3x3_wgrad_kernel<<<grid, kThreads, smem_bytes, stream>>>(tm_dy, tm_x, p);
   MIMO_LAUNCH_CHECK();

@@ -246,11 +246,7 @@ int conv3x3_wgrad_flat_launch(const ActView& dy, const ActView& x, float* dw, in
     if (rc) return rc;
   }
   if (!pre_zeroed) MIMO_CUDA(cudaMemsetAsync(dw, 0, (size_t)9 * p.cout * cin_pitch * sizeof(float), stream));
-  static bool attr_set = false;
-  if (!attr_set) {
-    MIMO_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  MIMO_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));   // per launch: the attribute is per DEVICE, a process-wide "done" flag would skip the other GPUs
   conv3x3_wgrad_flat_kernel<<<grid, kThreads, smem_bytes, stream>>>(tm_dy, tm_x, p);
   MIMO_LAUNCH_CHECK();
   return MIMO_OK;

@@ -303,11 +303,7 @@ int conv3x3_wgrad_flatk_launch(const ActView& dy, const ActView& x, float* dw, i
   p.ko = getenv("MIMO_WGK_KO") ? atoi(getenv("MIMO_WGK_KO")) : 0;
   if (!(p.ko & 2) && !pre_zeroed) MIMO_CUDA(cudaMemsetAsync(dw, 0, (size_t)9 * p.cout * cin_pitch * sizeof(float), stream));
   const size_t smem_bytes = (size_t)kStages * kStageBytes + (2 * kStages + 2) * 8 + 16 + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    MIMO_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_flatk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-    attr_set = true;
-  }
+  MIMO_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_flatk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));   // per launch: the attribute is per DEVICE, a process-wide "done" flag would skip the other GPUs
   const int grid = plan_grid(p, num_sms());
   conv3x3_wgrad_flatk_kernel<<<grid, kThreads, smem_bytes, stream>>>(tm_dy, tm_x, tm_x2, p);
   MIMO_LAUNCH_CHECK();

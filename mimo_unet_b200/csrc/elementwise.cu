@@ -1412,12 +1412,9 @@ int bn_bwd_launch(const ActView& G, const bf16* y, int ycp, const float* scale, 
       a.inv_count = 1.f / (float)((long long)G.N * G.H * G.W); a.training = training;
       a.part = part; a.dy = dy;
       const size_t smem = (size_t)kBulkStages * (kBulkStageCap + a.capG) + kBulkStages * 8 + 64;
-      static bool attr = false;
-      if (!attr) {
-        MIMO_CUDA(cudaFuncSetAttribute(bn_bwd_bulk_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        MIMO_CUDA(cudaFuncSetAttribute(bn_bwd_bulk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr = true;
-      }
+      // per launch (cheap): the attribute is per DEVICE, a process-wide "done" flag would skip the other GPUs of the process
+      MIMO_CUDA(cudaFuncSetAttribute(bn_bwd_bulk_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      MIMO_CUDA(cudaFuncSetAttribute(bn_bwd_bulk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       int grid = (smem <= 112 * 1024 ? 2 : 1) * num_sms();
       if (grid > a.n_chunks) grid = a.n_chunks;
       if (grid > bn_bwd_parts(C)) grid = bn_bwd_parts(C);

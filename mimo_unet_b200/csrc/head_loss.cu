@@ -861,8 +861,7 @@ int head_bwd_launch(const ActView& f, const float* W, int K, const float* dout, 
     }
   }
   const size_t smem = ((size_t)K * f.C + (size_t)K * kBlock + (size_t)kBlock * (f.C + 1)) * sizeof(float);
-  static bool attr = false;
-  if (!attr) { MIMO_CUDA(cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr = true; }
+  MIMO_CUDA(cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));   // per device -> per launch
   MIMO_CHECK(smem <= 160 * 1024, MIMO_ERR_ARG, "head_bwd: feature count too large for shared memory");
   head_bwd_kernel<<<nparts, kBlock, smem, st>>>(f, W, K, dout, out_bstride, grad_scale, G, part);
   MIMO_LAUNCH_CHECK();

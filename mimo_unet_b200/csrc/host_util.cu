@@ -27,7 +27,7 @@ const char* conv_kernel_name(int id) {
 }
 
 int num_sms() {
-  static int sms = 0;
+  static int sms = 0;   // every GPU of a node is the same part: the count of the first device queried serves them all
   if (sms == 0) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)

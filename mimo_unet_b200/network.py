@@ -226,14 +226,20 @@ class NetworkRuntime:
         # BatchNorm mode follows the BN modules (all share the module's mode; MC-dropout keeps BN in eval)
         bn_training = net.encoder.in_convs[0].double_conv[1].training
         masks = self._dropout_masks(plan, B, dev)
-        self._elementwise_dropout(plan, B, H, W, dev)
+        with torch.cuda.device(dev):
+            self._elementwise_dropout(plan, B, H, W, dev)
         g = None if gather is None else gather.to(device=dev, dtype=torch.int64).contiguous()
-        plan.forward(x, out, bn_training, gather=g, drop_masks=masks)
+        with torch.cuda.device(dev):   # streams and launches follow the TENSORS' device, not whatever device is current
+            plan.forward(x, out, bn_training, gather=g, drop_masks=masks)
         self._forward_token += 1
         self.last_launches = (plan.last_launches, self.last_launches[1])
         return out, plan
 
     def _backward_impl(self, plan: UNetPlan, dout: torch.Tensor, need_dx: bool, x_shape):
+        with torch.cuda.device(dout.device):
+            return self._backward_on_device(plan, dout, need_dx, x_shape)
+
+    def _backward_on_device(self, plan: UNetPlan, dout: torch.Tensor, need_dx: bool, x_shape):
         state = _state_entries(self.net)
         dout = dout.contiguous().float()
         dx = torch.empty(x_shape, dtype=torch.float32, device=dout.device) if need_dx else None
