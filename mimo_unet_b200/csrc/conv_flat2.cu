@@ -57,7 +57,7 @@ struct Flat2Params {
   int groups;          // 16-byte pieces per pixel in global memory (cpitch / 8)
   int c_valid;         // channels of the view; pieces holding channels >= c_valid are masked to zero in shared memory
   const bf16* in;      // first channel of the view at flattened position 0
-  int ko;              // diagnostic knock-outs (env MIMO_FLAT2_KO): 1 no global stores, 2 no loads, 4 no MMAs
+  int ko;              // diagnostic knock-outs (env MIMO_FLAT2_KO): 1 no global stores, 2 no loads, 4 no MMAs, 8 no re-layout
   long long* trace;    // diagnostic (env MIMO_FLAT2_TRACE): CTA 0 records clock64() of its pipeline events, [4 roles][64][4]
   EpiArgs epi;
 };
@@ -158,11 +158,11 @@ conv3x3_flat2_kernel(const __grid_constant__ CUtensorMap tmap_w, const Flat2Para
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < S; ++s) {
-        mbar_init(&full_bar[s], 2);   // one re-layout warp per CTA per chunk
+        mbar_init(&full_bar[s], 4);   // slot s of an even/odd chunk PAIR (index s/2 used): 2 chunks x 2 CTAs
       }
       for (int a = 0; a < kAcc; ++a) {
         mbar_init(&tmem_full[a], 1);
-        mbar_init(&tmem_empty[a], 8);   // 4 warps of the draining set in each CTA
+        mbar_init(&tmem_empty[a], 16);  // accumulator PAIR (index a/2 used): 2 tiles x 4 warps x 2 CTAs
       }
       for (int a = 0; a < p.st_slots; ++a) {
         mbar_init(&st_full[a], 1);
@@ -189,7 +189,7 @@ conv3x3_flat2_kernel(const __grid_constant__ CUtensorMap tmap_w, const Flat2Para
     }
     __syncwarp();
     // ===================== bulk-copy producer: chunk c = rows [128 (t_begin + c) + origin, +128) of the pixel list =====================
-    const int n_chunks = n_tiles + p.nc - 1;
+    const int n_chunks = (n_tiles + p.nc - 1 + 1) & ~1;
     const size_t row_bytes = (size_t)p.groups * 16;
     const uint8_t* gbase = reinterpret_cast<const uint8_t*>(p.in);
     long long row0 = (long long)t_begin * kBlockM + p.origin;
@@ -229,47 +229,56 @@ conv3x3_flat2_kernel(const __grid_constant__ CUtensorMap tmap_w, const Flat2Para
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) tap_row[kh * 3 + kw] = (uint32_t)(kh * p.wb + kw);
       MBAR_WAIT(b_full, 0);
-      int waited = 0;          // chunks whose arrival has been observed
-      int wslot = 0;
-      uint32_t wphase = 0;
+      // Tiles are multiplied in PAIRS (2j, 2j+1): per pair ONE wait for the two accumulators, ONE wait per chunk pair and ONE
+      // commit. An mbarrier wait costs the issuing warp 120..200 cycles even when the phase is long complete, and the issuing
+      // thread blocks while the tensor queue is full, so per-tile waits (350 cycles) sat serially next to the 700 MMA cycles.
+      int waited = 0;          // chunk PAIRS whose arrival has been observed
       int slot = 0;            // ring slot of chunk i (the first chunk of tile i)
-      for (int i = 0; i < n_tiles; ++i) {
-        const uint32_t acc = (uint32_t)i % kAcc;
+      for (int i = 0; i < n_tiles; i += 2) {
+        const uint32_t ap = ((uint32_t)i >> 1) % (kAcc / 2);          // accumulator pair
+        const uint32_t ause = ((uint32_t)i >> 1) / (kAcc / 2);
         const bool tr = p.trace && blockIdx.x == 0 && i < 64 && lane == 0;
         long long* trow = p.trace + (1 * 64 + i) * 4;
         if (tr) trow[0] = clock64();
-        MBAR_WAIT(&tmem_empty[acc], (((uint32_t)i / kAcc) & 1u) ^ 1u);
+        MBAR_WAIT(&tmem_empty[2 * ap], (ause & 1u) ^ 1u);
         if (tr) trow[1] = clock64();
-        while (waited < i + p.nc) {
-          MBAR_WAIT(&full_bar[wslot], wphase);
+        // tile i + 1 reads chunks up to i + nc: chunk pairs up to (i + nc) / 2
+        while (waited <= (i + p.nc) / 2) {
+          const int ps = waited % (S / 2);
+          MBAR_WAIT(&full_bar[2 * ps], (uint32_t)(waited / (S / 2)) & 1u);
           ++waited;
-          if (++wslot == S) { wslot = 0; wphase ^= 1; }
         }
         if (tr) trow[2] = clock64();
         tc_fence_after();
-        const uint32_t d_addr = tmem_base + acc * BN;
-        const uint32_t base_row = (uint32_t)slot * kBlockM;
         if (elect_one()) {
-          if (!no_mma) {
 #pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
-              uint32_t r = base_row + tap_row[tap];
-              if (r >= ring_rows) r -= ring_rows;          // windows that START past the ring end wrap; windows that only
-              const uint32_t a_lo = a_lo0 + r * 8;         // END past it continue into the mirror of slot 0
+          for (int t = 0; t < 2; ++t) {
+            const uint32_t d_addr = tmem_base + (2 * ap + (uint32_t)t) * BN;
+            uint32_t s0 = (uint32_t)slot + (uint32_t)t;
+            if (s0 >= (uint32_t)S) s0 -= (uint32_t)S;
+            const uint32_t base_row = s0 * kBlockM;
+            if (!no_mma) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                if ((uint32_t)k < ks)
-                  umma2_bf16_w(d_addr, a_lo + k * 2, hi, b_lo0 + ((tap * b_tap_bytes + k * 32) >> 4), hi, idesc, (tap | k) != 0);
+              for (int tap = 0; tap < 9; ++tap) {
+                uint32_t r = base_row + tap_row[tap];
+                if (r >= ring_rows) r -= ring_rows;          // windows that START past the ring end wrap; windows that only
+                const uint32_t a_lo = a_lo0 + r * 8;         // END past it continue into the mirror of slot 0
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  if ((uint32_t)k < ks)
+                    umma2_bf16_w(d_addr, a_lo + k * 2, hi, b_lo0 + ((tap * b_tap_bytes + k * 32) >> 4), hi, idesc, (tap | k) != 0);
+                }
               }
             }
           }
-          // ONE commit per tile: accumulator complete -> both epilogues; it also tells both CTAs' re-layout warps that chunk i
-          // (the oldest the tile read) is dead
-          umma_commit2_mc(&tmem_full[acc], 3);
+          // ONE commit per tile pair: both accumulators complete -> both epilogue sets of both CTAs; it also tells the re-layout
+          // warps that chunks i and i + 1 are dead
+          umma_commit2_mc(&tmem_full[2 * ap], 3);
         }
         __syncwarp();
         if (tr) trow[3] = clock64();
-        if (++slot == S) slot = 0;
+        slot += 2;
+        if (slot >= S) slot -= S;
       }
     }
   } else if (warp < 2 + 4 * SETS) {
@@ -304,13 +313,14 @@ conv3x3_flat2_kernel(const __grid_constant__ CUtensorMap tmap_w, const Flat2Para
       dw = rem - dh * p.wb;
     }
     for (int i = set; i < n_tiles; i += SETS) {
-      const uint32_t acc = (uint32_t)i % kAcc;
+      const uint32_t acc = (uint32_t)i % kAcc;                      // accumulator of tile i; barriers belong to the PAIR
+      const uint32_t ap = ((uint32_t)i >> 1) % (kAcc / 2), ause = ((uint32_t)i >> 1) / (kAcc / 2);
       const bool valid = pn < p.n_img && ph < p.out_h && pw < p.out_w && !(p.ko & 1);
       const size_t my_pix = (size_t)(pn * p.out_h + ph) * p.out_w + pw;
       const bool tr = p.trace && blockIdx.x == 0 && i < 64 && (et & 127) == 0;
       long long* trow = p.trace + (2 * 64 + i) * 4;
       if (tr) trow[0] = clock64();
-      MBAR_WAIT(&tmem_full[acc], ((uint32_t)i / kAcc) & 1u);
+      MBAR_WAIT(&tmem_full[2 * ap], ause & 1u);
       if (tr) trow[1] = clock64();
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
@@ -321,7 +331,7 @@ conv3x3_flat2_kernel(const __grid_constant__ CUtensorMap tmap_w, const Flat2Para
       // TMEM drained -> hand the accumulator back to the leader's MMA warp before doing the math / stores
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(tempty0 + acc * 8u);
+      if (lane == 0) mbar_arrive_cluster(tempty0 + 2u * ap * 8u);
       if (tr) trow[2] = clock64();
       if (valid) {
         bf16* dst = e.out + my_pix * e.out_cpitch;
@@ -393,7 +403,7 @@ conv3x3_flat2_kernel(const __grid_constant__ CUtensorMap tmap_w, const Flat2Para
     // fence, remote arrive) of the warps overlap
     const int lw = warp - (2 + 4 * SETS);
     const int G = p.groups;
-    const int n_chunks = n_tiles + p.nc - 1;
+    const int n_chunks = (n_tiles + p.nc - 1 + 1) & ~1;   // whole chunk pairs (a trailing chunk past the range is zero-filled)
     const uint32_t full0 = mapa_shared(smem_u32(full_bar), 0);
     // pieces that hold channels past the view (pad channels / garbage in memory) are zeroed, the boundary piece is masked
     const int last_g = (p.c_valid - 1) >> 3;                   // last piece with valid channels
@@ -407,9 +417,9 @@ conv3x3_flat2_kernel(const __grid_constant__ CUtensorMap tmap_w, const Flat2Para
       MBAR_WAIT(&st_full[ss], (uint32_t)(c / p.st_slots) & 1u);
       if (c >= S) {
         // the chunk that lived in this slot (c - S) is dead once tile c - S has been multiplied: its accumulator-full barrier
-        // (at most S - nc < kAcc tiles can have completed past it, so the parity is unambiguous)
-        const int t = c - S;
-        MBAR_WAIT(&tmem_full[t % kAcc], (uint32_t)(t / kAcc) & 1u);
+        // (fewer than kAcc / 2 tile pairs can have completed past it, so the parity is unambiguous)
+        const int tp = (c - S) >> 1;   // tile pair of tile c - S
+        MBAR_WAIT(&tmem_full[2 * (tp % (kAcc / 2))], (uint32_t)(tp / (kAcc / 2)) & 1u);
       }
       if (tr) trow[0] = clock64();   // (trace: waits done)
       const uint32_t src = smem_u32(smem_st) + (uint32_t)ss * (uint32_t)p.st_bytes;
@@ -417,6 +427,7 @@ conv3x3_flat2_kernel(const __grid_constant__ CUtensorMap tmap_w, const Flat2Para
       const uint32_t mirror = slot == 0 ? smem_u32(smem_a) + (uint32_t)S * kChunkBytes : 0u;   // mirror of slot 0
       const bool all_in = row0 >= 0 && row0 + kBlockM <= p.total_pos && !(p.ko & 2);
       const long long tp = (p.ko & 2) ? 0 : p.total_pos;
+      if (!(p.ko & 8))   // (knock-out 8: no re-layout traffic at all)
       switch (G) {
         case 1: relayout_chunk<1>(src, dst, mirror, lane, last_g, tail_mask, all_in, row0, tp); break;
         case 2: relayout_chunk<2>(src, dst, mirror, lane, last_g, tail_mask, all_in, row0, tp); break;
@@ -432,7 +443,7 @@ conv3x3_flat2_kernel(const __grid_constant__ CUtensorMap tmap_w, const Flat2Para
       if (tr) trow[2] = clock64();   // (trace: fence done)
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive_cluster(full0 + (uint32_t)slot * 8u);
+        mbar_arrive_cluster(full0 + (uint32_t)(slot & ~1) * 8u);   // the pair's barrier lives at the even slot
         mbar_arrive(&st_empty[ss]);
       }
       if (tr) trow[3] = clock64();
@@ -458,11 +469,12 @@ bool plan_smem(int block_n, int sets, int nc, int st_bytes, int* slots, int* st_
   const int b_bytes = (9 * (block_n / 2) * 128 + 1023) & ~1023;
   const int fixed = b_bytes + 8 * sets * block_n * 4 + (2 * kMaxSlots + 2 * kMaxStage + 2 * kAcc + 1) * 8 + 16 + 64 + 1024 /*alignment slack*/;
   const int budget = 227 * 1024 - fixed;
-  int S = nc + 3;
+  static const int s_extra = env_int("MIMO_FLAT2_SLACK", 4);
+  int S = (nc + s_extra + 1) & ~1;   // even: the slots are handed over in pairs; window of a tile pair (nc + 1) + prefetch
   if (S > kMaxSlots) S = kMaxSlots;
-  if (S < nc + 1) return false;
+  if (S < nc + 2) return false;
   int ns = (budget - (S + 1) * kChunkBytes) / st_bytes;
-  while (ns < 3 && S > nc + 1) { --S; ns = (budget - (S + 1) * kChunkBytes) / st_bytes; }
+  while (ns < 3 && S - 2 >= nc + 2) { S -= 2; ns = (budget - (S + 1) * kChunkBytes) / st_bytes; }
   if (ns < 2) return false;
   if (ns > kMaxStage) ns = kMaxStage;
   *slots = S;
@@ -512,7 +524,7 @@ int conv3x3_flat2_launch(const ActView& in, int mode, const bf16* wpacked, int c
   const int m_tiles = (int)ceil_div_ll(p.total_pos, kBlockM);
   int grid = num_sms() & ~1;
   if (grid > round_up(m_tiles, 2)) grid = round_up(m_tiles, 2);
-  p.tiles_per_cta = ceil_div(m_tiles, grid);
+  p.tiles_per_cta = round_up(ceil_div(m_tiles, grid), 2);   // tiles are multiplied in pairs
   grid = round_up(ceil_div(m_tiles, p.tiles_per_cta), 2);
   p.nc = ceil_div(2 * p.wb + 130, 128);
   p.k_steps = ceil_div(in.C, 16);
