@@ -248,6 +248,13 @@ int mimo_unet_backward(mimo_unet_plan_t* plan, const float* dout, const float* g
  * to the decoder features in front of head s; NULL entries = no dropout. Masks stay caller-owned until backward has run. */
 int mimo_unet_set_elementwise_dropout(mimo_unet_plan_t* plan, const void* center_keep, float center_scale,
                                       const void* const* final_keep, float final_scale);
+/* Inference mode of the following forward calls with training == 0 (EnsembleModule.forward, mimo/models/ensemble.py:76-115;
+ * validation_step, mimo/models/mimo_unet.py:146-183, under no_grad): with on != 0 the eval-mode BatchNorm affine, the ReLU and
+ * the Dropout2d factors of every DoubleConv (mimo/models/mimo_components/components.py:23-29) are applied in the convolution
+ * epilogues, which write straight into the consumer's haloed buffer; no raw convolution output is kept, so
+ * mimo_unet_backward is refused after such a forward. Off by default (eval-mode forward + backward, e.g. FGSM in
+ * scripts/test/test_nyuv2_depth.py:26-90, keeps working). */
+int mimo_unet_set_inference_fusion(mimo_unet_plan_t* plan, int on);
 /* Overlap hook for the data-parallel gradient all-reduce: events[4] are caller-owned cudaEvent_t (or NULL
  * to disable). mimo_unet_backward records events[k] on its stream as soon as the parameter gradients of stage k are
  * final: 0 = decoders + heads, 1 = core up path, 2 = core down path, 3 = encoders (end of backward). The state entries

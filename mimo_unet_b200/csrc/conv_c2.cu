@@ -228,14 +228,17 @@ conv3x3_c2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const long long pos = (((long long)mi * 2 + rank) * T + t) * kBlockM + row;
         bool valid = false;
         size_t my_pix = 0;
+        unsigned img = 0;
         if (pos < p.total_pos) {
           const unsigned up = (unsigned)pos;
           const unsigned ni = up / (unsigned)p.img_pix;
           const unsigned rem = up - ni * (unsigned)p.img_pix;
           const unsigned hp = rem / (unsigned)p.wb, wp = rem - hp * (unsigned)p.wb;
           valid = (int)hp < p.out_h && (int)wp < p.out_w;
-          my_pix = ((size_t)ni * p.out_h + hp) * p.out_w + wp;
+          img = ni;
+          my_pix = e.halo ? ((size_t)ni * (p.out_h + 2) + hp + 1) * (p.out_w + 2) + wp + 1 : ((size_t)ni * p.out_h + hp) * p.out_w + wp;
         }
+        const float* drow = (e.drop != nullptr && valid) ? e.drop + (size_t)img * e.cout : nullptr;
         const float vmask = valid ? 1.f : 0.f;
         bf16* dst = e.out + my_pix * e.out_cpitch + co0;
         const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (buf * (uint32_t)T + (uint32_t)t) * (uint32_t)p.block_n;
@@ -248,18 +251,38 @@ conv3x3_c2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           } else {
             tmem_ld16(t_addr + j * 16, v);
           }
-          if (e.bias != nullptr) {
+          if (e.scale != nullptr) {
+            // vec4 is set by the launcher when scale / shift hold round_up(cout, 16) floats per n-tile column range (the
+            // executor's BatchNorm vectors are padded with zeros up to the channel pitch) and are 16-byte aligned
+            const int c0 = co0 + j * 16;
+            if (e.relu & 2) {
+#pragma unroll
+              for (int i = 0; i < 16; i += 4) {
+                const float4 sc = __ldg(reinterpret_cast<const float4*>(e.scale + c0 + i));
+                const float4 sh = __ldg(reinterpret_cast<const float4*>(e.bias + c0 + i));
+                v[i] = fmaf(v[i], sc.x, sh.x); v[i + 1] = fmaf(v[i + 1], sc.y, sh.y);
+                v[i + 2] = fmaf(v[i + 2], sc.z, sh.z); v[i + 3] = fmaf(v[i + 3], sc.w, sh.w);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = (c0 + i < e.cout) ? fmaf(v[i], __ldg(e.scale + c0 + i), __ldg(e.bias + c0 + i)) : 0.f;
+            }
+          } else if (e.bias != nullptr) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] += (co0 + j * 16 + i < e.cout) ? __ldg(e.bias + co0 + j * 16 + i) : 0.f;
           }
-          if (e.relu) {
+          if (e.relu & 1) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
           }
+          if (drow != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] *= (co0 + j * 16 + i < e.cout) ? __ldg(drow + co0 + j * 16 + i) : 0.f;
+          }
           const uint4 lo = pack8(v), hi8 = pack8(v + 8);
           if (valid && !(p.ko & 16)) {
-            if (co0 + j * 16 < e.out_cpitch) *reinterpret_cast<uint4*>(dst + j * 16) = lo;
-            if (co0 + j * 16 + 8 < e.out_cpitch) *reinterpret_cast<uint4*>(dst + j * 16 + 8) = hi8;
+            if (co0 + j * 16 < e.out_cmax) *reinterpret_cast<uint4*>(dst + j * 16) = lo;
+            if (co0 + j * 16 + 8 < e.out_cmax) *reinterpret_cast<uint4*>(dst + j * 16 + 8) = hi8;
           }
           if (stats) {
             float f[16];
@@ -364,7 +387,7 @@ bool conv3x3_c2_ok(const ActView& in, int mode, int cout) {
 }
 
 int conv3x3_c2_launch(const ActView& in, int mode, const bf16* wpacked, int cout, int cin_pitch, bf16* out, int out_cpitch,
-                      float* stat_sum, float* stat_sq, const float* bias, int relu, cudaStream_t stream) {
+                      float* stat_sum, float* stat_sq, const float* bias, int relu, cudaStream_t stream, const ConvFuse* fuse) {
   note_kernel(7);
   C2Params p{};
   p.wb = in.wb();
@@ -412,8 +435,12 @@ int conv3x3_c2_launch(const ActView& in, int mode, const bf16* wpacked, int cout
   p.epi.out = out;
   p.epi.stat_sum = stat_sum;
   p.epi.stat_sq = stat_sq;
-  p.epi.bias = bias;
-  p.epi.relu = relu;
+  p.epi.bias = fuse ? fuse->shift : bias;
+  p.epi.relu = fuse ? ((fuse->relu ? 1 : 0) | 2) : relu;   // bit 1: fused affine vectors are padded / aligned for 16-byte loads
+  p.epi.scale = fuse ? fuse->scale : nullptr;
+  p.epi.drop = fuse ? fuse->drop : nullptr;
+  p.epi.halo = fuse ? fuse->halo : 0;
+  p.epi.out_cmax = fuse ? round_up(cout, 8) : out_cpitch;
   MIMO_CHECK((p.n_tiles_n - 1) * p.block_n < out_cpitch, MIMO_ERR_ARG, "conv3x3_c2: n-tiling exceeds out_cpitch");
 
   CUtensorMap tm_a, tm_a2, tm_w;

@@ -17,8 +17,22 @@ struct EpiArgs {
   bf16* out;        // [pixels][out_cpitch]
   float* stat_sum;  // [stat_rows][out_cpitch] or nullptr
   float* stat_sq;
-  const float* bias;  // optional per-cout bias (eval path) or nullptr
+  const float* bias;  // optional per-cout bias (eval path) or nullptr; with `scale` it is the shift of v * scale + bias
   int relu;
+  // ---- fused inference epilogue (eval-mode BatchNorm folded into the conv: v * scale[c] + bias[c] -> ReLU -> Dropout2d) ----
+  const float* scale; // optional per-cout scale
+  const float* drop;  // optional [N][cout] Dropout2d keep/scale factors (MC dropout), applied after the ReLU
+  int halo;           // 1: `out` is the interior of a haloed [N][H+2][W+2] buffer (the consumer's conv input); 0: dense [N][H][W]
+  int out_cmax;       // channels that may be written starting at `out` (multiple of 8; 0 = out_cpitch)
+};
+
+// what a launcher needs to know to fuse the eval-mode BatchNorm / ReLU / Dropout2d into the conv epilogue
+struct ConvFuse {
+  const float* scale;
+  const float* shift;
+  const float* drop;
+  int relu;
+  int halo;
 };
 
 // shared-memory scratch of the epilogue warps

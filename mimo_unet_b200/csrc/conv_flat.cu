@@ -215,7 +215,7 @@ conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
     const int row = q * 32 + lane;
     const int et = threadIdx.x - 64;    // 0 .. 128*SETS-1
     const EpiArgs& e = p.epi;
-    const bool stats = e.stat_sum != nullptr;
+    const bool stats = e.stat_sum != nullptr && e.scale == nullptr;
     float ssum[BN], ssq[BN];
 #pragma unroll
     for (int i = 0; i < BN; ++i) { ssum[i] = 0.f; ssq[i] = 0.f; }
@@ -237,10 +237,20 @@ conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
       dh = rem / p.wb;
       dw = rem - dh * p.wb;
     }
+    // fused inference epilogue: the per-channel affine lives in the registers the (unused) statistics would occupy
+    const bool affine = e.scale != nullptr;
+    if (affine) {
+#pragma unroll
+      for (int i = 0; i < BN; ++i) {
+        ssum[i] = i < e.cout ? __ldg(e.scale + i) : 0.f;
+        ssq[i] = i < e.cout ? __ldg(e.bias + i) : 0.f;
+      }
+    }
     for (int i = set; i < n_tiles; i += SETS) {
       const uint32_t acc = (uint32_t)i & 1u;
       const bool valid = pn < p.n_img && ph < p.out_h && pw < p.out_w && !(p.ko & 1);
-      const size_t my_pix = (size_t)(pn * p.out_h + ph) * p.out_w + pw;
+      const size_t my_pix = e.halo ? ((size_t)pn * (p.out_h + 2) + ph + 1) * (p.out_w + 2) + pw + 1 : (size_t)(pn * p.out_h + ph) * p.out_w + pw;
+      const float* drow = (e.drop != nullptr && valid) ? e.drop + (size_t)pn * e.cout : nullptr;
       const bool tr = p.trace && blockIdx.x == 0 && i < 64 && (et & 127) == 0;
       long long* trow = p.trace + (2 * 64 + i) * 4;
       if (tr) trow[0] = clock64();
@@ -264,18 +274,25 @@ conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
           float v[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[c + j]);
-          if (e.bias != nullptr) {
+          if (affine) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], ssum[c + j], ssq[c + j]);
+          } else if (e.bias != nullptr) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] += (c + j < e.cout) ? __ldg(e.bias + c + j) : 0.f;
           }
-          if (e.relu) {
+          if (e.relu & 1) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (drow != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] *= (c + j < e.cout) ? __ldg(drow + c + j) : 0.f;
           }
           bf16x8 o;
 #pragma unroll
           for (int j = 0; j < 8; ++j) o.v[j] = __float2bfloat16_rn(v[j]);
-          if (c < e.out_cpitch) *reinterpret_cast<bf16x8*>(dst + c) = o;
+          if (c < e.out_cmax) *reinterpret_cast<bf16x8*>(dst + c) = o;
           if (stats) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -374,7 +391,7 @@ bool conv3x3_flat_ok(const ActView& in, int mode, int cout) {
 }
 
 int conv3x3_flat_launch(const ActView& in, int mode, const bf16* wpacked, int cout, int cin_pitch, bf16* out, int out_cpitch,
-                        float* stat_sum, float* stat_sq, const float* bias, int relu, cudaStream_t stream) {
+                        float* stat_sum, float* stat_sq, const float* bias, int relu, cudaStream_t stream, const ConvFuse* fuse) {
   note_kernel(1);
   FlatParams p{};
   const int block_n = round_up(cout, 16);
@@ -410,8 +427,12 @@ int conv3x3_flat_launch(const ActView& in, int mode, const bf16* wpacked, int co
   p.epi.out = out;
   p.epi.stat_sum = stat_sum;
   p.epi.stat_sq = stat_sq;
-  p.epi.bias = bias;
-  p.epi.relu = relu;
+  p.epi.bias = fuse ? fuse->shift : bias;
+  p.epi.relu = fuse ? ((fuse->relu ? 1 : 0) | 2) : relu;   // bit 1: fused affine vectors are padded / aligned for 16-byte loads
+  p.epi.scale = fuse ? fuse->scale : nullptr;
+  p.epi.drop = fuse ? fuse->drop : nullptr;
+  p.epi.halo = fuse ? fuse->halo : 0;
+  p.epi.out_cmax = fuse ? round_up(cout, 8) : out_cpitch;
   {
     static bool told = false;
     if (!told && p.ko) {

@@ -231,8 +231,13 @@ int conv3x3_stat_rows() { return num_sms(); }
 //                            mode 1 (dgrad): pad == 0, output domain = (in.H+2) x (in.W+2)
 // wpacked : bf16 [9][cout][cin_pitch] (cin contiguous), cin_pitch multiple of 8
 // out     : bf16 [N][out_h][out_w][out_cpitch]
+bool conv3x3_fuse_ok(const ActView& in, int cout) {
+  if (conv3x3_flat2_ok(in, 0, cout)) return false;   // (the opt-in experiment has no fused epilogue)
+  return conv3x3_flat_ok(in, 0, cout) || conv3x3_c2_ok(in, 0, cout);
+}
+
 int conv3x3_launch(const ActView& in, int mode, const bf16* wpacked, int cout, int cin_pitch, bf16* out, int out_cpitch,
-                   float* stat_sum, float* stat_sq, const float* bias, int relu, cudaStream_t stream) {
+                   float* stat_sum, float* stat_sq, const float* bias, int relu, cudaStream_t stream, const ConvFuse* fuse) {
   MIMO_CHECK(mode == 0 || mode == 1, MIMO_ERR_ARG, "conv3x3: bad mode %d", mode);
   MIMO_CHECK(mode == 0 ? in.pad == 1 : (in.pad == 0 || in.pad == 2), MIMO_ERR_ARG, "conv3x3: mode %d got a pad=%d input", mode, in.pad);
   MIMO_CHECK(in.cpitch % 8 == 0 && in.c_off % 8 == 0, MIMO_ERR_ALIGN, "conv3x3: input cpitch/c_off must be multiples of 8 (got %d/%d)", in.cpitch, in.c_off);
@@ -241,6 +246,14 @@ int conv3x3_launch(const ActView& in, int mode, const bf16* wpacked, int cout, i
   MIMO_CHECK(((uintptr_t)in.base % 16) == 0 && ((uintptr_t)wpacked % 16) == 0 && ((uintptr_t)out % 16) == 0, MIMO_ERR_ALIGN,
              "conv3x3: pointers must be 16-byte aligned");
   MIMO_CHECK(in.H >= 2 && in.W >= 2, MIMO_ERR_ARG, "conv3x3: reflect padding needs H,W >= 2");
+  if (fuse != nullptr) {
+    if (conv3x3_flat_ok(in, mode, cout) && !conv3x3_flat2_ok(in, mode, cout))
+      return conv3x3_flat_launch(in, mode, wpacked, cout, cin_pitch, out, out_cpitch, stat_sum, stat_sq, bias, relu, stream, fuse);
+    if (conv3x3_c2_ok(in, mode, cout))
+      return conv3x3_c2_launch(in, mode, wpacked, cout, cin_pitch, out, out_cpitch, stat_sum, stat_sq, bias, relu, stream, fuse);
+    set_error("conv3x3: no kernel with a fused inference epilogue for this layer (check conv3x3_fuse_ok first)");
+    return MIMO_ERR_ARG;
+  }
   if (conv3x3_flat2_ok(in, mode, cout))
     return conv3x3_flat2_launch(in, mode, wpacked, cout, cin_pitch, out, out_cpitch, stat_sum, stat_sq, bias, relu, stream);
   if (conv3x3_flat_ok(in, mode, cout))

@@ -309,6 +309,37 @@ __global__ void maxpool_kernel(ActView in, ActView o, long long* __restrict__ id
 }
 
 // ------------------------------------------------------------------------------------------------
+// Reflect halo of a pad==1 view from its interior (row -1 := row 1, row H := row H-2, same for columns, corners from the
+// mirrored rows): the fused inference epilogue of the conv kernels writes only interior pixels. One thread per (halo cell, 8-channel
+// group); the halo is 2 (H + W + 2) of the (H+2)(W+2) cells, so this is a few percent of one pass over the tensor.
+// ------------------------------------------------------------------------------------------------
+__global__ void halo_fill_kernel(ActView v) {
+  const int groups = (v.C + 7) >> 3;
+  const int ring = 2 * (v.W + 2) + 2 * v.H;
+  const long long total = (long long)v.N * ring * groups;
+  const bool vec = ((v.c_off | v.cpitch) & 7) == 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    long long r = i / groups;
+    const int k = (int)(r % ring);
+    const int n = (int)(r / ring);
+    int h, w;   // halo cell in interior coordinates (-1 .. H, -1 .. W)
+    if (k < v.W + 2) { h = -1; w = k - 1; }
+    else if (k < 2 * (v.W + 2)) { h = v.H; w = k - (v.W + 2) - 1; }
+    else { const int t = k - 2 * (v.W + 2); h = t >> 1; w = (t & 1) ? v.W : -1; }
+    const int sh = reflect1(h, v.H), sw = reflect1(w, v.W);
+    const int c = g * 8, nv = min(8, v.C - c);
+    const bf16* src = v.base + v.pix(n, sh, sw) + c;
+    bf16* dst = v.base + v.pix(n, h, w) + c;
+    if (vec && nv == 8) {
+      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
+    } else {
+      for (int j = 0; j < nv; ++j) dst[j] = src[j];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // bilinear x2, align_corners=True, then zero F.pad to the skip size (components.py:78,112-115), written
 // into a channel slice of the (padded, reflect-halo) concat buffer.
 // ------------------------------------------------------------------------------------------------
@@ -1285,6 +1316,14 @@ int maxpool_launch(const ActView& in, const ActView& o, long long* idx_nchw, cud
   MIMO_CHECK(o.H == in.H / 2 && o.W == in.W / 2 && o.C == in.C && o.N == in.N, MIMO_ERR_ARG, "maxpool: shape mismatch");
   const long long total = (long long)o.N * o.H * o.W * ((o.C + 7) / 8);
   maxpool_kernel<<<grid_for(total), kBlock, 0, st>>>(in, o, idx_nchw);
+  MIMO_LAUNCH_CHECK();
+  return MIMO_OK;
+}
+
+int halo_fill_launch(const ActView& v, cudaStream_t st) {
+  MIMO_CHECK(v.pad == 1, MIMO_ERR_ARG, "halo_fill: needs a pad == 1 view");
+  const long long total = (long long)v.N * (2 * (v.W + 2) + 2 * v.H) * ((v.C + 7) / 8);
+  halo_fill_kernel<<<grid_for(total), kBlock, 0, st>>>(v);
   MIMO_LAUNCH_CHECK();
   return MIMO_OK;
 }

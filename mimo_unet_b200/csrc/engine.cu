@@ -89,6 +89,9 @@ struct mimo_unet_plan {
   GraphSlot g_fwd, g_bwd[4];
   cudaStream_t cap_stream = nullptr;   // private stream the graphs are captured on
   int graph_mode = 1;          // env MIMO_GRAPH (0 disables)
+  int eval_fuse = 1;           // env MIMO_EVAL_FUSE (0: eval mode keeps the unfused conv -> y -> bn_relu_apply path)
+  bool fuse_next = false;      // mimo_unet_set_inference_fusion: the caller promises not to call backward on the next forwards
+  bool last_fused = false;     // the last forward took the fused inference path (it keeps no raw conv outputs: no backward)
   bool graph_failed = false;   // a capture failed once: stay eager
   int fwd_calls = 0, bwd_calls = 0;
   std::vector<WgradUnpackJob> unpack_jobs;   // pending weight-gradient transposes of the current backward stage
@@ -279,6 +282,25 @@ int conv_bn_forward(mimo_unet_plan* P, ConvL& c, const ActView& in, const ActVie
   bf16* y = reinterpret_cast<bf16*>(P->ws + P->bufs[c.y].off);
   float* vec = fptr(P, c.vec);
   float *scale = vec, *shift = vec + c.cout_p, *mean = vec + 2 * c.cout_p, *invstd = vec + 3 * c.cout_p;
+  // Inference (BatchNorm with running statistics): the affine is known BEFORE the convolution, so it is folded into the conv
+  // epilogue together with the ReLU and the Dropout2d factors (reference components.py:23-29 in eval mode, ensemble.py:54-66
+  // for MC dropout). The epilogue writes the activation straight into the interior of the consumer's haloed buffer: no raw
+  // output y, no bn_relu_apply pass; the halo ring and the pooled copy are produced by two small kernels. The first conv
+  // channels past C of the last 8-channel group are written as zeros: they are pad channels or belong to a concat slice that a
+  // LATER kernel of the forward pass writes (up-sampling into dcat, the next subnetwork's slice of cat3).
+  if (!training && P->eval_fuse && P->fuse_next && out.pad == 1 && (out.c_off & 7) == 0 && out.c_off + round_up(c.cout, 8) <= out.cpitch &&
+      conv3x3_fuse_ok(in, c.cout)) {
+    const float* bias0 = (const float*)P->state[c.state0 + 1];
+    RUN(kBnFinalize, bn_eval_affine_launch(c.cout, (const float*)P->state[c.state0 + 2], (const float*)P->state[c.state0 + 3], bias0,
+                                           (const float*)P->state[c.state0 + 4], (const float*)P->state[c.state0 + 5], 1e-5f, scale, shift,
+                                           mean, invstd, st));
+    ConvFuse fz{scale, shift, drop, 1, 1};
+    RUN(kConvFprop, conv3x3_launch(in, 0, bptr(P, c.wf), c.cout, c.cin_p, out.base + out.c_off, out.cpitch, nullptr, nullptr, nullptr, 0,
+                                   st, &fz));
+    RUN(kBnApply, halo_fill_launch(out, st));
+    if (pool) RUN(kBnApply, maxpool_launch(out, *pool, nullptr, st));
+    return MIMO_OK;
+  }
   RUN(kConvFprop, conv3x3_launch(in, 0, bptr(P, c.wf), c.cout, c.cin_p, y, c.cout_p, training ? fptr(P, c.psum) : nullptr,
                      training ? fptr(P, c.psq) : nullptr, nullptr, 0, st));
   const float* bias = (const float*)P->state[c.state0 + 1];
@@ -394,6 +416,7 @@ int mimo_unet_plan_create(const mimo_unet_config_t* cfg, mimo_unet_plan_t** out)
   mimo_unet_plan* P = new mimo_unet_plan();
   P->cfg = *cfg;
   { const char* e = getenv("MIMO_GRAPH"); P->graph_mode = e ? atoi(e) : 1; }
+  { const char* e = getenv("MIMO_EVAL_FUSE"); P->eval_fuse = e ? atoi(e) : 1; }
   const int S = cfg->num_subnetworks, f = cfg->filter_base_count, N = cfg->batch, Cin = cfg->in_channels;
   P->Hs[0] = cfg->height; P->Ws[0] = cfg->width;
   for (int l = 1; l < 5; ++l) { P->Hs[l] = P->Hs[l - 1] / 2; P->Ws[l] = P->Ws[l - 1] / 2; }
@@ -626,7 +649,7 @@ int mimo_unet_forward(mimo_unet_plan_t* P, const float* x, const long long* gath
   bool elem_drop = P->center_keep != nullptr;
   for (const bf16* m : P->final_keep) elem_drop = elem_drop || (m != nullptr);
   const bool allow = P->graph_mode != 0 && !P->graph_failed && !P->prof && drop_masks == nullptr && !elem_drop && P->fwd_calls > 2;
-  int rc = run_graphed(P, P->g_fwd, tr ? 1ull : 0ull, allow, st, body);
+  int rc = run_graphed(P, P->g_fwd, (tr ? 1ull : 0ull) | ((!tr && P->eval_fuse && P->fuse_next) ? 2ull : 0ull), allow, st, body);
   if (rc) return rc;
   const int K = cfg.out_channels;
   for (int s = 0; s < S; ++s) {
@@ -635,6 +658,7 @@ int mimo_unet_forward(mimo_unet_plan_t* P, const float* x, const long long* gath
                         out + (long long)s * K * HW, (long long)S * K * HW, st));
   }
   P->last_training = tr;
+  P->last_fused = !tr && P->eval_fuse && P->fuse_next;
   P->have_forward = true;
   return MIMO_OK;
 }
@@ -642,6 +666,8 @@ int mimo_unet_forward(mimo_unet_plan_t* P, const float* x, const long long* gath
 int mimo_unet_backward(mimo_unet_plan_t* P, const float* dout, const float* grad_scale, float* dx, int accumulate, void* stream) {
   MIMO_CHECK(P && P->bound, MIMO_ERR_STATE, "backward: plan is not bound");
   MIMO_CHECK(P->have_forward, MIMO_ERR_STATE, "backward: no forward pass to differentiate");
+  MIMO_CHECK(!P->last_fused, MIMO_ERR_STATE, "backward: the last forward ran with the fused inference epilogues (mimo_unet_set_inference_fusion), "
+                                             "which keep no raw convolution outputs; run the forward without it to differentiate");
   MIMO_CHECK(dout, MIMO_ERR_ARG, "backward: null dout");
   cudaStream_t st = (cudaStream_t)stream;
   const mimo_unet_config_t& cfg = P->cfg;
@@ -810,6 +836,12 @@ int mimo_unet_set_elementwise_dropout(mimo_unet_plan_t* P, const void* center_ke
   if (final_keep)
     for (int s = 0; s < P->cfg.num_subnetworks; ++s) P->final_keep[s] = (const bf16*)final_keep[s];
   P->final_scale = final_scale;
+  return MIMO_OK;
+}
+
+int mimo_unet_set_inference_fusion(mimo_unet_plan_t* P, int on) {
+  MIMO_CHECK(P, MIMO_ERR_ARG, "set_inference_fusion: null plan");
+  P->fuse_next = on != 0;
   return MIMO_OK;
 }
 

@@ -2,6 +2,7 @@
 // Every function enqueues work on `stream`, never synchronises, never allocates device memory.
 #pragma once
 #include "common.cuh"
+#include "conv_epilogue.cuh"
 
 namespace mimo {
 
@@ -10,9 +11,13 @@ int conv3x3_block_n(int cout);
 int conv3x3_stat_rows();
 bool conv3x3_flat_ok(const ActView& in, int mode, int cout);
 int conv3x3_flat_launch(const ActView& in, int mode, const bf16* wpacked, int cout, int cin_pitch, bf16* out, int out_cpitch,
-                        float* stat_sum, float* stat_sq, const float* bias, int relu, cudaStream_t stream);
+                        float* stat_sum, float* stat_sq, const float* bias, int relu, cudaStream_t stream, const ConvFuse* fuse = nullptr);
+// fuse != nullptr (inference): out = interior/first channel of the CONSUMER's haloed buffer, out_cpitch its pixel pitch; the
+// epilogue applies v * scale + shift, ReLU and the Dropout2d factors; only kernels with that epilogue are eligible
+// (conv3x3_fuse_ok), the halo ring is filled afterwards by halo_fill_launch.
 int conv3x3_launch(const ActView& in, int mode, const bf16* wpacked, int cout, int cin_pitch, bf16* out, int out_cpitch,
-                   float* stat_sum, float* stat_sq, const float* bias, int relu, cudaStream_t stream);
+                   float* stat_sum, float* stat_sq, const float* bias, int relu, cudaStream_t stream, const ConvFuse* fuse = nullptr);
+bool conv3x3_fuse_ok(const ActView& in, int cout);
 bool conv3x3_flatk_ok(const ActView& in, int mode, int cout);
 int conv3x3_flatk_launch(const ActView& in, int mode, const bf16* wpacked, int cout, int cin_pitch, bf16* out, int out_cpitch,
                          float* stat_sum, float* stat_sq, const float* bias, int relu, cudaStream_t stream);
@@ -21,7 +26,7 @@ int conv3x3_flat2_launch(const ActView& in, int mode, const bf16* wpacked, int c
                          float* stat_sum, float* stat_sq, const float* bias, int relu, cudaStream_t stream);
 bool conv3x3_c2_ok(const ActView& in, int mode, int cout);
 int conv3x3_c2_launch(const ActView& in, int mode, const bf16* wpacked, int cout, int cin_pitch, bf16* out, int out_cpitch,
-                      float* stat_sum, float* stat_sq, const float* bias, int relu, cudaStream_t stream);
+                      float* stat_sum, float* stat_sq, const float* bias, int relu, cudaStream_t stream, const ConvFuse* fuse = nullptr);
 // pre_zeroed: the caller has already cleared dw_packed on `stream` (the executor clears all layers with one memset)
 int conv3x3_wgrad_launch(const ActView& dy, const ActView& x, float* dw_packed, int cin_pitch, cudaStream_t stream, bool pre_zeroed = false);
 bool conv3x3_wgrad_flat_ok(const ActView& dy, const ActView& x);
@@ -53,6 +58,7 @@ int upsample_launch(const ActView& in, const ActView& o, cudaStream_t st);
 int upsample_bwd_launch(const ActView& gdst, const ActView& gsrc, int accumulate, cudaStream_t st);
 int grad_gather_launch(const ActView* dpad, const ActView* gpool, const ActView* act, const ActView& gout, int accumulate,
                        cudaStream_t st);
+int halo_fill_launch(const ActView& v, cudaStream_t st);
 int mask_mul_launch(const ActView& a, const bf16* keep, int mask_cp, float scale, cudaStream_t st);
 int maxunpool_launch(const ActView& in, const long long* idx_nchw, const ActView& o, cudaStream_t st);
 int convtranspose2x2_launch(const ActView& in, const float* wt, const float* bias, const ActView& o, cudaStream_t st);

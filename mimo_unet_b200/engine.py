@@ -99,6 +99,10 @@ class UNetPlan:
         check(self.lib.mimo_unet_set_elementwise_dropout(self.handle, _ptr(center_keep), float(center_scale), fk, float(final_scale)),
               "mimo_unet_set_elementwise_dropout")
 
+    def set_inference_fusion(self, on: bool):
+        """Fused inference epilogues for the following eval-mode forwards (no backward possible after them)."""
+        check(self.lib.mimo_unet_set_inference_fusion(self.handle, int(bool(on))), "mimo_unet_set_inference_fusion")
+
     def set_backward_events(self, events: Optional[Sequence["torch.cuda.Event"]]):
         """events: 4 torch.cuda.Event objects (already recorded once so their handles exist) or None; see
         mimo_unet_set_backward_events."""

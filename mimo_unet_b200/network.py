@@ -203,11 +203,11 @@ class NetworkRuntime:
         params = [p for p in net.parameters()]
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params)):
             return _UNetFunction.apply(self, x, gather, *params)
-        out, _ = self._forward_impl(x, gather)
+        out, _ = self._forward_impl(x, gather, inference=True)   # nothing records a graph: fused inference epilogues
         return out
 
     # ------------------------------------------------------------------------------------------
-    def _forward_impl(self, x: torch.Tensor, gather):
+    def _forward_impl(self, x: torch.Tensor, gather, inference: bool = False):
         net = self.net
         x = x.detach()
         if x.dtype != torch.float32:
@@ -230,6 +230,7 @@ class NetworkRuntime:
             self._elementwise_dropout(plan, B, H, W, dev)
         g = None if gather is None else gather.to(device=dev, dtype=torch.int64).contiguous()
         with torch.cuda.device(dev):   # streams and launches follow the TENSORS' device, not whatever device is current
+            plan.set_inference_fusion(inference and not bn_training)
             plan.forward(x, out, bn_training, gather=g, drop_masks=masks)
         self._forward_token += 1
         self.last_launches = (plan.last_launches, self.last_launches[1])

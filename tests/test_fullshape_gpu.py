@@ -28,6 +28,11 @@ CONFIGS = {
     # configs[3]: M=4 inference (BatchNorm in eval mode), plain and with one MC-dropout pass (injected Dropout2d masks)
     "C4_eval": dict(S=4, f=21, cin=3, B=64, H=128, W=160, training=False, drop=0.0, backward=False),
     "C4_mc": dict(S=4, f=21, cin=3, B=64, H=128, W=160, training=False, drop=0.1, backward=False),
+    # the same with the fused inference epilogues (mimo_unet_set_inference_fusion: eval BatchNorm + ReLU + Dropout2d applied in
+    # the conv epilogue, written straight into the consumer's haloed buffer; what EnsembleModule.forward runs under no_grad)
+    "C4_eval_fused": dict(S=4, f=21, cin=3, B=64, H=128, W=160, training=False, drop=0.0, backward=False, fused=True),
+    "C4_mc_fused": dict(S=4, f=21, cin=3, B=64, H=128, W=160, training=False, drop=0.1, backward=False, fused=True),
+    "C2_eval_fused": dict(S=2, f=21, cin=3, B=64, H=128, W=160, training=False, drop=0.1, backward=False, fused=True),
     # training with Dropout2d masks at the C2 shape (smaller batch: the eager path is the same code)
     "C2_drop": dict(S=2, f=21, cin=3, B=16, H=128, W=160, training=True, drop=0.1, backward=True),
 }
@@ -104,6 +109,8 @@ def test_teacher_forced_fullshape(name):
     if p_drop > 0:
         masks = [((torch.rand(B * plan.drop_channels[i], device=dev) >= p_drop).float() / (1.0 - p_drop)).contiguous() for i in range(len(nodes))]
     out = torch.empty(B, S, 2, H, W, device=dev)
+    fused = bool(cfg.get("fused"))
+    plan.set_inference_fusion(fused)
     plan.forward(x, out, training, drop_masks=masks)
     torch.cuda.synchronize()
     assert torch.isfinite(out).all()
@@ -113,6 +120,16 @@ def test_teacher_forced_fullshape(name):
 
     def mask_of(i):
         return None if masks is None else masks[i].view(B, -1)
+
+    def fused_layer(xin, w, pre, bi, ci, m):
+        """conv -> eval BatchNorm -> ReLU -> Dropout2d with ONE bf16 rounding at the end (the fused epilogue works on the fp32 accumulator)"""
+        gamma, beta, bias = sd[f"{pre}{bi}.weight"], sd[f"{pre}{bi}.bias"], sd[f"{pre}{ci}.bias"]
+        z = O.batchnorm_eval(O.conv3x3_reflect(xin, w, None) + bias[None, :, None, None], gamma, beta, sd[f"{pre}{bi}.running_mean"],
+                             sd[f"{pre}{bi}.running_var"])
+        h = F.relu(z)
+        if m is not None:
+            h = h * m[:, :, None, None]
+        return bf16r(h)
 
     def bn_relu(y, pre, bi, ci, m, check_stats):
         gamma, beta, bias = sd[f"{pre}{bi}.weight"], sd[f"{pre}{bi}.bias"], sd[f"{pre}{ci}.bias"]
@@ -136,12 +153,25 @@ def test_teacher_forced_fullshape(name):
 
     # ------------------------------------------------------------------ forward, layer by layer
     for i, (nd, pre) in enumerate(nodes):
-        xin, a1, y1, y2, o = dbg(nd + ".in"), dbg(nd + ".a1"), dbg(nd + ".c1.y"), dbg(nd + ".c2.y"), dbg(nd + ".out")
+        xin, a1, o = dbg(nd + ".in"), dbg(nd + ".a1"), dbg(nd + ".out")
         w1, w2 = bf16r(sd[pre + "0.weight"]), bf16r(sd[pre + "3.weight"])
-        chk(f"fprop:{nd}.c1", y1, bf16r(O.conv3x3_reflect(xin, w1, None)))
-        chk(f"bn_apply:{nd}.c1", a1, bn_relu(y1, pre, 1, 0, None, (nd, "c1")))
-        chk(f"fprop:{nd}.c2", y2, bf16r(O.conv3x3_reflect(a1, w2, None)))
-        chk(f"bn_apply:{nd}.c2", o, bn_relu(y2, pre, 4, 3, mask_of(i), (nd, "c2")))
+        # the M per-subnetwork encoders' second conv may write an unaligned concat slice: those layers keep the unfused path
+        if fused:
+            chk(f"fused_layer:{nd}.c1", a1, fused_layer(xin, w1, pre, 1, 0, None))
+        else:
+            y1 = dbg(nd + ".c1.y")
+            chk(f"fprop:{nd}.c1", y1, bf16r(O.conv3x3_reflect(xin, w1, None)))
+            chk(f"bn_apply:{nd}.c1", a1, bn_relu(y1, pre, 1, 0, None, (nd, "c1")))
+        ref_fused = fused_layer(a1, w2, pre, 4, 3, mask_of(i)) if fused else None
+        y2 = dbg(nd + ".c2.y")
+        ref_unfused = bn_relu(bf16r(O.conv3x3_reflect(a1, w2, None)), pre, 4, 3, mask_of(i), None) if fused else None
+        if fused:
+            # either path is legal for c2 (alignment of the destination slice decides): accept the closer one
+            e_f, e_u = rel_l2(o, ref_fused), rel_l2(o, ref_unfused)
+            chk(f"fused_layer:{nd}.c2", o, ref_fused if e_f <= e_u else ref_unfused)
+        else:
+            chk(f"fprop:{nd}.c2", y2, bf16r(O.conv3x3_reflect(a1, w2, None)))
+            chk(f"bn_apply:{nd}.c2", o, bn_relu(y2, pre, 4, 3, mask_of(i), (nd, "c2")))
         # the producers write the reflect halo of every conv input
         for buf in (".in", ".a1"):
             xp = plan.debug_tensor_padded(nd + buf)

@@ -13,10 +13,11 @@ from tests.util import rel_l2
 pytestmark = pytest.mark.gpu
 
 
-def run_plan(cfg, sd, x, training, dout=None, need_dx=False):
+def run_plan(cfg, sd, x, training, dout=None, need_dx=False, fused=False):
     S, f, cin = cfg["S"], cfg["f"], cfg["cin"]
     B, _, _, H, W = x.shape
     plan = UNetPlan(cin, 2, S, f, B, H, W, torch.device("cuda"))
+    plan.set_inference_fusion(fused)
     names = [n for n, _, _ in O.state_dict_spec(cin, 2, S, f)]
     state = [sd[n].cuda().contiguous() for n in names]
     grads = [torch.full_like(t, float("nan")) if t.dtype == torch.float32 and ("running" not in n) else None
@@ -51,6 +52,14 @@ def test_eval_forward_vs_oracle_and_golden(cases, name):
     print(name, "eval: vs bf16 oracle", e_emu, "vs fp32 reference", e_ref)
     assert e_emu <= 5e-3      # accumulation-order 1-ulp bf16 flips amplified through 13 layers
     assert e_ref <= 3e-2      # bf16 storage vs the fp32 reference (reference vs itself under autocast: 5.2e-3..7e-2)
+    # fused inference epilogues (BatchNorm affine + ReLU applied to the fp32 accumulator, ONE bf16 rounding per layer instead of
+    # two): judged against the fp32 reference with the same bound; backward is refused after such a forward
+    rf = run_plan(cfg, sd, c["x"], training=False, fused=True)
+    e_fused = rel_l2(rf["out"].cpu(), c["eval"]["out"])
+    print(name, "eval fused: vs fp32 reference", e_fused, " vs unfused", rel_l2(rf["out"], r["out"]))
+    assert e_fused <= 3e-2
+    with pytest.raises(Exception):
+        rf["plan"].backward(torch.zeros_like(rf["out"]))
 
 
 @pytest.mark.parametrize("name", ["m1_f8_32x32", "m2_f8_32x32", "m2_f8_37x45", "m2_f21_32x48", "m4_f8_32x32", "m2_f30_c2_32x32"])

@@ -148,7 +148,8 @@ def test_lightning_module_steps():
     assert "val_loss_combined" in m.logged and "metric_val/epistemic_std_mean" in m.logged
     # validation math vs oracle on the module's own output
     img5 = repeat_subnetworks(batch["image"], 2)
-    p1, p2 = m(img5)
+    with torch.no_grad():   # the same executor path as validation_step (fused inference epilogues)
+        p1, p2 = m(img5)
     o = torch.cat([p1, p2], dim=2).cpu()
     vl, comb, mean, alea, epi = O.validation_math(o, repeat_subnetworks(batch["label"], 2).cpu(), batch["mask"].cpu())
     assert rel_l2(v["preds"].cpu(), mean) <= 1e-5 and rel_l2(v["epistemic_std_map"].cpu(), epi.sqrt()) <= 1e-4
