@@ -49,6 +49,7 @@ struct C2Params {
   int T;                              // tiles per CTA per item
   int n_mitems, n_tiles_n, block_n;   // block_n = N of the pair's MMA (multiple of 16); each CTA stages block_n / 2 weight rows
   int cin_chunks, ks_last;            // 64-channel chunks; 16-channel k-steps that carry data in the last chunk
+  int split, ks_split;                // virtual concat: chunks [0, split) come from the first input view (k-steps of its last chunk), the rest from the second
   int seg_rows, seg_full, seg_rem;    // A segment: T*128 + 2*wb + 2 rows = seg_full boxes of 128 rows + one box of seg_rem rows
   int a_slots, a_slot_bytes, b_slots, b_slot_bytes, b_tap_bytes;
   int acc_cols;                       // n_tiles_n * block_n: columns of the per-warp statistics accumulators
@@ -58,6 +59,7 @@ struct C2Params {
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv3x3_c2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2,
+                  const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_b2,
                   const __grid_constant__ CUtensorMap tmap_w, const C2Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -85,6 +87,8 @@ conv3x3_c2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_a2);
+    prefetch_tmap(&tmap_b);
+    prefetch_tmap(&tmap_b2);
     prefetch_tmap(&tmap_w);
   }
   if (warp == 1) {
@@ -133,8 +137,12 @@ conv3x3_c2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           const uint32_t fb = a_full0 + (uint32_t)sa * 8u;
           if (rank == 0) mbar_arrive_expect_tx(&a_full[sa], 2u * a_tx);
           if (!(p.ko & 2)) {
-            for (int i = 0; i < p.seg_full; ++i) tma_load_2d_cg2(&tmap_a, fb, st + (size_t)i * (kBlockM * 128), cc * 64, (int)p0 + i * kBlockM);
-            if (p.seg_rem) tma_load_2d_cg2(&tmap_a2, fb, st + (size_t)p.seg_full * (kBlockM * 128), cc * 64, (int)p0 + p.seg_full * kBlockM);
+            const bool second = cc >= p.split;   // virtual concat: the chunk lives in the second input view
+            const CUtensorMap* m1 = second ? &tmap_b : &tmap_a;
+            const CUtensorMap* m2 = second ? &tmap_b2 : &tmap_a2;
+            const int ch0 = (second ? cc - p.split : cc) * 64;
+            for (int i = 0; i < p.seg_full; ++i) tma_load_2d_cg2(m1, fb, st + (size_t)i * (kBlockM * 128), ch0, (int)p0 + i * kBlockM);
+            if (p.seg_rem) tma_load_2d_cg2(m2, fb, st + (size_t)p.seg_full * (kBlockM * 128), ch0, (int)p0 + p.seg_full * kBlockM);
           }
         }
         __syncwarp();
@@ -171,7 +179,7 @@ conv3x3_c2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         for (int cc = 0; cc < p.cin_chunks; ++cc) {
           mbar_wait(&a_full[sa], pa);
           const uint32_t a_lo = a_lo0 + (uint32_t)sa * a_step;
-          const uint32_t ks = (cc == p.cin_chunks - 1) ? (uint32_t)p.ks_last : 4u;
+          const uint32_t ks = (cc == p.cin_chunks - 1) ? (uint32_t)p.ks_last : (cc == p.split - 1 ? (uint32_t)p.ks_split : 4u);
           for (int kh = 0; kh < 3; ++kh) {
             mbar_wait(&b_full[sb], pb);
             tc_fence_after();
@@ -387,7 +395,8 @@ bool conv3x3_c2_ok(const ActView& in, int mode, int cout) {
 }
 
 int conv3x3_c2_launch(const ActView& in, int mode, const bf16* wpacked, int cout, int cin_pitch, bf16* out, int out_cpitch,
-                      float* stat_sum, float* stat_sq, const float* bias, int relu, cudaStream_t stream, const ConvFuse* fuse) {
+                      float* stat_sum, float* stat_sq, const float* bias, int relu, cudaStream_t stream, const ConvFuse* fuse,
+                      const ActView* in2) {
   note_kernel(7);
   C2Params p{};
   p.wb = in.wb();
@@ -402,6 +411,16 @@ int conv3x3_c2_launch(const ActView& in, int mode, const bf16* wpacked, int cout
   { static const int ko = env_int("MIMO_C2_KO", 0); p.ko = ko; }
   p.cin_chunks = ceil_div(in.C, 64);
   p.ks_last = ceil_div(in.C - (p.cin_chunks - 1) * 64, 16);
+  p.split = p.cin_chunks;
+  p.ks_split = p.ks_last;
+  if (in2 != nullptr) {
+    MIMO_CHECK(in2->N == in.N && in2->H == in.H && in2->W == in.W && in2->pad == in.pad, MIMO_ERR_ARG, "conv3x3_c2: the two views of a virtual concat differ in shape");
+    MIMO_CHECK(in2->cpitch % 8 == 0 && in2->c_off % 8 == 0 && ((uintptr_t)in2->base % 16) == 0, MIMO_ERR_ALIGN, "conv3x3_c2: second view not 16-byte aligned");
+    const int c2chunks = ceil_div(in2->C, 64);
+    p.cin_chunks = p.split + c2chunks;
+    p.ks_last = ceil_div(in2->C - (c2chunks - 1) * 64, 16);
+    MIMO_CHECK(cin_pitch >= p.split * 64 + in2->C, MIMO_ERR_ARG, "conv3x3_c2: weight pitch %d too small for the chunk-aligned virtual concat", cin_pitch);
+  }
   MIMO_CHECK((p.block_n / 2) % 8 == 0, MIMO_ERR_ARG, "conv3x3_c2: block_n/2 must be a multiple of 8");
   // tiles per CTA: more tiles share one weight block and one segment halo (fewer bytes through TMA per FLOP) but make the
   // items coarser (wave quantisation over the 74 CTA pairs). Pick the T with the lowest modelled cost.
@@ -443,15 +462,16 @@ int conv3x3_c2_launch(const ActView& in, int mode, const bf16* wpacked, int cout
   p.epi.out_cmax = fuse ? round_up(cout, 8) : out_cpitch;
   MIMO_CHECK((p.n_tiles_n - 1) * p.block_n < out_cpitch, MIMO_ERR_ARG, "conv3x3_c2: n-tiling exceeds out_cpitch");
 
-  CUtensorMap tm_a, tm_a2, tm_w;
-  {
-    uint64_t dims[2] = {(uint64_t)in.C, (uint64_t)p.total_pos};
-    uint64_t strides[1] = {(uint64_t)in.cpitch * 2};
+  CUtensorMap tm_a, tm_a2, tm_b, tm_b2, tm_w;
+  for (int v = 0; v < 2; ++v) {
+    const ActView& av = (v == 1 && in2 != nullptr) ? *in2 : in;   // without a second view the maps are duplicates (never read)
+    uint64_t dims[2] = {(uint64_t)av.C, (uint64_t)p.total_pos};
+    uint64_t strides[1] = {(uint64_t)av.cpitch * 2};
     uint32_t box[2] = {64, (uint32_t)kBlockM};
-    int rc = encode_tmap_bf16(&tm_a, in.base + in.c_off, 2, dims, strides, box, 1);
+    int rc = encode_tmap_bf16(v ? &tm_b : &tm_a, av.base + av.c_off, 2, dims, strides, box, 1);
     if (rc) return rc;
     uint32_t box2[2] = {64, (uint32_t)(p.seg_rem ? p.seg_rem : 1)};
-    rc = encode_tmap_bf16(&tm_a2, in.base + in.c_off, 2, dims, strides, box2, 1);
+    rc = encode_tmap_bf16(v ? &tm_b2 : &tm_a2, av.base + av.c_off, 2, dims, strides, box2, 1);
     if (rc) return rc;
   }
   {
@@ -464,7 +484,7 @@ int conv3x3_c2_launch(const ActView& in, int mode, const bf16* wpacked, int cout
   MIMO_CUDA(cudaFuncSetAttribute(conv3x3_c2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   const int items = p.n_mitems * p.n_tiles_n;
   const int grid = 2 * (items < max_pairs ? items : max_pairs);
-  conv3x3_c2_kernel<<<grid, kThreads, smem_bytes, stream>>>(tm_a, tm_a2, tm_w, p);
+  conv3x3_c2_kernel<<<grid, kThreads, smem_bytes, stream>>>(tm_a, tm_a2, tm_b, tm_b2, tm_w, p);
   MIMO_LAUNCH_CHECK();
   return MIMO_OK;
 }

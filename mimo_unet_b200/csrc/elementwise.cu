@@ -139,7 +139,8 @@ __global__ void weight_pack_batched_kernel(const PackBatch b) {
   const int total_d = q.wd ? 9 * cin * cout_pitch : 0;
   for (int i = ((int)blockIdx.x - b.first_block[j]) * blockDim.x + threadIdx.x; i < total_f + total_d; i += nblk * blockDim.x) {
     if (i < total_f) {
-      const int ci = i % cin_pitch, co = (i / cin_pitch) % cout, tap = i / (cin_pitch * cout);
+      const int cp = i % cin_pitch, co = (i / cin_pitch) % cout, tap = i / (cin_pitch * cout);
+      const int ci = cp < q.gap_at || q.gap == 0 ? cp : (cp >= q.gap_at + q.gap ? cp - q.gap : cin);   // cin = "zero" marker
       q.wf[i] = __float2bfloat16_rn(ci < cin ? q.w[((size_t)co * cin + ci) * 9 + tap] : 0.f);
     } else {
       const int k = i - total_f;

@@ -46,6 +46,7 @@ struct ConvL {
   int m_tiles = 0;
   size_t wf = 0, wd = 0, psum = 0, psq = 0, vec = 0 /* scale,shift,mean,invstd,s1,s2: 6*cout_p floats */, bnpart = 0, dwp = 0;
   int y = -1, dy = -1, dpad = -1;  // Buf ids: raw output, its gradient, padded-domain input gradient
+  size_t wf_v = 0; int cin_pv = 0; // inference-only weight pack in the chunk-aligned channel order of a virtual concat (decoders)
 };
 
 struct Node {  // one DoubleConv
@@ -76,6 +77,7 @@ struct mimo_unet_plan {
   // extra buffers
   std::vector<int> xin, dcat, p1, gp1;   // per subnetwork
   int cat3 = -1, cat2 = -1, cat1 = -1, pxc = -1, px3 = -1, px4 = -1, x5 = -1, u1 = -1, u2 = -1, u3 = -1;
+  int upd = -1;   // inference: the up-sampled core output shared by all decoders (virtual concat), -1 when not used
   int g_xc = -1, g_x3 = -1, g_x4 = -1, g_x5 = -1, g_u1 = -1, g_u2 = -1, g_u3 = -1;
   int gp_xc = -1, gp_x3 = -1, gp_x4 = -1;  // pooled-map gradients
   int tmp0 = -1, tmp1 = -1, tmp2 = -1, tmp3 = -1;  // folded upsample-branch gradients per level
@@ -278,7 +280,7 @@ float* fptr(const mimo_unet_plan* P, size_t off) { return reinterpret_cast<float
 bf16* bptr(const mimo_unet_plan* P, size_t off) { return reinterpret_cast<bf16*>(P->ws + off); }
 
 int conv_bn_forward(mimo_unet_plan* P, ConvL& c, const ActView& in, const ActView& out, const ActView* pool, const float* drop,
-                    bool training, cudaStream_t st) {
+                    bool training, cudaStream_t st, const ActView* in2 = nullptr) {
   bf16* y = reinterpret_cast<bf16*>(P->ws + P->bufs[c.y].off);
   float* vec = fptr(P, c.vec);
   float *scale = vec, *shift = vec + c.cout_p, *mean = vec + 2 * c.cout_p, *invstd = vec + 3 * c.cout_p;
@@ -289,14 +291,18 @@ int conv_bn_forward(mimo_unet_plan* P, ConvL& c, const ActView& in, const ActVie
   // channels past C of the last 8-channel group are written as zeros: they are pad channels or belong to a concat slice that a
   // LATER kernel of the forward pass writes (up-sampling into dcat, the next subnetwork's slice of cat3).
   if (!training && P->eval_fuse && P->fuse_next && out.pad == 1 && (out.c_off & 7) == 0 && out.c_off + round_up(c.cout, 8) <= out.cpitch &&
-      conv3x3_fuse_ok(in, c.cout)) {
+      (in2 != nullptr ? conv3x3_c2_ok(in, 0, c.cout) : conv3x3_fuse_ok(in, c.cout))) {
     const float* bias0 = (const float*)P->state[c.state0 + 1];
     RUN(kBnFinalize, bn_eval_affine_launch(c.cout, (const float*)P->state[c.state0 + 2], (const float*)P->state[c.state0 + 3], bias0,
                                            (const float*)P->state[c.state0 + 4], (const float*)P->state[c.state0 + 5], 1e-5f, scale, shift,
                                            mean, invstd, st));
     ConvFuse fz{scale, shift, drop, 1, 1};
-    RUN(kConvFprop, conv3x3_launch(in, 0, bptr(P, c.wf), c.cout, c.cin_p, out.base + out.c_off, out.cpitch, nullptr, nullptr, nullptr, 0,
-                                   st, &fz));
+    if (in2 != nullptr)   // virtual concat (decoders): `in` is the skip slice, *in2 the shared up-sampled core output
+      RUN(kConvFprop, conv3x3_c2_launch(in, 0, bptr(P, c.wf_v), c.cout, c.cin_pv, out.base + out.c_off, out.cpitch, nullptr, nullptr, nullptr,
+                                        0, st, &fz, in2));
+    else
+      RUN(kConvFprop, conv3x3_launch(in, 0, bptr(P, c.wf), c.cout, c.cin_p, out.base + out.c_off, out.cpitch, nullptr, nullptr, nullptr, 0,
+                                     st, &fz));
     RUN(kBnApply, halo_fill_launch(out, st));
     if (pool) RUN(kBnApply, maxpool_launch(out, *pool, nullptr, st));
     return MIMO_OK;
@@ -319,13 +325,14 @@ int conv_bn_forward(mimo_unet_plan* P, ConvL& c, const ActView& in, const ActVie
   return MIMO_OK;
 }
 
-int node_forward(mimo_unet_plan* P, int ni, bool training, const float* drop, cudaStream_t st) {
+int node_forward(mimo_unet_plan* P, int ni, bool training, const float* drop, cudaStream_t st, const ActView* in1 = nullptr,
+                 const ActView* in2 = nullptr) {
   Node& n = P->nodes[ni];
-  const ActView in = view_of(P, n.in);
+  const ActView in = in1 ? *in1 : view_of(P, n.in);
   const ActView a1 = view_of(P, n.a1, 0, n.c1.cout);
   const ActView out = view_of(P, n.out);
   P->cur_tag = 2 * ni;
-  int rc = conv_bn_forward(P, n.c1, in, a1, nullptr, nullptr, training, st);
+  int rc = conv_bn_forward(P, n.c1, in, a1, nullptr, nullptr, training, st, in2);
   if (rc) return rc;
   P->cur_tag = 2 * ni + 1;
   if (n.pool.buf >= 0) {
@@ -477,6 +484,16 @@ int mimo_unet_plan_create(const mimo_unet_config_t* cfg, mimo_unet_plan_t** out)
     P->nodes[ni].g2 = V(P->g_feat[s], 0, f);
     P->dec.push_back(ni);
   }
+  // Inference with more than 64 concat channels per decoder (M >= 3 at f = 21): the decoders' first conv reads cat([x1_s, up(u3)])
+  // as a VIRTUAL concat (conv_c2.cu): u3 is up-sampled ONCE into `upd` instead of once per subnetwork into every dcat[s].
+  if (f + c / 2 > 64) {
+    P->upd = buf(0, 1, c / 2);
+    for (int s = 0; s < S; ++s) {
+      ConvL& cl = P->nodes[P->dec[s]].c1;
+      cl.cin_pv = round_up(round_up(f, 64) + c / 2, 8);
+      cl.wf_v = A.take((size_t)9 * cl.cout * cl.cin_pv * sizeof(bf16));
+    }
+  }
   P->head_state0 = cur;
   cur += 2 * S;
   P->n_state = cur;
@@ -613,12 +630,19 @@ int mimo_unet_forward(mimo_unet_plan_t* P, const float* x, const long long* gath
     if (gather) RUN(kPackIn, pack_input_launch(x, (long long)Cin * HW, HW, gather + (long long)s * B, xin, st));
     else RUN(kPackIn, pack_input_launch(x + (long long)s * Cin * HW, (long long)S * Cin * HW, HW, nullptr, xin, st));
   }
+  const bool virt = !tr && P->eval_fuse && P->fuse_next && P->upd >= 0 &&
+                    conv3x3_c2_ok(view_of(P, P->dcat[0], 0, f), 0, P->nodes[P->dec[0]].c1.cout);
   auto body = [&]() -> int {
     {  // bf16 weight packs of every layer (fprop layout + flipped dgrad layout): one launch
       std::vector<WeightPackJob> jobs;
       for (auto& n : P->nodes)
         for (ConvL* cl : {&n.c1, &n.c2})
-          jobs.push_back({(const float*)P->state[cl->state0], bptr(P, cl->wf), bptr(P, cl->wd), cl->cout, cl->cin, cl->cin_p, cl->cout_p});
+          jobs.push_back({(const float*)P->state[cl->state0], bptr(P, cl->wf), bptr(P, cl->wd), cl->cout, cl->cin, cl->cin_p, cl->cout_p, 0, 0});
+      if (virt)   // chunk-aligned packs of the decoders' first conv: [x1_s (f, padded to 64) | up (c/2)]
+        for (int s2 = 0; s2 < S; ++s2) {
+          ConvL& cl = P->nodes[P->dec[s2]].c1;
+          jobs.push_back({(const float*)P->state[cl.state0], bptr(P, cl.wf_v), nullptr, cl.cout, cl.cin, cl.cin_pv, cl.cout_p, f, round_up(f, 64) - f});
+        }
       RUN(kPackW, weight_pack_batched_launch(jobs.data(), (int)jobs.size(), st));
     }
     int rc;
@@ -637,9 +661,15 @@ int mimo_unet_forward(mimo_unet_plan_t* P, const float* x, const long long* gath
     if ((rc = node_forward(P, P->up2, tr, mask(P->up2), st))) return rc;
     RUN(kUpsample, upsample_launch(view_of(P, P->u2, 0, c), view_of(P, P->cat3, c, c), st));
     if ((rc = node_forward(P, P->up3, tr, mask(P->up3), st))) return rc;
+    if (virt) RUN(kUpsample, upsample_launch(view_of(P, P->u3, 0, c / 2), view_of(P, P->upd, 0, c / 2), st));
     for (int s = 0; s < S; ++s) {
-      RUN(kUpsample, upsample_launch(view_of(P, P->u3, 0, c / 2), view_of(P, P->dcat[s], f, c / 2), st));
-      if ((rc = node_forward(P, P->dec[s], tr, mask(P->dec[s]), st))) return rc;
+      if (virt) {
+        const ActView skip = view_of(P, P->dcat[s], 0, f), up = view_of(P, P->upd, 0, c / 2);
+        if ((rc = node_forward(P, P->dec[s], tr, mask(P->dec[s]), st, &skip, &up))) return rc;
+      } else {
+        RUN(kUpsample, upsample_launch(view_of(P, P->u3, 0, c / 2), view_of(P, P->dcat[s], f, c / 2), st));
+        if ((rc = node_forward(P, P->dec[s], tr, mask(P->dec[s]), st))) return rc;
+      }
       if (s < (int)P->final_keep.size() && P->final_keep[s])  // x_i = final_dropouts[i](x_i), model.py:294
         RUN(kOther, mask_mul_launch(view_of(P, P->nodes[P->dec[s]].out), P->final_keep[s], p8(f), P->final_scale, st));
     }

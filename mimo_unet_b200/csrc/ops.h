@@ -26,7 +26,11 @@ int conv3x3_flat2_launch(const ActView& in, int mode, const bf16* wpacked, int c
                          float* stat_sum, float* stat_sq, const float* bias, int relu, cudaStream_t stream);
 bool conv3x3_c2_ok(const ActView& in, int mode, int cout);
 int conv3x3_c2_launch(const ActView& in, int mode, const bf16* wpacked, int cout, int cin_pitch, bf16* out, int out_cpitch,
-                      float* stat_sum, float* stat_sq, const float* bias, int relu, cudaStream_t stream, const ConvFuse* fuse = nullptr);
+                      float* stat_sum, float* stat_sq, const float* bias, int relu, cudaStream_t stream, const ConvFuse* fuse = nullptr,
+                      const ActView* in2 = nullptr);
+// in2 != nullptr: VIRTUAL CONCAT -- the conv input is cat([in, in2], channels) without the concatenated tensor existing: the K
+// loop reads the 64-channel chunks of `in` and then those of `in2` through separate tensor maps; wpacked must use the chunk-aligned
+// channel order (WeightPackJob gap_at = in.C, gap = round_up(in.C, 64) - in.C), cin_pitch accordingly.
 // pre_zeroed: the caller has already cleared dw_packed on `stream` (the executor clears all layers with one memset)
 int conv3x3_wgrad_launch(const ActView& dy, const ActView& x, float* dw_packed, int cin_pitch, cudaStream_t stream, bool pre_zeroed = false);
 bool conv3x3_wgrad_flat_ok(const ActView& dy, const ActView& x);
@@ -35,7 +39,9 @@ bool conv3x3_wgrad_flatk_ok(const ActView& dy, const ActView& x);
 int conv3x3_wgrad_flatk_launch(const ActView& dy, const ActView& x, float* dw_packed, int cin_pitch, cudaStream_t stream, bool pre_zeroed = false);
 // batched variants: one launch for many layers (the per-layer kernels are a few microseconds each; their launch gaps
 // cost more than their work)
-struct WeightPackJob { const float* w; bf16* wf; bf16* wd; int cout, cin, cin_pitch, cout_pitch; };
+// gap_at/gap (fprop pack only): packed input channel c' holds source channel c' (c' < gap_at) or c' - gap (c' >= gap_at + gap), zeros in
+// between: the chunk-aligned channel order of a virtual concat (conv3x3_c2_launch with a second input view)
+struct WeightPackJob { const float* w; bf16* wf; bf16* wd; int cout, cin, cin_pitch, cout_pitch; int gap_at, gap; };
 struct WgradUnpackJob { const float* packed; float* grad; int cout, cin, cin_pitch; };
 int weight_pack_batched_launch(const WeightPackJob* jobs, int n, cudaStream_t st);
 int wgrad_unpack_batched_launch(const WgradUnpackJob* jobs, int n, float scale, int accumulate, cudaStream_t st);

@@ -154,6 +154,12 @@ def test_teacher_forced_fullshape(name):
     # ------------------------------------------------------------------ forward, layer by layer
     for i, (nd, pre) in enumerate(nodes):
         xin, a1, o = dbg(nd + ".in"), dbg(nd + ".a1"), dbg(nd + ".out")
+        virtual = fused and nd.startswith("decoder") and f + c // 2 > 64
+        if virtual:
+            # inference with > 64 concat channels: the decoders read cat([x1_s, up(u3)]) as a VIRTUAL concat (the up-sampled
+            # core output exists once, not once per dcat buffer): rebuild the conv input from its two sources
+            up = bf16r(O.pad_to(O.upsample_bilinear2x_ac(dbg("core.up3.out")), xin.shape[2], xin.shape[3]))
+            xin = torch.cat([xin[:, :f], up], dim=1)
         w1, w2 = bf16r(sd[pre + "0.weight"]), bf16r(sd[pre + "3.weight"])
         # the M per-subnetwork encoders' second conv may write an unaligned concat slice: those layers keep the unfused path
         if fused:
@@ -175,6 +181,10 @@ def test_teacher_forced_fullshape(name):
         # the producers write the reflect halo of every conv input
         for buf in (".in", ".a1"):
             xp = plan.debug_tensor_padded(nd + buf)
+            if virtual and buf == ".in":   # only the skip slice of dcat is written
+                xp = xp[:, :f]
+                assert torch.equal(xp, F.pad(dbg(nd + buf)[:, :f], (1, 1, 1, 1), mode="reflect")), f"{nd}{buf} halo"
+                continue
             assert torch.equal(xp, F.pad(dbg(nd + buf), (1, 1, 1, 1), mode="reflect")), f"{nd}{buf} halo"
         if "in_convs" in nd or "down" in nd and "down4" not in nd:
             assert torch.equal(dbg(nd + ".pool"), F.max_pool2d(o, 2)), f"{nd} pool"   # bit exact
@@ -182,6 +192,8 @@ def test_teacher_forced_fullshape(name):
     ups = [("core.up1", "core.down4", 4 * c), ("core.up2", "core.up1", 2 * c), ("core.up3", "core.up2", c)] + \
           [(f"decoder.up4s.{s}", "core.up3", f) for s in range(S)]
     for nd, src, skip_c in ups:
+        if fused and nd.startswith("decoder") and f + c // 2 > 64:
+            continue   # virtual concat: checked through the decoder's first conv above
         xin = dbg(nd + ".in")
         ref = bf16r(O.pad_to(O.upsample_bilinear2x_ac(dbg(src + ".out")), xin.shape[2], xin.shape[3]))
         chk(f"upsample:{nd}", xin[:, skip_c:], ref)
