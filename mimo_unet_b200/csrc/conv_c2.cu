@@ -50,7 +50,9 @@ struct C2Params {
   int n_mitems, n_tiles_n, block_n;   // block_n = N of the pair's MMA (multiple of 16); each CTA stages block_n / 2 weight rows
   int cin_chunks, ks_last;            // 64-channel chunks; 16-channel k-steps that carry data in the last chunk
   int split, ks_split;                // virtual concat: chunks [0, split) come from the first input view (k-steps of its last chunk), the rest from the second
-  int seg_rows, seg_full, seg_rem;    // A segment: T*128 + 2*wb + 2 rows = seg_full boxes of 128 rows + one box of seg_rem rows
+  int seg_kh;                         // 0: one A segment per chunk serves all nine taps (T*128 + 2*wb + 2 rows); 1: one per (chunk, kh)
+                                      //    (T*128 + 2 rows, three kw taps): cheaper when 2*wb is large against T*128 (wide maps)
+  int seg_rows, seg_full, seg_rem;    // A segment rows = seg_full boxes of 128 rows + one box of seg_rem rows
   int a_slots, a_slot_bytes, b_slots, b_slot_bytes, b_tap_bytes;
   int acc_cols;                       // n_tiles_n * block_n: columns of the per-warp statistics accumulators
   int ko;                             // diagnostic knock-outs (env MIMO_C2_KO): 1 no MMAs, 2 no A loads, 4 no B loads, 8 no stats, 16 no stores, 32 no TMEM loads
@@ -131,23 +133,26 @@ conv3x3_c2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const long long p0 = ((long long)mi * 2 + rank) * (T * kBlockM) + p.origin;
       const int co0 = nt * p.block_n + (int)rank * b_rows;
       for (int cc = 0; cc < p.cin_chunks; ++cc) {
-        mbar_wait(&a_empty[sa], pa ^ 1);
-        if (elect_one()) {
-          uint8_t* st = smem_a + (size_t)sa * p.a_slot_bytes;
-          const uint32_t fb = a_full0 + (uint32_t)sa * 8u;
-          if (rank == 0) mbar_arrive_expect_tx(&a_full[sa], 2u * a_tx);
-          if (!(p.ko & 2)) {
-            const bool second = cc >= p.split;   // virtual concat: the chunk lives in the second input view
-            const CUtensorMap* m1 = second ? &tmap_b : &tmap_a;
-            const CUtensorMap* m2 = second ? &tmap_b2 : &tmap_a2;
-            const int ch0 = (second ? cc - p.split : cc) * 64;
-            for (int i = 0; i < p.seg_full; ++i) tma_load_2d_cg2(m1, fb, st + (size_t)i * (kBlockM * 128), ch0, (int)p0 + i * kBlockM);
-            if (p.seg_rem) tma_load_2d_cg2(m2, fb, st + (size_t)p.seg_full * (kBlockM * 128), ch0, (int)p0 + p.seg_full * kBlockM);
-          }
-        }
-        __syncwarp();
-        if (++sa == p.a_slots) { sa = 0; pa ^= 1; }
         for (int kh = 0; kh < 3; ++kh) {
+          if (p.seg_kh || kh == 0) {
+            mbar_wait(&a_empty[sa], pa ^ 1);
+            if (elect_one()) {
+              uint8_t* st = smem_a + (size_t)sa * p.a_slot_bytes;
+              const uint32_t fb = a_full0 + (uint32_t)sa * 8u;
+              if (rank == 0) mbar_arrive_expect_tx(&a_full[sa], 2u * a_tx);
+              if (!(p.ko & 2)) {
+                const bool second = cc >= p.split;   // virtual concat: the chunk lives in the second input view
+                const CUtensorMap* m1 = second ? &tmap_b : &tmap_a;
+                const CUtensorMap* m2 = second ? &tmap_b2 : &tmap_a2;
+                const int ch0 = (second ? cc - p.split : cc) * 64;
+                const int r0 = (int)p0 + (p.seg_kh ? kh * p.wb : 0);
+                for (int i = 0; i < p.seg_full; ++i) tma_load_2d_cg2(m1, fb, st + (size_t)i * (kBlockM * 128), ch0, r0 + i * kBlockM);
+                if (p.seg_rem) tma_load_2d_cg2(m2, fb, st + (size_t)p.seg_full * (kBlockM * 128), ch0, r0 + p.seg_full * kBlockM);
+              }
+            }
+            __syncwarp();
+            if (++sa == p.a_slots) { sa = 0; pa ^= 1; }
+          }
           mbar_wait(&b_empty[sb], pb ^ 1);
           if (elect_one()) {
             if (rank == 0) mbar_arrive_expect_tx(&b_full[sb], 2u * b_tx);
@@ -177,14 +182,18 @@ conv3x3_c2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         tc_fence_after();
         const uint32_t d0 = tmem_base + buf * (uint32_t)T * bn;
         for (int cc = 0; cc < p.cin_chunks; ++cc) {
-          mbar_wait(&a_full[sa], pa);
-          const uint32_t a_lo = a_lo0 + (uint32_t)sa * a_step;
+          if (!p.seg_kh) mbar_wait(&a_full[sa], pa);
+          uint32_t a_lo = a_lo0 + (uint32_t)sa * a_step;
           const uint32_t ks = (cc == p.cin_chunks - 1) ? (uint32_t)p.ks_last : (cc == p.split - 1 ? (uint32_t)p.ks_split : 4u);
           for (int kh = 0; kh < 3; ++kh) {
+            if (p.seg_kh) {
+              mbar_wait(&a_full[sa], pa);
+              a_lo = a_lo0 + (uint32_t)sa * a_step;
+            }
             mbar_wait(&b_full[sb], pb);
             tc_fence_after();
             const uint32_t b_lo = b_lo0 + (uint32_t)sb * b_step;
-            const uint32_t a_kh = a_lo + (uint32_t)(kh * p.wb) * 8u;   // 128 B per row = 8 descriptor units
+            const uint32_t a_kh = a_lo + (p.seg_kh ? 0u : (uint32_t)(kh * p.wb) * 8u);   // 128 B per row = 8 descriptor units
             if (elect_one()) {
               for (int t = 0; t < T; ++t) {
                 const uint32_t a_t = a_kh + (uint32_t)t * (kBlockM * 8u);
@@ -200,12 +209,13 @@ conv3x3_c2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 }
               }
               umma_commit2_mc(&b_empty[sb], 3);                 // frees the weight block in both CTAs
-              if (kh == 2) umma_commit2_mc(&a_empty[sa], 3);    // ... and the A segment after its last kernel row
+              if (p.seg_kh || kh == 2) umma_commit2_mc(&a_empty[sa], 3);    // ... and the A segment after its last use
             }
             __syncwarp();
             if (++sb == p.b_slots) { sb = 0; pb ^= 1; }
+            if (p.seg_kh && ++sa == p.a_slots) { sa = 0; pa ^= 1; }
           }
-          if (++sa == p.a_slots) { sa = 0; pa ^= 1; }
+          if (!p.seg_kh && ++sa == p.a_slots) { sa = 0; pa ^= 1; }
         }
         if (elect_one()) umma_commit2_mc(&tmem_full[buf], 3);
         __syncwarp();
@@ -356,9 +366,10 @@ void plan_n(int cout, int* block_n, int* n_tiles) {
 }
 
 // shared-memory plan for T tiles per CTA; returns false when it does not fit
-bool plan_smem(int T, int wb, int block_n, int acc_cols, C2Params* p, size_t* smem_bytes) {
+bool plan_smem(int T, int seg_kh, int wb, int block_n, int acc_cols, C2Params* p, size_t* smem_bytes) {
   p->T = T;
-  p->seg_rows = T * kBlockM + 2 * wb + 2;
+  p->seg_kh = seg_kh;
+  p->seg_rows = T * kBlockM + (seg_kh ? 2 : 2 * wb + 2);
   p->seg_full = p->seg_rows / kBlockM;
   p->seg_rem = p->seg_rows % kBlockM;
   p->a_slot_bytes = round_up(p->seg_rows * 128, 1024);
@@ -367,10 +378,10 @@ bool plan_smem(int T, int wb, int block_n, int acc_cols, C2Params* p, size_t* sm
   const int fixed = 8 * acc_cols * 4 + (2 * kMaxASlots + 2 * kMaxBSlots + 4) * 8 + 16 + 64 + 1024;
   const int budget = 227 * 1024 - fixed;
   // at least two A segments and three weight blocks in flight; then weight blocks up to 6, then a third A segment
-  int a_slots = 2, b_slots = 3;
+  int a_slots = seg_kh ? 3 : 2, b_slots = 3;
   if (a_slots * p->a_slot_bytes + b_slots * p->b_slot_bytes > budget) return false;
   while (b_slots < 6 && a_slots * p->a_slot_bytes + (b_slots + 1) * p->b_slot_bytes <= budget) ++b_slots;
-  while (a_slots < 3 && (a_slots + 1) * p->a_slot_bytes + b_slots * p->b_slot_bytes <= budget) ++a_slots;
+  while (a_slots < (seg_kh ? kMaxASlots : 3) && (a_slots + 1) * p->a_slot_bytes + b_slots * p->b_slot_bytes <= budget) ++a_slots;
   while (b_slots < kMaxBSlots && a_slots * p->a_slot_bytes + (b_slots + 1) * p->b_slot_bytes <= budget) ++b_slots;
   p->a_slots = a_slots;
   p->b_slots = b_slots;
@@ -391,7 +402,7 @@ bool conv3x3_c2_ok(const ActView& in, int mode, int cout) {
   plan_n(cout, &block_n, &n_tiles);
   C2Params p{};
   size_t smem_bytes;
-  return plan_smem(1, in.wb(), block_n, block_n * n_tiles, &p, &smem_bytes);
+  return plan_smem(1, 0, in.wb(), block_n, block_n * n_tiles, &p, &smem_bytes) || plan_smem(1, 1, in.wb(), block_n, block_n * n_tiles, &p, &smem_bytes);
 }
 
 int conv3x3_c2_launch(const ActView& in, int mode, const bf16* wpacked, int cout, int cin_pitch, bf16* out, int out_cpitch,
@@ -428,22 +439,27 @@ int conv3x3_c2_launch(const ActView& in, int mode, const bf16* wpacked, int cout
   size_t smem_bytes = 0;
   {
     static const int forced_t = env_int("MIMO_C2_T", 0);
-    int best_t = 0;
+    static const int forced_kh = env_int("MIMO_C2_SEGKH", -1);
+    int best_t = 0, best_kh = 0;
     double best = 1e300;
     for (int T = 1; T <= 4; T *= 2) {
       if (forced_t && T != forced_t) continue;
       if (2 * T * p.block_n > 512) continue;
-      C2Params q = p;
-      size_t sb;
-      if (!plan_smem(T, p.wb, p.block_n, p.acc_cols, &q, &sb)) continue;
-      const long long items = ceil_div_ll(p.total_pos, 2ll * T * kBlockM) * p.n_tiles_n;
-      const long long waves = ceil_div_ll(items, max_pairs);
-      const double rows_per_item = p.cin_chunks * ((double)q.seg_rows + 9.0 * (p.block_n / 2));   // TMA rows per CTA per item
-      const double cost = (double)waves * rows_per_item;
-      if (cost < best) { best = cost; best_t = T; }
+      for (int kh = 0; kh < 2; ++kh) {
+        if (forced_kh >= 0 && kh != forced_kh) continue;
+        C2Params q = p;
+        size_t sb;
+        if (!plan_smem(T, kh, p.wb, p.block_n, p.acc_cols, &q, &sb)) continue;
+        const long long items = ceil_div_ll(p.total_pos, 2ll * T * kBlockM) * p.n_tiles_n;
+        const long long waves = ceil_div_ll(items, max_pairs);
+        const double a_rows = kh ? 3.0 * q.seg_rows : (double)q.seg_rows;
+        const double rows_per_item = p.cin_chunks * (a_rows + 9.0 * (p.block_n / 2));   // TMA rows per CTA per item
+        const double cost = (double)waves * rows_per_item;
+        if (cost < best) { best = cost; best_t = T; best_kh = kh; }
+      }
     }
     MIMO_CHECK(best_t > 0, MIMO_ERR_ARG, "conv3x3_c2: not enough shared memory for block_n=%d, row pitch %d", p.block_n, p.wb);
-    plan_smem(best_t, p.wb, p.block_n, p.acc_cols, &p, &smem_bytes);
+    plan_smem(best_t, best_kh, p.wb, p.block_n, p.acc_cols, &p, &smem_bytes);
   }
   p.n_mitems = (int)ceil_div_ll(p.total_pos, 2ll * p.T * kBlockM);
   p.epi.block_n = p.block_n;
