@@ -117,14 +117,17 @@ __device__ __forceinline__ void relayout_chunk(uint32_t src, uint32_t dst, uint3
   }
 }
 
-template <int BN, int SETS>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128 * SETS + 32 * kLoaderWarps, 1)
+// CG = CTAs per MMA group: 2 = CTA pair (tcgen05 cta_group::2, launched as 2-CTA clusters), 1 = the same pipeline with
+// single-CTA MMAs (cta_group::1, no cluster) -- it keeps the bulk-copy + re-layout loader, whose per-row cost (none) is what
+// the TMA-tiled loader of conv_flat.cu is bound by.
+template <int BN, int SETS, int CG>
+__global__ void __launch_bounds__(64 + 128 * SETS + 32 * kLoaderWarps, 1)
 conv3x3_flat2_kernel(const __grid_constant__ CUtensorMap tmap_w, const Flat2Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [B: 9 x BN/2 x 128 B][ring: (S+1) x 16 KB][end-of-kernel statistics partials][barriers]
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_b = smem;
-  constexpr int b_tap_bytes = (BN / 2) * 128;     // BN/2 % 8 == 0 -> every tap starts 1024-byte aligned
+  constexpr int b_tap_bytes = (BN / CG) * 128;    // BN/CG % 8 == 0 -> every tap starts 1024-byte aligned
   constexpr int b_bytes = 9 * b_tap_bytes;
   uint8_t* smem_a = smem_b + ((b_bytes + 1023) & ~1023);
   uint8_t* smem_st = smem_a + (size_t)(p.slots + 1) * kChunkBytes;                           // staging ring
@@ -141,7 +144,7 @@ conv3x3_flat2_kernel(const __grid_constant__ CUtensorMap tmap_w, const Flat2Para
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
   constexpr uint32_t tmem_cols = (kAcc * BN <= 128) ? 128 : (kAcc * BN <= 256) ? 256 : 512;
 
   const int t_begin = blockIdx.x * p.tiles_per_cta;   // this CTA's contiguous tile range
@@ -158,11 +161,11 @@ conv3x3_flat2_kernel(const __grid_constant__ CUtensorMap tmap_w, const Flat2Para
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < S; ++s) {
-        mbar_init(&full_bar[s], 4);   // slot s of an even/odd chunk PAIR (index s/2 used): 2 chunks x 2 CTAs
+        mbar_init(&full_bar[s], 2 * CG);   // slot s of an even/odd chunk PAIR (index s/2 used): 2 chunks x CG CTAs
       }
       for (int a = 0; a < kAcc; ++a) {
         mbar_init(&tmem_full[a], 1);
-        mbar_init(&tmem_empty[a], 16);  // accumulator PAIR (index a/2 used): 2 tiles x 4 warps x 2 CTAs
+        mbar_init(&tmem_empty[a], 8 * CG);  // accumulator PAIR (index a/2 used): 2 tiles x 4 warps x CG CTAs
       }
       for (int a = 0; a < p.st_slots; ++a) {
         mbar_init(&st_full[a], 1);
@@ -172,20 +175,21 @@ conv3x3_flat2_kernel(const __grid_constant__ CUtensorMap tmap_w, const Flat2Para
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc2(tmem_ptr, tmem_cols);
-    tmem_relinquish2();
+    if constexpr (CG == 2) { tmem_alloc2(tmem_ptr, tmem_cols); tmem_relinquish2(); }
+    else { tmem_alloc(tmem_ptr, tmem_cols); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
-  cluster_sync_all();
+  if constexpr (CG == 2) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
     // ===================== resident weights: each CTA loads ITS half of the rows of all nine taps, once =====================
     if (elect_one()) {
-      if (rank == 0) mbar_arrive_expect_tx(b_full, 2u * (uint32_t)b_bytes);
-      tma_load_3d_cg2(&tmap_w, mapa_shared(smem_u32(b_full), 0), smem_b, 0, (int)rank * (BN / 2), 0);   // box (64 cin, BN/2 cout, 9 taps)
+      if (rank == 0) mbar_arrive_expect_tx(b_full, (uint32_t)CG * (uint32_t)b_bytes);
+      if constexpr (CG == 2) tma_load_3d_cg2(&tmap_w, mapa_shared(smem_u32(b_full), 0), smem_b, 0, (int)rank * (BN / 2), 0);   // box (64 cin, BN/2 cout, 9 taps)
+      else tma_load_3d(&tmap_w, b_full, smem_b, 0, 0, 0);
     }
     __syncwarp();
     // ===================== bulk-copy producer: chunk c = rows [128 (t_begin + c) + origin, +128) of the pixel list =====================
@@ -216,7 +220,7 @@ conv3x3_flat2_kernel(const __grid_constant__ CUtensorMap tmap_w, const Flat2Para
   } else if (warp == 1) {
     if (rank == 0) {
       // ===================== MMA issuer (leader CTA) =====================
-      const uint32_t idesc = make_idesc_bf16(2 * kBlockM, BN, 0, 0);
+      const uint32_t idesc = make_idesc_bf16(CG * kBlockM, BN, 0, 0);
       constexpr uint32_t hi = desc_hi(1024, kLayoutSW128);
       const uint32_t b_lo0 = desc_lo(smem_u32(smem_b), 16);
       const uint32_t a_lo0 = desc_lo(smem_u32(smem_a), 16);
@@ -265,15 +269,18 @@ conv3x3_flat2_kernel(const __grid_constant__ CUtensorMap tmap_w, const Flat2Para
                 const uint32_t a_lo = a_lo0 + r * 8;         // END past it continue into the mirror of slot 0
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                  if ((uint32_t)k < ks)
-                    umma2_bf16_w(d_addr, a_lo + k * 2, hi, b_lo0 + ((tap * b_tap_bytes + k * 32) >> 4), hi, idesc, (tap | k) != 0);
+                  if ((uint32_t)k < ks) {
+                    if constexpr (CG == 2) umma2_bf16_w(d_addr, a_lo + k * 2, hi, b_lo0 + ((tap * b_tap_bytes + k * 32) >> 4), hi, idesc, (tap | k) != 0);
+                    else umma_bf16_w(d_addr, a_lo + k * 2, hi, b_lo0 + ((tap * b_tap_bytes + k * 32) >> 4), hi, idesc, (tap | k) != 0);
+                  }
                 }
               }
             }
           }
           // ONE commit per tile pair: both accumulators complete -> both epilogue sets of both CTAs; it also tells the re-layout
           // warps that chunks i and i + 1 are dead
-          umma_commit2_mc(&tmem_full[2 * ap], 3);
+          if constexpr (CG == 2) umma_commit2_mc(&tmem_full[2 * ap], 3);
+          else umma_commit(&tmem_full[2 * ap]);
         }
         __syncwarp();
         if (tr) trow[3] = clock64();
@@ -452,10 +459,11 @@ conv3x3_flat2_kernel(const __grid_constant__ CUtensorMap tmap_w, const Flat2Para
 
   tc_fence_before();
   __syncthreads();
-  cluster_sync_all();
+  if constexpr (CG == 2) cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc2(tmem_base, tmem_cols);
+    if constexpr (CG == 2) tmem_dealloc2(tmem_base, tmem_cols);
+    else tmem_dealloc(tmem_base, tmem_cols);
   }
 }
 
@@ -465,8 +473,8 @@ int env_int(const char* name, int dflt) {
 }
 
 // shared-memory plan: operand ring of nc + 3 slots (+ mirror), the rest goes to the staging ring; false = does not fit
-bool plan_smem(int block_n, int sets, int nc, int st_bytes, int* slots, int* st_slots, size_t* smem_bytes) {
-  const int b_bytes = (9 * (block_n / 2) * 128 + 1023) & ~1023;
+bool plan_smem(int block_n, int cg, int sets, int nc, int st_bytes, int* slots, int* st_slots, size_t* smem_bytes) {
+  const int b_bytes = (9 * (block_n / cg) * 128 + 1023) & ~1023;
   const int fixed = b_bytes + 8 * sets * block_n * 4 + (2 * kMaxSlots + 2 * kMaxStage + 2 * kAcc + 1) * 8 + 16 + 64 + 1024 /*alignment slack*/;
   const int budget = 227 * 1024 - fixed;
   static const int s_extra = env_int("MIMO_FLAT2_SLACK", 4);
@@ -483,20 +491,47 @@ bool plan_smem(int block_n, int sets, int nc, int st_bytes, int* slots, int* st_
   return true;
 }
 
-template <int BN, int SETS>
+template <int BN, int SETS, int CG>
 int launch_flat2(const CUtensorMap& tm_w, const Flat2Params& p, size_t smem_bytes, int grid, cudaStream_t stream) {
-  MIMO_CUDA(cudaFuncSetAttribute(conv3x3_flat2_kernel<BN, SETS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  conv3x3_flat2_kernel<BN, SETS><<<grid, 64 + 128 * SETS + 32 * kLoaderWarps, smem_bytes, stream>>>(tm_w, p);
-  MIMO_LAUNCH_CHECK();
+  MIMO_CUDA(cudaFuncSetAttribute(conv3x3_flat2_kernel<BN, SETS, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3((unsigned)grid);
+  lc.blockDim = dim3(64 + 128 * SETS + 32 * kLoaderWarps);
+  lc.dynamicSmemBytes = smem_bytes;
+  lc.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CG;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  lc.attrs = at;
+  lc.numAttrs = CG == 2 ? 1 : 0;
+  MIMO_CUDA(cudaLaunchKernelEx(&lc, conv3x3_flat2_kernel<BN, SETS, CG>, tm_w, p));
   return MIMO_OK;
+}
+
+template <int CG>
+int dispatch_flat2(int block_n, const CUtensorMap& tm_w, const Flat2Params& p, size_t smem_bytes, int grid, cudaStream_t stream) {
+  switch (block_n) {
+    case 16: return launch_flat2<16, 2, CG>(tm_w, p, smem_bytes, grid, stream);
+    case 32: return launch_flat2<32, 2, CG>(tm_w, p, smem_bytes, grid, stream);
+    case 48: return launch_flat2<48, 2, CG>(tm_w, p, smem_bytes, grid, stream);
+    default: return launch_flat2<64, 1, CG>(tm_w, p, smem_bytes, grid, stream);
+  }
+}
+
+// 0: kernel not used; 1: single-CTA MMAs; 2: CTA pairs (env MIMO_CONV_FLAT2)
+int flat2_mode() {
+  static const int mode = env_int("MIMO_CONV_FLAT2", 0);
+  return mode;
 }
 
 }  // namespace
 
 bool conv3x3_flat2_ok(const ActView& in, int mode, int cout) {
-  // opt-in (MIMO_CONV_FLAT2=1): measured on B200 it only ties with conv_flat.cu inside the training step (profiles/r02_findings.md)
-  static const int enabled = env_int("MIMO_CONV_FLAT2", 0);
-  if (!enabled) return false;
+  // opt-in (MIMO_CONV_FLAT2 = 1 single-CTA MMAs, 2 CTA pairs): see profiles/r02_findings.md
+  if (flat2_mode() == 0) return false;
+  if (flat2_mode() == 1 && round_up(cout, 16) == 16) return false;   // (BN / CG must stay a multiple of 8 rows: fine; BN=16 untested here)
   if (in.C > 64 || round_up(cout, 16) > 64) return false;
   if (mode == 0 && in.pad != 1) return false;
   if (mode == 1 && in.pad != 2) return false;
@@ -505,12 +540,13 @@ bool conv3x3_flat2_ok(const ActView& in, int mode, int cout) {
   size_t smem;
   int slots, st_slots;
   const int bn = round_up(cout, 16);
-  return plan_smem(bn, bn <= 48 ? 2 : 1, ceil_div(2 * in.wb() + 130, 128), kBlockM * in.cpitch * 2, &slots, &st_slots, &smem);
+  return plan_smem(bn, flat2_mode() == 2 ? 2 : 1, bn <= 48 ? 2 : 1, ceil_div(2 * in.wb() + 130, 128), kBlockM * in.cpitch * 2, &slots, &st_slots, &smem);
 }
 
 int conv3x3_flat2_launch(const ActView& in, int mode, const bf16* wpacked, int cout, int cin_pitch, bf16* out, int out_cpitch,
                          float* stat_sum, float* stat_sq, const float* bias, int relu, cudaStream_t stream) {
   note_kernel(9);
+  const int CG = flat2_mode() == 2 ? 2 : 1;
   Flat2Params p{};
   const int block_n = round_up(cout, 16);
   const int sets = block_n <= 48 ? 2 : 1;   // 8 epilogue warps unless the per-thread statistics registers do not fit
@@ -542,7 +578,7 @@ int conv3x3_flat2_launch(const ActView& in, int mode, const bf16* wpacked, int c
   MIMO_CHECK(in.cpitch <= 64 && in.c_off == 0, MIMO_ERR_ARG, "conv3x3_flat2: needs a whole-pixel view with <= 64 channels per pixel");
   size_t smem_bytes = 0;
   p.st_bytes = kBlockM * in.cpitch * 2;
-  MIMO_CHECK(plan_smem(block_n, sets, p.nc, p.st_bytes, &p.slots, &p.st_slots, &smem_bytes), MIMO_ERR_ARG,
+  MIMO_CHECK(plan_smem(block_n, CG, sets, p.nc, p.st_bytes, &p.slots, &p.st_slots, &smem_bytes), MIMO_ERR_ARG,
              "conv3x3_flat2: ring of %d chunks does not fit shared memory (block_n=%d)", p.nc, block_n);
   p.epi.block_n = block_n;
   p.epi.cout = cout;
@@ -559,17 +595,11 @@ int conv3x3_flat2_launch(const ActView& in, int mode, const bf16* wpacked, int c
   {
     uint64_t dims[3] = {(uint64_t)cin_pitch, (uint64_t)cout, 9};
     uint64_t strides[2] = {(uint64_t)cin_pitch * 2, (uint64_t)cout * cin_pitch * 2};
-    uint32_t box[3] = {64, (uint32_t)(block_n / 2), 9};
+    uint32_t box[3] = {64, (uint32_t)(block_n / CG), 9};
     int rc = encode_tmap_bf16(&tm_w, wpacked, 3, dims, strides, box, 1);
     if (rc) return rc;
   }
-  int rc;
-  switch (block_n) {
-    case 16: rc = launch_flat2<16, 2>(tm_w, p, smem_bytes, grid, stream); break;
-    case 32: rc = launch_flat2<32, 2>(tm_w, p, smem_bytes, grid, stream); break;
-    case 48: rc = launch_flat2<48, 2>(tm_w, p, smem_bytes, grid, stream); break;
-    default: rc = launch_flat2<64, 1>(tm_w, p, smem_bytes, grid, stream); break;
-  }
+  const int rc = CG == 2 ? dispatch_flat2<2>(block_n, tm_w, p, smem_bytes, grid, stream) : dispatch_flat2<1>(block_n, tm_w, p, smem_bytes, grid, stream);
   if (rc == MIMO_OK && p.trace) {
     // diagnostic only (synchronises!): dump CTA 0's pipeline timeline relative to its first event
     static long long host[4 * 64 * 4];

@@ -547,14 +547,15 @@ def test_mask_mul_elementwise_dropout(lib, C_, c_off, cp, pad):
     assert torch.equal(after, before)
 
 
-def test_conv_flat2_opt_in_kernel_parity():
-    """The CTA-pair small-channel kernel (conv_flat2.cu) is opt-in (MIMO_CONV_FLAT2=1, read once per process): run the fprop / dgrad
-    parity cases in a subprocess with the switch on."""
+@pytest.mark.parametrize("mode", ["1", "2"])
+def test_conv_flat2_opt_in_kernel_parity(mode):
+    """The bulk-copy-loader small-channel kernel (conv_flat2.cu) is opt-in (MIMO_CONV_FLAT2 = 1 single-CTA MMAs, 2 CTA pairs; read
+    once per process): run the fprop / dgrad parity cases in a subprocess with the switch on."""
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, MIMO_CONV_FLAT2="1")
+    env = dict(os.environ, MIMO_CONV_FLAT2=mode)
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_kernels_gpu.py"), "-q", "-m", "gpu", "-x", "-p",
                         "no:cacheprovider", "-k", "test_weight_pack_and_conv_fprop or test_conv_dgrad"], capture_output=True, text=True,
                        env=env, cwd=root, timeout=600)
