@@ -31,13 +31,14 @@
 #include "conv_epilogue.cuh"
 #include "ops.h"
 
+#include <stdio.h>
 #include <stdlib.h>
 
 namespace mimo {
 namespace {
 
 constexpr int kBlockM = 128;                     // positions per tile
-constexpr int kThreads = 192;                    // warp 0 TMA, warp 1 TMEM + MMA (leader only), warps 2..5 epilogue
+constexpr int kThreads = 320;                    // warp 0 TMA, warp 1 TMEM + MMA (leader only), warps 2..9 epilogue
 constexpr int kMaxASlots = 4;
 constexpr int kMaxBSlots = 8;
 
@@ -47,6 +48,7 @@ struct C2Params {
   int origin;
   int out_h, out_w, n_img;
   int T;                              // tiles per CTA per item
+  int acc_stages;                     // 2: two TMEM accumulator sets of T tiles (epilogue overlaps the next item's MMAs); 1: one set
   int n_mitems, n_tiles_n, block_n;   // block_n = N of the pair's MMA (multiple of 16); each CTA stages block_n / 2 weight rows
   int cin_chunks, ks_last;            // 64-channel chunks; 16-channel k-steps that carry data in the last chunk
   int split, ks_split;                // virtual concat: chunks [0, split) come from the first input view (k-steps of its last chunk), the rest from the second
@@ -55,10 +57,15 @@ struct C2Params {
   int seg_rows, seg_full, seg_rem;    // A segment rows = seg_full boxes of 128 rows + one box of seg_rem rows
   int a_slots, a_slot_bytes, b_slots, b_slot_bytes, b_tap_bytes;
   int acc_cols;                       // n_tiles_n * block_n: columns of the per-warp statistics accumulators
+  long long* trace;                   // diagnostic (env MIMO_C2_TRACE=2): per-CTA cycle counters, 16 per CTA
   int ko;                             // diagnostic knock-outs (env MIMO_C2_KO): 1 no MMAs, 2 no A loads, 4 no B loads, 8 no stats, 16 no stores, 32 no TMEM loads
   EpiArgs epi;
 };
 
+// DIAG: knock-out bits and cycle trace compiled in (diagnostic launches only: every ko test in the single-warp roles is a
+// constant-bank load + branch on the critical path). EPI: 0 plain store (dgrad), 1 store + BatchNorm statistics (training fprop),
+// 2 generic (bias / fused inference affine, ReLU, Dropout2d factor, halo destination, optional statistics).
+template <bool DIAG, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv3x3_c2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2,
                   const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_b2,
@@ -74,16 +81,29 @@ conv3x3_c2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   uint64_t* b_full = a_empty + kMaxASlots;            // leader only
   uint64_t* b_empty = b_full + kMaxBSlots;            // per CTA (multicast commit)
   uint64_t* tmem_full = b_empty + kMaxBSlots;         // per CTA (multicast commit)
-  uint64_t* tmem_empty = tmem_full + 2;               // leader only: 4 epilogue warps x 2 CTAs
+  uint64_t* tmem_empty = tmem_full + 2;               // leader only: 8 epilogue warps x 2 CTAs
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
+  const int ko = DIAG ? p.ko : 0;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
+  // diagnostic: ko bit 64 = polling waits on the ring barriers, bit 128 = polling waits on the accumulator hand-over barriers
+  auto WAIT = [&](uint64_t* bar, uint32_t ph) { if (ko & 64) mbar_wait_poll(bar, ph); else mbar_wait(bar, ph); };
+  auto WAITX = [&](uint64_t* bar, uint32_t ph) { if (ko & 128) mbar_wait_poll(bar, ph); else mbar_wait(bar, ph); };
+  const bool tracing = DIAG && p.trace != nullptr;
+  long long tw0 = 0, tw1 = 0, tw2 = 0, twork = 0;
+  unsigned long long tcommit = 0, tidx = 0, tarrive = 0;   // cycles spent in the role's waits / work (lane 0 of each role reports them)
+  const long long t_begin = tracing ? clock64() : 0;
+  auto TW = [&](long long& acc, uint64_t* bar, uint32_t ph, bool x) {
+    const long long t0 = tracing ? clock64() : 0;
+    if (x) WAITX(bar, ph); else WAIT(bar, ph);
+    if (tracing) acc += clock64() - t0;
+  };
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
   const int n_items = p.n_mitems * p.n_tiles_n;
   const int T = p.T;
-  const uint32_t cols = 2u * (uint32_t)(T * p.block_n);   // double-buffered accumulators of T tiles
+  const uint32_t cols = (uint32_t)(p.acc_stages * T * p.block_n);   // accumulators of T tiles, double-buffered when 2 sets fit in 512 columns
   const uint32_t tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
 
   if (warp == 0 && lane == 0) {
@@ -105,7 +125,7 @@ conv3x3_c2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(&tmem_full[a], 1);
-        mbar_init(&tmem_empty[a], 8);
+        mbar_init(&tmem_empty[a], 16);
       }
       fence_barrier_init();
     }
@@ -123,8 +143,8 @@ conv3x3_c2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     // ===================== TMA producer (both CTAs; completion on the leader's barriers) =====================
     int sa = 0, sb = 0;
     uint32_t pa = 0, pb = 0;
-    const uint32_t a_tx = (p.ko & 2) ? 0u : (uint32_t)p.seg_rows * 128u;   // per CTA
-    const uint32_t b_tx = (p.ko & 4) ? 0u : 3u * (uint32_t)p.b_tap_bytes;
+    const uint32_t a_tx = (ko & 2) ? 0u : (uint32_t)p.seg_rows * 128u;   // per CTA
+    const uint32_t b_tx = (ko & 4) ? 0u : 3u * (uint32_t)p.b_tap_bytes;
     const uint32_t a_full0 = mapa_shared(smem_u32(a_full), 0);
     const uint32_t b_full0 = mapa_shared(smem_u32(b_full), 0);
     const int b_rows = p.block_n >> 1;
@@ -135,12 +155,12 @@ conv3x3_c2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       for (int cc = 0; cc < p.cin_chunks; ++cc) {
         for (int kh = 0; kh < 3; ++kh) {
           if (p.seg_kh || kh == 0) {
-            mbar_wait(&a_empty[sa], pa ^ 1);
+            TW(tw0, &a_empty[sa], pa ^ 1, false);
             if (elect_one()) {
               uint8_t* st = smem_a + (size_t)sa * p.a_slot_bytes;
               const uint32_t fb = a_full0 + (uint32_t)sa * 8u;
               if (rank == 0) mbar_arrive_expect_tx(&a_full[sa], 2u * a_tx);
-              if (!(p.ko & 2)) {
+              if (!(ko & 2)) {
                 const bool second = cc >= p.split;   // virtual concat: the chunk lives in the second input view
                 const CUtensorMap* m1 = second ? &tmap_b : &tmap_a;
                 const CUtensorMap* m2 = second ? &tmap_b2 : &tmap_a2;
@@ -153,10 +173,10 @@ conv3x3_c2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             __syncwarp();
             if (++sa == p.a_slots) { sa = 0; pa ^= 1; }
           }
-          mbar_wait(&b_empty[sb], pb ^ 1);
+          TW(tw1, &b_empty[sb], pb ^ 1, false);
           if (elect_one()) {
             if (rank == 0) mbar_arrive_expect_tx(&b_full[sb], 2u * b_tx);
-            if (!(p.ko & 4)) tma_load_3d_cg2(&tmap_w, b_full0 + (uint32_t)sb * 8u, smem_b + (size_t)sb * p.b_slot_bytes, cc * 64, co0, kh * 3);
+            if (!(ko & 4)) tma_load_3d_cg2(&tmap_w, b_full0 + (uint32_t)sb * 8u, smem_b + (size_t)sb * p.b_slot_bytes, cc * 64, co0, kh * 3);
           }
           __syncwarp();
           if (++sb == p.b_slots) { sb = 0; pb ^= 1; }
@@ -177,21 +197,22 @@ conv3x3_c2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       uint32_t pa = 0, pb = 0;
       uint32_t n = 0;
       for (int it = pair; it < n_items; it += n_pairs, ++n) {
-        const uint32_t buf = n & 1u;
-        mbar_wait(&tmem_empty[buf], ((n >> 1) & 1u) ^ 1u);
+        const uint32_t buf = p.acc_stages == 2 ? (n & 1u) : 0u;
+        TW(tw2, &tmem_empty[buf], ((p.acc_stages == 2 ? (n >> 1) : n) & 1u) ^ 1u, true);
         tc_fence_after();
         const uint32_t d0 = tmem_base + buf * (uint32_t)T * bn;
         for (int cc = 0; cc < p.cin_chunks; ++cc) {
-          if (!p.seg_kh) mbar_wait(&a_full[sa], pa);
+          if (!p.seg_kh) TW(tw0, &a_full[sa], pa, false);
           uint32_t a_lo = a_lo0 + (uint32_t)sa * a_step;
           const uint32_t ks = (cc == p.cin_chunks - 1) ? (uint32_t)p.ks_last : (cc == p.split - 1 ? (uint32_t)p.ks_split : 4u);
           for (int kh = 0; kh < 3; ++kh) {
             if (p.seg_kh) {
-              mbar_wait(&a_full[sa], pa);
+              TW(tw0, &a_full[sa], pa, false);
               a_lo = a_lo0 + (uint32_t)sa * a_step;
             }
-            mbar_wait(&b_full[sb], pb);
+            TW(tw1, &b_full[sb], pb, false);
             tc_fence_after();
+            const long long tq0 = tracing ? clock64() : 0;
             const uint32_t b_lo = b_lo0 + (uint32_t)sb * b_step;
             const uint32_t a_kh = a_lo + (p.seg_kh ? 0u : (uint32_t)(kh * p.wb) * 8u);   // 128 B per row = 8 descriptor units
             if (elect_one()) {
@@ -202,16 +223,19 @@ conv3x3_c2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 for (int kw = 0; kw < 3; ++kw) {
 #pragma unroll
                   for (int k = 0; k < 4; ++k) {
-                    if ((uint32_t)k < ks && !(p.ko & 1))
+                    if ((uint32_t)k < ks && !(ko & 1))
                       umma2_bf16_w(d_t, a_t + (uint32_t)(kw * 8 + k * 2), hi, b_lo + (uint32_t)kw * b_tap + (uint32_t)(k * 2), hi, idesc,
                                    (cc | kh | kw | k) != 0);
                   }
                 }
               }
+              const long long tc0 = tracing ? clock64() : 0;
               umma_commit2_mc(&b_empty[sb], 3);                 // frees the weight block in both CTAs
               if (p.seg_kh || kh == 2) umma_commit2_mc(&a_empty[sa], 3);    // ... and the A segment after its last use
+              if (tracing) tcommit += clock64() - tc0;
             }
             __syncwarp();
+            if (tracing) twork += clock64() - tq0;
             if (++sb == p.b_slots) { sb = 0; pb ^= 1; }
             if (p.seg_kh && ++sa == p.a_slots) { sa = 0; pa ^= 1; }
           }
@@ -222,111 +246,162 @@ conv3x3_c2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       }
     }
   } else {
-    // ===================== epilogue (4 warps per CTA, each CTA drains its own 128 accumulator rows per tile) =====================
+    // ===================== epilogue (8 warps per CTA, each CTA drains its own 128 accumulator rows per tile) =====================
+    // Two warps share a TMEM lane quarter and split the 16-column chunks (even / odd). A warp walks chunk-outer, tile-inner: the T
+    // loads of a chunk are in flight together, the per-channel vectors are read once per chunk, and the BatchNorm statistics are
+    // reduced across lanes once per chunk for all T tiles (the 32 shuffles of the two transposed butterflies were the largest part of
+    // the drain: ~900 cycles per chunk and tile with one warp per quarter, measured with MIMO_C2_TRACE=2).
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
+    const int grp = (warp - 2) >> 2;         // 0: even chunks, 1: odd chunks
     const int row = q * 32 + lane;
     const int et = threadIdx.x - 64;
     const EpiArgs& e = p.epi;
-    const bool stats = e.stat_sum != nullptr && !(p.ko & 8);
-    const int nchunks = p.block_n >> 4;
-    float* wacc_s = smem_acc + (size_t)q * 2 * p.acc_cols;
+    const bool stats = (EPI == 1 || (EPI == 2 && e.stat_sum != nullptr)) && !(ko & 8);
+    // loop invariants in registers (the parameter struct lives in the constant bank)
+    const int block_n = p.block_n, wb = p.wb, img_pix = p.img_pix, out_h = p.out_h, out_w = p.out_w, out_cpitch = e.out_cpitch;
+    const int out_cmax = EPI == 2 ? e.out_cmax : out_cpitch;
+    const int halo = EPI == 2 ? e.halo : 0;
+    const long long total_pos = p.total_pos;
+    bf16* const out = e.out;
+    const int n_tiles_n = p.n_tiles_n, acc_stages = p.acc_stages;
+    const int nchunks = block_n >> 4;
+    float* wacc_s = smem_acc + (size_t)q * 2 * p.acc_cols;   // shared by the two warps of the quarter (disjoint columns)
     float* wacc_q = wacc_s + p.acc_cols;
-    for (int i = lane; i < 2 * p.acc_cols; i += 32) wacc_s[i] = 0.f;
-    __syncwarp();
+    for (int i = et; i < 8 * p.acc_cols; i += 256) smem_acc[i] = 0.f;
+    named_bar_sync(1, 256);
     const uint32_t tempty0 = mapa_shared(smem_u32(tmem_empty), 0);
     uint32_t n = 0;
     for (int it = pair; it < n_items; it += n_pairs, ++n) {
-      const uint32_t buf = n & 1u;
-      const int mi = it / p.n_tiles_n, nt = it - mi * p.n_tiles_n;
-      const int co0 = nt * p.block_n;
-      mbar_wait(&tmem_full[buf], (n >> 1) & 1u);
-      tc_fence_after();
-#pragma unroll 1
-      for (int t = 0; t < T; ++t) {
-        const long long pos = (((long long)mi * 2 + rank) * T + t) * kBlockM + row;
-        bool valid = false;
-        size_t my_pix = 0;
-        unsigned img = 0;
-        if (pos < p.total_pos) {
-          const unsigned up = (unsigned)pos;
-          const unsigned ni = up / (unsigned)p.img_pix;
-          const unsigned rem = up - ni * (unsigned)p.img_pix;
-          const unsigned hp = rem / (unsigned)p.wb, wp = rem - hp * (unsigned)p.wb;
-          valid = (int)hp < p.out_h && (int)wp < p.out_w;
-          img = ni;
-          my_pix = e.halo ? ((size_t)ni * (p.out_h + 2) + hp + 1) * (p.out_w + 2) + wp + 1 : ((size_t)ni * p.out_h + hp) * p.out_w + wp;
-        }
-        const float* drow = (e.drop != nullptr && valid) ? e.drop + (size_t)img * e.cout : nullptr;
-        const float vmask = valid ? 1.f : 0.f;
-        bf16* dst = e.out + my_pix * e.out_cpitch + co0;
-        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (buf * (uint32_t)T + (uint32_t)t) * (uint32_t)p.block_n;
-#pragma unroll 1
-        for (int j = 0; j < nchunks; ++j) {
-          float v[16];
-          if (p.ko & 32) {
+      const uint32_t buf = acc_stages == 2 ? (n & 1u) : 0u;
+      const int mi = it / n_tiles_n, nt = it - mi * n_tiles_n;
+      const int co0 = nt * block_n;
+      // output pixel of this thread's row in each of the T tiles
+      const long long ti0 = tracing ? clock64() : 0;
+      bf16* dst[4];
+      const float* drow[4];
+      float vmask[4];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = (float)(i + j);
-          } else {
-            tmem_ld16(t_addr + j * 16, v);
-          }
-          if (e.scale != nullptr) {
-            // vec4 is set by the launcher when scale / shift hold round_up(cout, 16) floats per n-tile column range (the
-            // executor's BatchNorm vectors are padded with zeros up to the channel pitch) and are 16-byte aligned
-            const int c0 = co0 + j * 16;
-            if (e.relu & 2) {
-#pragma unroll
-              for (int i = 0; i < 16; i += 4) {
-                const float4 sc = __ldg(reinterpret_cast<const float4*>(e.scale + c0 + i));
-                const float4 sh = __ldg(reinterpret_cast<const float4*>(e.bias + c0 + i));
-                v[i] = fmaf(v[i], sc.x, sh.x); v[i + 1] = fmaf(v[i + 1], sc.y, sh.y);
-                v[i + 2] = fmaf(v[i + 2], sc.z, sh.z); v[i + 3] = fmaf(v[i + 3], sc.w, sh.w);
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = (c0 + i < e.cout) ? fmaf(v[i], __ldg(e.scale + c0 + i), __ldg(e.bias + c0 + i)) : 0.f;
+      for (int t = 0; t < 4; ++t) {
+        dst[t] = nullptr; drow[t] = nullptr; vmask[t] = 0.f;
+        if (t < T) {
+          const long long pos = (((long long)mi * 2 + rank) * T + t) * kBlockM + row;
+          if (pos < total_pos) {
+            const unsigned up = (unsigned)pos;
+            const unsigned ni = up / (unsigned)img_pix;
+            const unsigned rem = up - ni * (unsigned)img_pix;
+            const unsigned hp = rem / (unsigned)wb, wp = rem - hp * (unsigned)wb;
+            if ((int)hp < out_h && (int)wp < out_w) {
+              const size_t pix = halo ? ((size_t)ni * (out_h + 2) + hp + 1) * (out_w + 2) + wp + 1 : ((size_t)ni * out_h + hp) * out_w + wp;
+              dst[t] = out + pix * out_cpitch + co0;
+              vmask[t] = 1.f;
+              if (EPI == 2 && e.drop != nullptr) drow[t] = e.drop + (size_t)ni * e.cout;
             }
-          } else if (e.bias != nullptr) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += (co0 + j * 16 + i < e.cout) ? __ldg(e.bias + co0 + j * 16 + i) : 0.f;
-          }
-          if (e.relu & 1) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-          }
-          if (drow != nullptr) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] *= (co0 + j * 16 + i < e.cout) ? __ldg(drow + co0 + j * 16 + i) : 0.f;
-          }
-          const uint4 lo = pack8(v), hi8 = pack8(v + 8);
-          if (valid && !(p.ko & 16)) {
-            if (co0 + j * 16 < e.out_cmax) *reinterpret_cast<uint4*>(dst + j * 16) = lo;
-            if (co0 + j * 16 + 8 < e.out_cmax) *reinterpret_cast<uint4*>(dst + j * 16 + 8) = hi8;
-          }
-          if (stats) {
-            float f[16];
-            unpack8(lo, f);
-            unpack8(hi8, f + 8);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] *= vmask;   // statistics of the values as stored; unstored rows count as 0
-            const float cs = warp_colsum16(f, lane);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] *= f[i];
-            const float cq = warp_colsum16(f, lane);
-            // lane l holds column (l >> 1): even lanes keep the sums, odd lanes the squares (private per-warp accumulators)
-            const int col = co0 + j * 16 + (lane >> 1);
-            if ((lane & 1) == 0) wacc_s[col] += cs;
-            else wacc_q[col] += cq;
           }
         }
       }
+      if (tracing) tidx += clock64() - ti0;
+      TW(tw2, &tmem_full[buf], (acc_stages == 2 ? (n >> 1) : n) & 1u, true);
+      tc_fence_after();
+      const long long tq0 = tracing ? clock64() : 0;
+      const uint32_t t_addr0 = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)T * (uint32_t)block_n;
+#pragma unroll 1
+      for (int j = grp; j < nchunks; j += 2) {
+        const int c0 = co0 + j * 16;
+        uint32_t raw[4][16];
+        if (!(ko & 32)) {
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            if (t < T) tmem_ld16_nowait(t_addr0 + (uint32_t)t * (uint32_t)block_n + j * 16, raw[t]);
+          tmem_ld_wait();
+        }
+        // per-channel vectors of this chunk (fused inference epilogue / bias): vec4 is set by the launcher when scale / shift hold
+        // round_up(cout, 16) floats per n-tile column range (the executor's BatchNorm vectors are zero-padded up to the channel pitch)
+        float sc[16], sh[16];
+        const bool affine = EPI == 2 && e.scale != nullptr;
+        const bool biased = EPI == 2 && !affine && e.bias != nullptr;
+        const bool relu = EPI == 2 && (e.relu & 1);
+        if (affine) {
+          if (e.relu & 2) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              const float4 a = __ldg(reinterpret_cast<const float4*>(e.scale + c0 + i));
+              const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + c0 + i));
+              sc[i] = a.x; sc[i + 1] = a.y; sc[i + 2] = a.z; sc[i + 3] = a.w;
+              sh[i] = b.x; sh[i + 1] = b.y; sh[i + 2] = b.z; sh[i + 3] = b.w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              sc[i] = (c0 + i < e.cout) ? __ldg(e.scale + c0 + i) : 0.f;
+              sh[i] = (c0 + i < e.cout) ? __ldg(e.bias + c0 + i) : 0.f;
+            }
+          }
+        } else if (biased) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) sh[i] = (c0 + i < e.cout) ? __ldg(e.bias + c0 + i) : 0.f;
+        }
+        float ssum[16], ssq[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { ssum[i] = 0.f; ssq[i] = 0.f; }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          if (t < T) {
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = (ko & 32) ? (float)(i + j) : __uint_as_float(raw[t][i]);
+            if (affine) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], sc[i], sh[i]);
+            } else if (biased) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] += sh[i];
+            }
+            if (relu) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+            }
+            if (EPI == 2 && drow[t] != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] *= (c0 + i < e.cout) ? __ldg(drow[t] + c0 + i) : 0.f;
+            }
+            const uint4 lo = pack8(v), hi8 = pack8(v + 8);
+            if (dst[t] != nullptr && !(ko & 16)) {
+              if (c0 < out_cmax) *reinterpret_cast<uint4*>(dst[t] + j * 16) = lo;
+              if (c0 + 8 < out_cmax) *reinterpret_cast<uint4*>(dst[t] + j * 16 + 8) = hi8;
+            }
+            if (stats) {
+              // statistics of the values as stored (bf16); rows that are not stored count as 0
+              float f[16];
+              unpack8(lo, f);
+              unpack8(hi8, f + 8);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float x = f[i] * vmask[t];
+                ssum[i] += x;
+                ssq[i] = fmaf(x, x, ssq[i]);
+              }
+            }
+          }
+        }
+        if (stats) {
+          const float cs = warp_colsum16(ssum, lane);
+          const float cq = warp_colsum16(ssq, lane);
+          // lane l holds column (l >> 1): even lanes keep the sums, odd lanes the squares (accumulators private to the quarter's chunk owner)
+          const int col = c0 + (lane >> 1);
+          if ((lane & 1) == 0) wacc_s[col] += cs;
+          else wacc_q[col] += cq;
+        }
+      }
+      const long long ta0 = tracing ? clock64() : 0;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tempty0 + buf * 8u);
+      if (tracing) { twork += ta0 - tq0; tarrive += clock64() - ta0; }
     }
     if (stats) {
-      // combine the four warps (fixed order) and write this CTA's partial row
-      named_bar_sync(1, 128);
-      for (int col = et; col < e.out_cpitch; col += 128) {
+      // combine the four quarters (fixed order) and write this CTA's partial row
+      named_bar_sync(1, 256);
+      for (int col = et; col < e.out_cpitch; col += 256) {
         float s_ = 0.f, q_ = 0.f;
         if (col < p.acc_cols) {
 #pragma unroll
@@ -345,6 +420,12 @@ conv3x3_c2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
   }
 
+  if (tracing && lane == 0 && warp <= 2) {
+    long long* tr = p.trace + (size_t)blockIdx.x * 16 + warp * 5;
+    tr[0] = clock64() - t_begin; tr[1] = tw0; tr[2] = tw1; tr[3] = tw2; tr[4] = twork;
+    if (warp == 2) { p.trace[(size_t)blockIdx.x * 16 + 15] = (long long)tidx; p.trace[(size_t)blockIdx.x * 16 + 11] = (long long)tarrive; }
+  }
+  if (tracing && warp == 1 && tcommit) atomicAdd(reinterpret_cast<unsigned long long*>(p.trace + (size_t)blockIdx.x * 16 + 12), tcommit);
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();   // no CTA frees its tensor memory / exits while the pair's MMAs or remote arrives may still target it
@@ -440,11 +521,16 @@ int conv3x3_c2_launch(const ActView& in, int mode, const bf16* wpacked, int cout
   {
     static const int forced_t = env_int("MIMO_C2_T", 0);
     static const int forced_kh = env_int("MIMO_C2_SEGKH", -1);
-    int best_t = 0, best_kh = 0;
+    static const int allow_single = env_int("MIMO_C2_SINGLE", 1);
+    int best_t = 0, best_kh = 0, best_stages = 2;
     double best = 1e300;
     for (int T = 1; T <= 4; T *= 2) {
       if (forced_t && T != forced_t) continue;
-      if (2 * T * p.block_n > 512) continue;
+      if (T * p.block_n > 512) continue;
+      // two accumulator sets (the epilogue of one item overlaps the MMAs of the next) when they fit in the 512 TMEM columns,
+      // else one set: wide outputs (block_n > 128) then still get T = 2 and halve their weight traffic
+      const int stages = 2 * T * p.block_n <= 512 ? 2 : 1;
+      if (stages == 1 && !allow_single) continue;
       for (int kh = 0; kh < 2; ++kh) {
         if (forced_kh >= 0 && kh != forced_kh) continue;
         C2Params q = p;
@@ -454,12 +540,23 @@ int conv3x3_c2_launch(const ActView& in, int mode, const bf16* wpacked, int cout
         const long long waves = ceil_div_ll(items, max_pairs);
         const double a_rows = kh ? 3.0 * q.seg_rows : (double)q.seg_rows;
         const double rows_per_item = p.cin_chunks * (a_rows + 9.0 * (p.block_n / 2));   // TMA rows per CTA per item
-        const double cost = (double)waves * rows_per_item;
-        if (cost < best) { best = cost; best_t = T; best_kh = kh; }
+        // cycles per item: TMA delivers ~20 B/cycle/SM (6.4 cycles per 128-byte row), a pair MMA costs max(N/2, 40) cycles, the
+        // epilogue ~5 cycles per accumulator column and tile (exposed only with a single accumulator set)
+        const double k_steps = 4.0 * (p.cin_chunks - 1 - (in2 != nullptr ? 1 : 0)) + p.ks_last + (in2 != nullptr ? p.ks_split : 0);
+        const double load = 6.4 * rows_per_item;
+        const double mma = (double)T * 9.0 * k_steps * (p.block_n / 2 > 40 ? p.block_n / 2 : 40);
+        const double epi = stages == 1 ? 5.0 * T * p.block_n : 0.0;
+        const double cost = (double)waves * ((load > mma ? load : mma) + epi);
+        if (cost < best) { best = cost; best_t = T; best_kh = kh; best_stages = stages; }
       }
     }
     MIMO_CHECK(best_t > 0, MIMO_ERR_ARG, "conv3x3_c2: not enough shared memory for block_n=%d, row pitch %d", p.block_n, p.wb);
     plan_smem(best_t, best_kh, p.wb, p.block_n, p.acc_cols, &p, &smem_bytes);
+    p.acc_stages = best_stages;
+    static const int trace = env_int("MIMO_C2_TRACE", 0);
+    if (trace)
+      fprintf(stderr, "c2 plan: mode %d cin %d cout %d pos %lld wb %d -> block_n %d x %d, T %d, seg_kh %d, acc_stages %d, a_slots %d b_slots %d\n", mode, in.C,
+              cout, p.total_pos, p.wb, p.block_n, p.n_tiles_n, p.T, p.seg_kh, p.acc_stages, p.a_slots, p.b_slots);
   }
   p.n_mitems = (int)ceil_div_ll(p.total_pos, 2ll * p.T * kBlockM);
   p.epi.block_n = p.block_n;
@@ -497,11 +594,34 @@ int conv3x3_c2_launch(const ActView& in, int mode, const bf16* wpacked, int cout
     int rc = encode_tmap_bf16(&tm_w, wpacked, 3, dims, strides, box, 1);
     if (rc) return rc;
   }
-  MIMO_CUDA(cudaFuncSetAttribute(conv3x3_c2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  static const int trace_mode = env_int("MIMO_C2_TRACE", 0);
+  const bool diag = p.ko != 0 || trace_mode == 2;
+  const int epi = (fuse != nullptr || bias != nullptr || relu != 0) ? 2 : (stat_sum != nullptr ? 1 : 0);
+  using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const C2Params);
+  static const KernelFn table[2][3] = {{conv3x3_c2_kernel<false, 0>, conv3x3_c2_kernel<false, 1>, conv3x3_c2_kernel<false, 2>},
+                                       {conv3x3_c2_kernel<true, 0>, conv3x3_c2_kernel<true, 1>, conv3x3_c2_kernel<true, 2>}};
+  const KernelFn kernel = table[diag ? 1 : 0][epi];
+  MIMO_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   const int items = p.n_mitems * p.n_tiles_n;
   const int grid = 2 * (items < max_pairs ? items : max_pairs);
-  conv3x3_c2_kernel<<<grid, kThreads, smem_bytes, stream>>>(tm_a, tm_a2, tm_b, tm_b2, tm_w, p);
+  static long long* trace_buf = nullptr;
+  if (trace_mode == 2) {   // diagnostic only: synchronous, not graph-capturable
+    if (!trace_buf) MIMO_CUDA(cudaMalloc(&trace_buf, 512 * 16 * sizeof(long long)));
+    MIMO_CUDA(cudaMemsetAsync(trace_buf, 0, 512 * 16 * sizeof(long long), stream));
+    p.trace = trace_buf;
+  }
+  kernel<<<grid, kThreads, smem_bytes, stream>>>(tm_a, tm_a2, tm_b, tm_b2, tm_w, p);
   MIMO_LAUNCH_CHECK();
+  if (trace_mode == 2) {
+    static long long host[512 * 16];
+    MIMO_CUDA(cudaStreamSynchronize(stream));
+    MIMO_CUDA(cudaMemcpy(host, trace_buf, sizeof(host), cudaMemcpyDeviceToHost));
+    for (int b : {0, 1, grid / 2, grid / 2 + 1, grid - 2, grid - 1}) {
+      const long long* t = host + (size_t)b * 16;
+      fprintf(stderr, "c2 trace cta %3d: loader total %lld wait a_empty %lld b_empty %lld | issuer total %lld wait a_full %lld b_full %lld tmem_empty %lld issue %lld | "
+                      "epilogue(w2) total %lld wait tmem_full %lld work %lld idx %lld arrive %lld | commits %lld\n", b, t[0], t[1], t[2], t[5], t[6], t[7], t[8], t[9], t[10], t[13], t[14], t[15], t[11], t[12]);
+    }
+  }
   return MIMO_OK;
 }
 

@@ -14,6 +14,14 @@ namespace {
 
 constexpr int kBlock = 256;
 
+// MIMO_ELEM_REV=1 (default 0): the BN apply pass and the second BN-backward pass walk their tensors back to front, hoping for L2
+// reuse between a producer's tail and the consumer's head. Measured on B200 (C2, tools/gpu/r2_rev.sh): 8.351 -> 8.342 ms/step, i.e.
+// nothing: a 126 MB streaming write does not leave a useful tail in L2. Kept as an experiment knob.
+inline int elementwise_reverse() {
+  static const int v = [] { const char* e = getenv("MIMO_ELEM_REV"); return e ? atoi(e) : 0; }();
+  return v;
+}
+
 inline int grid_for(long long work) {
   long long g = ceil_div_ll(work, kBlock);
   const long long cap = (long long)num_sms() * 16;
@@ -224,7 +232,7 @@ template <bool VEC_O, bool VEC_P>
 __global__ void __launch_bounds__(256, 2)
 bn_relu_apply_kernel(const bf16* __restrict__ y, int ycp, const float* __restrict__ scale,
                      const float* __restrict__ shift, const float* __restrict__ drop /*[N][C] or null*/,
-                     ActView o, ActView pool, int do_pool) {
+                     ActView o, ActView pool, int do_pool, int rev) {
   const int cells_h = (o.H + 1) >> 1, cells_w = (o.W + 1) >> 1;
   const int groups = (o.C + 7) >> 3;
   const int lanes = blockDim.x / groups;
@@ -236,7 +244,10 @@ bn_relu_apply_kernel(const bf16* __restrict__ y, int ycp, const float* __restric
 #pragma unroll
   for (int k = 0; k < 8; ++k) { sc[k] = (k < nv) ? scale[c + k] : 0.f; sh[k] = (k < nv) ? shift[c + k] : 0.f; }
   const int cell_rows = o.N * cells_h;
-  for (int cr = blockIdx.x; cr < cell_rows; cr += gridDim.x) {
+  for (int cr0 = blockIdx.x; cr0 < cell_rows; cr0 += gridDim.x) {
+    // rev: walk the tensor back to front, so the rows the producing convolution wrote LAST (still in L2) are read first and
+    // the rows written last here are the ones the consuming convolution reads first
+    const int cr = rev ? cell_rows - 1 - cr0 : cr0;
     const int n = cr / cells_h, chh = cr - n * cells_h;
     const int h0 = chh * 2;
     const bool row1 = h0 + 1 < o.H;
@@ -960,6 +971,7 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint
 struct BulkArgs {
   const bf16* G; const bf16* y;   // dense [rows][W][cp]; fold mode: G = padded-domain gradient [N][H+2][W+2][cp]
   int fold;                       // 1: the upstream gradient is fold_reflect(G) (adjoint of the reflect halo), formed on the fly
+  int rev;                        // 1: walk the chunks back to front (pass 2 then starts on the data pass 1 left in L2)
   int capG;                       // bytes of the G part of a stage
   int cp, C, W, H, rows;          // rows = N*H
   int rows_per_chunk, segs, seg_w, n_chunks;
@@ -1015,8 +1027,9 @@ bn_bwd_bulk_kernel(const BulkArgs a) {
   }
   __syncthreads();
   const int my_n = (a.n_chunks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  auto chunk_of = [&](int i) { const int k = blockIdx.x + i * gridDim.x; return a.rev ? a.n_chunks - 1 - k : k; };
   if (threadIdx.x == 0)
-    for (int i = 0; i < kBulkStages && i < my_n; ++i) issue(blockIdx.x + i * gridDim.x, i);
+    for (int i = 0; i < kBulkStages && i < my_n; ++i) issue(chunk_of(i), i);
 
   float sc[8], sf[8], ca[8], cb[8], a1[8], a2[8];
 #pragma unroll
@@ -1033,7 +1046,7 @@ bn_bwd_bulk_kernel(const BulkArgs a) {
 
   int stage = 0; uint32_t phase = 0;
   for (int i = 0; i < my_n; ++i) {
-    const int chunk = blockIdx.x + i * gridDim.x;
+    const int chunk = chunk_of(i);
     int row0, w0, npx_rows, npx_w;
     if (a.fold) { row0 = chunk; w0 = 0; npx_w = W; npx_rows = 1; }
     else if (a.segs > 1) { row0 = chunk / a.segs; const int sg = chunk - row0 * a.segs; w0 = sg * a.seg_w; npx_w = min(a.seg_w, W - w0); npx_rows = 1; }
@@ -1103,7 +1116,7 @@ bn_bwd_bulk_kernel(const BulkArgs a) {
       }
     }
     __syncthreads();   // every thread is done with this stage: refill it
-    if (threadIdx.x == 0 && i + kBulkStages < my_n) issue(blockIdx.x + (i + kBulkStages) * gridDim.x, stage);
+    if (threadIdx.x == 0 && i + kBulkStages < my_n) issue(chunk_of(i + kBulkStages), stage);
     if (++stage == kBulkStages) { stage = 0; phase ^= 1; }
   }
   if (MODE == 0) {
@@ -1305,10 +1318,10 @@ int bn_relu_apply_launch(const bf16* y, int ycp, const float* scale, const float
   const int cell_rows = o.N * ((o.H + 1) / 2);
   const int grid = cell_rows < 8 * num_sms() ? cell_rows : 8 * num_sms();
   const bool vo = view_store_vec_ok(o), vp = view_store_vec_ok(pv);
-  if (vo && vp) bn_relu_apply_kernel<true, true><<<grid, kBlock, 0, st>>>(y, ycp, scale, shift, drop, o, pv, pool ? 1 : 0);
-  else if (vo) bn_relu_apply_kernel<true, false><<<grid, kBlock, 0, st>>>(y, ycp, scale, shift, drop, o, pv, pool ? 1 : 0);
-  else if (vp) bn_relu_apply_kernel<false, true><<<grid, kBlock, 0, st>>>(y, ycp, scale, shift, drop, o, pv, pool ? 1 : 0);
-  else bn_relu_apply_kernel<false, false><<<grid, kBlock, 0, st>>>(y, ycp, scale, shift, drop, o, pv, pool ? 1 : 0);
+  if (vo && vp) bn_relu_apply_kernel<true, true><<<grid, kBlock, 0, st>>>(y, ycp, scale, shift, drop, o, pv, pool ? 1 : 0, elementwise_reverse());
+  else if (vo) bn_relu_apply_kernel<true, false><<<grid, kBlock, 0, st>>>(y, ycp, scale, shift, drop, o, pv, pool ? 1 : 0, elementwise_reverse());
+  else if (vp) bn_relu_apply_kernel<false, true><<<grid, kBlock, 0, st>>>(y, ycp, scale, shift, drop, o, pv, pool ? 1 : 0, elementwise_reverse());
+  else bn_relu_apply_kernel<false, false><<<grid, kBlock, 0, st>>>(y, ycp, scale, shift, drop, o, pv, pool ? 1 : 0, elementwise_reverse());
   MIMO_LAUNCH_CHECK();
   return MIMO_OK;
 }
@@ -1462,6 +1475,7 @@ int bn_bwd_launch(const ActView& G, const bf16* y, int ycp, const float* scale, 
       MIMO_LAUNCH_CHECK();
       bn_bwd_finalize_kernel<<<ceil_div(C, 8), 256, 0, st>>>(part, grid, C, s1s2, dgamma, dbeta, dbias, scale, mean, invstd, training, grad_scale, accumulate);
       MIMO_LAUNCH_CHECK();
+      a.rev = elementwise_reverse();
       bn_bwd_bulk_kernel<1><<<grid, kBlock, smem, st>>>(a);
       MIMO_LAUNCH_CHECK();
       return MIMO_OK;
