@@ -56,6 +56,8 @@ struct C2Params {
                                       //    (T*128 + 2 rows, three kw taps): cheaper when 2*wb is large against T*128 (wide maps)
   int seg_rows, seg_full, seg_rem;    // A segment rows = seg_full boxes of 128 rows + one box of seg_rem rows
   int a_slots, a_slot_bytes, b_slots, b_slot_bytes, b_tap_bytes;
+  int b_resident;                     // 1: all 3 * cin_chunks weight blocks of the pair's n-tile stay in shared memory for the whole kernel
+                                      //    (thin-K layers: no weight streaming, no per-block barrier / commit); b_slots = 3 * cin_chunks
   int acc_cols;                       // n_tiles_n * block_n: columns of the per-warp statistics accumulators
   long long* trace;                   // diagnostic (env MIMO_C2_TRACE=2): per-CTA cycle counters, 16 per CTA
   int ko;                             // diagnostic knock-outs (env MIMO_C2_KO): 1 no MMAs, 2 no A loads, 4 no B loads, 8 no stats, 16 no stores, 32 no TMEM loads
@@ -119,7 +121,8 @@ conv3x3_c2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         mbar_init(&a_full[s], 1);
         mbar_init(&a_empty[s], 1);
       }
-      for (int s = 0; s < p.b_slots; ++s) {
+      const int b_bars = p.b_resident ? 1 : p.b_slots;
+      for (int s = 0; s < b_bars; ++s) {
         mbar_init(&b_full[s], 1);
         mbar_init(&b_empty[s], 1);
       }
@@ -148,6 +151,18 @@ conv3x3_c2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const uint32_t a_full0 = mapa_shared(smem_u32(a_full), 0);
     const uint32_t b_full0 = mapa_shared(smem_u32(b_full), 0);
     const int b_rows = p.block_n >> 1;
+    if (p.b_resident && pair < n_items) {
+      // the launcher makes n_pairs a multiple of n_tiles_n: every item of this pair has the same n-tile -> one weight load per kernel
+      const int co0 = (pair % p.n_tiles_n) * p.block_n + (int)rank * b_rows;
+      if (elect_one()) {
+        if (rank == 0) mbar_arrive_expect_tx(&b_full[0], 2u * b_tx * 3u * (uint32_t)p.cin_chunks);
+        if (!(ko & 4))
+          for (int cc = 0; cc < p.cin_chunks; ++cc)
+            for (int kh = 0; kh < 3; ++kh)
+              tma_load_3d_cg2(&tmap_w, b_full0, smem_b + (size_t)(cc * 3 + kh) * p.b_slot_bytes, cc * 64, co0, kh * 3);
+      }
+      __syncwarp();
+    }
     for (int it = pair; it < n_items; it += n_pairs) {
       const int mi = it / p.n_tiles_n, nt = it - mi * p.n_tiles_n;
       const long long p0 = ((long long)mi * 2 + rank) * (T * kBlockM) + p.origin;
@@ -173,6 +188,7 @@ conv3x3_c2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             __syncwarp();
             if (++sa == p.a_slots) { sa = 0; pa ^= 1; }
           }
+          if (p.b_resident) continue;
           TW(tw1, &b_empty[sb], pb ^ 1, false);
           if (elect_one()) {
             if (rank == 0) mbar_arrive_expect_tx(&b_full[sb], 2u * b_tx);
@@ -196,6 +212,11 @@ conv3x3_c2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       uint32_t n = 0;
+      const bool resident = p.b_resident != 0;
+      if (resident && pair < n_items) {
+        TW(tw1, &b_full[0], 0, false);
+        tc_fence_after();
+      }
       for (int it = pair; it < n_items; it += n_pairs, ++n) {
         const uint32_t buf = p.acc_stages == 2 ? (n & 1u) : 0u;
         TW(tw2, &tmem_empty[buf], ((p.acc_stages == 2 ? (n >> 1) : n) & 1u) ^ 1u, true);
@@ -210,10 +231,10 @@ conv3x3_c2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               TW(tw0, &a_full[sa], pa, false);
               a_lo = a_lo0 + (uint32_t)sa * a_step;
             }
-            TW(tw1, &b_full[sb], pb, false);
+            if (!resident) TW(tw1, &b_full[sb], pb, false);
             tc_fence_after();
             const long long tq0 = tracing ? clock64() : 0;
-            const uint32_t b_lo = b_lo0 + (uint32_t)sb * b_step;
+            const uint32_t b_lo = b_lo0 + (uint32_t)(resident ? cc * 3 + kh : sb) * b_step;
             const uint32_t a_kh = a_lo + (p.seg_kh ? 0u : (uint32_t)(kh * p.wb) * 8u);   // 128 B per row = 8 descriptor units
             if (elect_one()) {
               for (int t = 0; t < T; ++t) {
@@ -230,13 +251,13 @@ conv3x3_c2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 }
               }
               const long long tc0 = tracing ? clock64() : 0;
-              umma_commit2_mc(&b_empty[sb], 3);                 // frees the weight block in both CTAs
+              if (!resident) umma_commit2_mc(&b_empty[sb], 3);   // frees the weight block in both CTAs
               if (p.seg_kh || kh == 2) umma_commit2_mc(&a_empty[sa], 3);    // ... and the A segment after its last use
               if (tracing) tcommit += clock64() - tc0;
             }
             __syncwarp();
             if (tracing) twork += clock64() - tq0;
-            if (++sb == p.b_slots) { sb = 0; pb ^= 1; }
+            if (!resident && ++sb == p.b_slots) { sb = 0; pb ^= 1; }
             if (p.seg_kh && ++sa == p.a_slots) { sa = 0; pa ^= 1; }
           }
           if (!p.seg_kh && ++sa == p.a_slots) { sa = 0; pa ^= 1; }
@@ -440,14 +461,15 @@ int env_int(const char* name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 
-void plan_n(int cout, int* block_n, int* n_tiles) {
+// n-tiling of the output channels: `split` = 1 is the coarsest tiling (fewest n-tiles with block_n <= 256), 2 halves the tiles
+void plan_n(int cout, int split, int* block_n, int* n_tiles) {
   const int c16 = round_up(cout, 16);
-  *n_tiles = ceil_div(c16, 256);
+  *n_tiles = ceil_div(c16, 256) * split;
   *block_n = round_up(ceil_div(c16, *n_tiles), 16);
 }
 
 // shared-memory plan for T tiles per CTA; returns false when it does not fit
-bool plan_smem(int T, int seg_kh, int wb, int block_n, int acc_cols, C2Params* p, size_t* smem_bytes) {
+bool plan_smem(int T, int seg_kh, int wb, int block_n, int acc_cols, int resident_blocks, C2Params* p, size_t* smem_bytes) {
   p->T = T;
   p->seg_kh = seg_kh;
   p->seg_rows = T * kBlockM + (seg_kh ? 2 : 2 * wb + 2);
@@ -456,14 +478,22 @@ bool plan_smem(int T, int seg_kh, int wb, int block_n, int acc_cols, C2Params* p
   p->a_slot_bytes = round_up(p->seg_rows * 128, 1024);
   p->b_tap_bytes = (block_n / 2) * 128;
   p->b_slot_bytes = round_up(3 * p->b_tap_bytes, 1024);
+  p->b_resident = resident_blocks > 0 ? 1 : 0;
   const int fixed = 8 * acc_cols * 4 + (2 * kMaxASlots + 2 * kMaxBSlots + 4) * 8 + 16 + 64 + 1024;
   const int budget = 227 * 1024 - fixed;
-  // at least two A segments and three weight blocks in flight; then weight blocks up to 6, then a third A segment
   int a_slots = seg_kh ? 3 : 2, b_slots = 3;
-  if (a_slots * p->a_slot_bytes + b_slots * p->b_slot_bytes > budget) return false;
-  while (b_slots < 6 && a_slots * p->a_slot_bytes + (b_slots + 1) * p->b_slot_bytes <= budget) ++b_slots;
-  while (a_slots < (seg_kh ? kMaxASlots : 3) && (a_slots + 1) * p->a_slot_bytes + b_slots * p->b_slot_bytes <= budget) ++a_slots;
-  while (b_slots < kMaxBSlots && a_slots * p->a_slot_bytes + (b_slots + 1) * p->b_slot_bytes <= budget) ++b_slots;
+  if (resident_blocks > 0) {
+    // every weight block of the n-tile resident; the rest of the memory is the A ring
+    b_slots = resident_blocks;
+    if (a_slots * p->a_slot_bytes + b_slots * p->b_slot_bytes > budget) return false;
+    while (a_slots < kMaxASlots && (a_slots + 1) * p->a_slot_bytes + b_slots * p->b_slot_bytes <= budget) ++a_slots;
+  } else {
+    // at least two A segments and three weight blocks in flight; then weight blocks up to 6, then a third A segment
+    if (a_slots * p->a_slot_bytes + b_slots * p->b_slot_bytes > budget) return false;
+    while (b_slots < 6 && a_slots * p->a_slot_bytes + (b_slots + 1) * p->b_slot_bytes <= budget) ++b_slots;
+    while (a_slots < (seg_kh ? kMaxASlots : 3) && (a_slots + 1) * p->a_slot_bytes + b_slots * p->b_slot_bytes <= budget) ++a_slots;
+    while (b_slots < kMaxBSlots && a_slots * p->a_slot_bytes + (b_slots + 1) * p->b_slot_bytes <= budget) ++b_slots;
+  }
   p->a_slots = a_slots;
   p->b_slots = b_slots;
   *smem_bytes = (size_t)a_slots * p->a_slot_bytes + (size_t)b_slots * p->b_slot_bytes + fixed;
@@ -480,10 +510,10 @@ bool conv3x3_c2_ok(const ActView& in, int mode, int cout) {
   const long long total_pos = (long long)in.N * in.hb() * in.wb();
   if (total_pos >= (1ll << 31) - 65536) return false;
   int block_n, n_tiles;
-  plan_n(cout, &block_n, &n_tiles);
+  plan_n(cout, 1, &block_n, &n_tiles);
   C2Params p{};
   size_t smem_bytes;
-  return plan_smem(1, 0, in.wb(), block_n, block_n * n_tiles, &p, &smem_bytes) || plan_smem(1, 1, in.wb(), block_n, block_n * n_tiles, &p, &smem_bytes);
+  return plan_smem(1, 0, in.wb(), block_n, block_n * n_tiles, 0, &p, &smem_bytes) || plan_smem(1, 1, in.wb(), block_n, block_n * n_tiles, 0, &p, &smem_bytes);
 }
 
 int conv3x3_c2_launch(const ActView& in, int mode, const bf16* wpacked, int cout, int cin_pitch, bf16* out, int out_cpitch,
@@ -498,8 +528,6 @@ int conv3x3_c2_launch(const ActView& in, int mode, const bf16* wpacked, int cout
   p.out_h = mode == 0 ? in.H : in.H + 2;
   p.out_w = mode == 0 ? in.W : in.W + 2;
   p.n_img = in.N;
-  plan_n(cout, &p.block_n, &p.n_tiles_n);
-  p.acc_cols = p.block_n * p.n_tiles_n;
   { static const int ko = env_int("MIMO_C2_KO", 0); p.ko = ko; }
   p.cin_chunks = ceil_div(in.C, 64);
   p.ks_last = ceil_div(in.C - (p.cin_chunks - 1) * 64, 16);
@@ -513,50 +541,69 @@ int conv3x3_c2_launch(const ActView& in, int mode, const bf16* wpacked, int cout
     p.ks_last = ceil_div(in2->C - (c2chunks - 1) * 64, 16);
     MIMO_CHECK(cin_pitch >= p.split * 64 + in2->C, MIMO_ERR_ARG, "conv3x3_c2: weight pitch %d too small for the chunk-aligned virtual concat", cin_pitch);
   }
-  MIMO_CHECK((p.block_n / 2) % 8 == 0, MIMO_ERR_ARG, "conv3x3_c2: block_n/2 must be a multiple of 8");
-  // tiles per CTA: more tiles share one weight block and one segment halo (fewer bytes through TMA per FLOP) but make the
-  // items coarser (wave quantisation over the 74 CTA pairs). Pick the T with the lowest modelled cost.
+  // Plan: n-tiling (coarsest, or halved so that a thin-K layer's weights fit), weights streamed through a ring or RESIDENT, tiles per
+  // CTA T (more tiles share one weight block and one segment halo: fewer bytes through TMA per FLOP, but coarser items: wave
+  // quantisation over the 74 CTA pairs), A segment mode. Pick the combination with the lowest modelled cost.
   const int max_pairs = num_sms() / 2;
   size_t smem_bytes = 0;
   {
     static const int forced_t = env_int("MIMO_C2_T", 0);
     static const int forced_kh = env_int("MIMO_C2_SEGKH", -1);
-    static const int allow_single = env_int("MIMO_C2_SINGLE", 1);
-    int best_t = 0, best_kh = 0, best_stages = 2;
+    static const int allow_single = env_int("MIMO_C2_SINGLE", 0);
+    static const int allow_resident = env_int("MIMO_C2_RESIDENT", 1);
+    struct Choice { int T, kh, stages, split, resident; };
+    Choice bestc{0, 0, 2, 1, 0};
     double best = 1e300;
-    for (int T = 1; T <= 4; T *= 2) {
-      if (forced_t && T != forced_t) continue;
-      if (T * p.block_n > 512) continue;
-      // two accumulator sets (the epilogue of one item overlaps the MMAs of the next) when they fit in the 512 TMEM columns,
-      // else one set: wide outputs (block_n > 128) then still get T = 2 and halve their weight traffic
-      const int stages = 2 * T * p.block_n <= 512 ? 2 : 1;
-      if (stages == 1 && !allow_single) continue;
-      for (int kh = 0; kh < 2; ++kh) {
-        if (forced_kh >= 0 && kh != forced_kh) continue;
-        C2Params q = p;
-        size_t sb;
-        if (!plan_smem(T, kh, p.wb, p.block_n, p.acc_cols, &q, &sb)) continue;
-        const long long items = ceil_div_ll(p.total_pos, 2ll * T * kBlockM) * p.n_tiles_n;
-        const long long waves = ceil_div_ll(items, max_pairs);
-        const double a_rows = kh ? 3.0 * q.seg_rows : (double)q.seg_rows;
-        const double rows_per_item = p.cin_chunks * (a_rows + 9.0 * (p.block_n / 2));   // TMA rows per CTA per item
-        // cycles per item: TMA delivers ~20 B/cycle/SM (6.4 cycles per 128-byte row), a pair MMA costs max(N/2, 40) cycles, the
-        // epilogue ~5 cycles per accumulator column and tile (exposed only with a single accumulator set)
-        const double k_steps = 4.0 * (p.cin_chunks - 1 - (in2 != nullptr ? 1 : 0)) + p.ks_last + (in2 != nullptr ? p.ks_split : 0);
-        const double load = 6.4 * rows_per_item;
-        const double mma = (double)T * 9.0 * k_steps * (p.block_n / 2 > 40 ? p.block_n / 2 : 40);
-        const double epi = stages == 1 ? 5.0 * T * p.block_n : 0.0;
-        const double cost = (double)waves * ((load > mma ? load : mma) + epi);
-        if (cost < best) { best = cost; best_t = T; best_kh = kh; best_stages = stages; }
+    const double k_steps = 4.0 * (p.cin_chunks - 1 - (in2 != nullptr ? 1 : 0)) + p.ks_last + (in2 != nullptr ? p.ks_split : 0);
+    for (int split = 1; split <= 2; ++split) {
+      int block_n, n_tiles;
+      plan_n(cout, split, &block_n, &n_tiles);
+      if ((block_n / 2) % 8 != 0 || (n_tiles - 1) * block_n >= out_cpitch) continue;
+      for (int resident = 0; resident <= (allow_resident ? 1 : 0); ++resident) {
+        if (split == 2 && !resident) continue;                 // halving the n-tiles only pays when it makes the weights resident
+        if (resident && max_pairs % n_tiles != 0) continue;   // a pair must keep one n-tile for the whole kernel
+        // measured (tools/gpu/r2_c2.sh): with three or more K chunks the resident weights leave room for T = 1 only and the per-item
+        // overheads eat the saved weight traffic (168 -> 84 @ 64x80: 99 us streamed, 106 us resident)
+        if (resident && p.cin_chunks > 2) continue;
+        for (int T = 1; T <= 4; T *= 2) {
+          if (forced_t && T != forced_t) continue;
+          if (T * block_n > 512) continue;
+          // two accumulator sets (the epilogue of one item overlaps the MMAs of the next) when they fit in the 512 TMEM columns
+          const int stages = 2 * T * block_n <= 512 ? 2 : 1;
+          if (stages == 1 && !allow_single) continue;
+          for (int kh = 0; kh < 2; ++kh) {
+            if (forced_kh >= 0 && kh != forced_kh) continue;
+            C2Params q = p;
+            size_t sb;
+            if (!plan_smem(T, kh, p.wb, block_n, block_n * n_tiles, resident ? 3 * p.cin_chunks : 0, &q, &sb)) continue;
+            const long long items = ceil_div_ll(p.total_pos, 2ll * T * kBlockM) * n_tiles;
+            const long long waves = ceil_div_ll(items, max_pairs);
+            const double a_rows = kh ? 3.0 * q.seg_rows : (double)q.seg_rows;
+            const double b_rows = 9.0 * (block_n / 2);
+            // cycles per item: TMA delivers ~20 B/cycle/SM (6.4 cycles per 128-byte row), a pair MMA costs max(N/2, 40) cycles, a
+            // tcgen05.commit ~400 cycles of the issuing thread, the epilogue ~5 cycles per accumulator column and tile (exposed only
+            // with a single accumulator set)
+            const double load = 6.4 * p.cin_chunks * (a_rows + (resident ? 0.0 : b_rows));
+            const double mma = (double)T * 9.0 * k_steps * (block_n / 2 > 40 ? block_n / 2 : 40);
+            const double issue = 400.0 * (p.cin_chunks * ((kh ? 3.0 : 1.0) + (resident ? 0.0 : 3.0)) + 1.0) + (double)T * 9.0 * k_steps * 16.0;
+            const double epi = stages == 1 ? 5.0 * T * block_n : 0.0;
+            double item = load > mma ? load : mma;
+            if (issue > item) item = issue;
+            const double cost = (double)waves * (item + epi) + (resident ? 6.4 * p.cin_chunks * b_rows : 0.0);
+            if (cost < best) { best = cost; bestc = Choice{T, kh, stages, split, resident}; }
+          }
+        }
       }
     }
-    MIMO_CHECK(best_t > 0, MIMO_ERR_ARG, "conv3x3_c2: not enough shared memory for block_n=%d, row pitch %d", p.block_n, p.wb);
-    plan_smem(best_t, best_kh, p.wb, p.block_n, p.acc_cols, &p, &smem_bytes);
-    p.acc_stages = best_stages;
+    MIMO_CHECK(bestc.T > 0, MIMO_ERR_ARG, "conv3x3_c2: not enough shared memory for cout=%d, row pitch %d", cout, p.wb);
+    plan_n(cout, bestc.split, &p.block_n, &p.n_tiles_n);
+    p.acc_cols = p.block_n * p.n_tiles_n;
+    plan_smem(bestc.T, bestc.kh, p.wb, p.block_n, p.acc_cols, bestc.resident ? 3 * p.cin_chunks : 0, &p, &smem_bytes);
+    p.acc_stages = bestc.stages;
     static const int trace = env_int("MIMO_C2_TRACE", 0);
     if (trace)
-      fprintf(stderr, "c2 plan: mode %d cin %d cout %d pos %lld wb %d -> block_n %d x %d, T %d, seg_kh %d, acc_stages %d, a_slots %d b_slots %d\n", mode, in.C,
-              cout, p.total_pos, p.wb, p.block_n, p.n_tiles_n, p.T, p.seg_kh, p.acc_stages, p.a_slots, p.b_slots);
+      fprintf(stderr, "c2 plan: mode %d cin %d cout %d pos %lld wb %d -> block_n %d x %d, T %d, seg_kh %d, acc_stages %d, resident %d, a_slots %d b_slots %d\n",
+              mode, in.C, cout, p.total_pos, p.wb, p.block_n, p.n_tiles_n, p.T, p.seg_kh, p.acc_stages, p.b_resident, p.a_slots, p.b_slots);
   }
   p.n_mitems = (int)ceil_div_ll(p.total_pos, 2ll * p.T * kBlockM);
   p.epi.block_n = p.block_n;
@@ -603,7 +650,7 @@ int conv3x3_c2_launch(const ActView& in, int mode, const bf16* wpacked, int cout
   const KernelFn kernel = table[diag ? 1 : 0][epi];
   MIMO_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   const int items = p.n_mitems * p.n_tiles_n;
-  const int grid = 2 * (items < max_pairs ? items : max_pairs);
+  const int grid = 2 * (items < max_pairs ? items : max_pairs);   // items and max_pairs are multiples of n_tiles_n in resident mode
   static long long* trace_buf = nullptr;
   if (trace_mode == 2) {   // diagnostic only: synchronous, not graph-capturable
     if (!trace_buf) MIMO_CUDA(cudaMalloc(&trace_buf, 512 * 16 * sizeof(long long)));

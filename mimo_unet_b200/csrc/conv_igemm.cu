@@ -231,6 +231,17 @@ int conv3x3_stat_rows() { return num_sms(); }
 //                            mode 1 (dgrad): pad == 0, output domain = (in.H+2) x (in.W+2)
 // wpacked : bf16 [9][cout][cin_pitch] (cin contiguous), cin_pitch multiple of 8
 // out     : bf16 [N][out_h][out_w][out_cpitch]
+// Small-channel layers that the CTA-pair kernel serves better than conv3x3_flat_kernel (measured, tools/gpu/r2_c2flat.sh): with a
+// narrow row pitch four tiles per CTA share one segment halo (64 x 80 maps: 37 -> 30 us, 35 -> 29 us), and with more than 32
+// input or output channels the pair MMA (39 cycles for 256 rows at small N) beats the 43-cycle fixed cost per single-CTA MMA
+// (63 -> 31 @ 128 x 160: 94 -> 83 us, its dgrad 117 -> 97 us). Wide full-resolution maps with <= 32 channels stay on the flat
+// kernel: there the 2 (W + 2) + 2 halo rows per segment cost more than the instruction shape gains (21 -> 21: 79 vs 85 us).
+static bool prefer_c2(const ActView& in, int mode, int cout) {
+  static const int enabled = getenv("MIMO_C2_SMALL") ? atoi(getenv("MIMO_C2_SMALL")) : 1;
+  if (!enabled || !conv3x3_c2_ok(in, mode, cout)) return false;
+  return 2 * in.wb() + 2 <= 256 || in.C > 32 || cout > 32;
+}
+
 bool conv3x3_fuse_ok(const ActView& in, int cout) {
   if (conv3x3_flat2_ok(in, 0, cout)) return false;   // (the opt-in experiment has no fused epilogue)
   return conv3x3_flat_ok(in, 0, cout) || conv3x3_c2_ok(in, 0, cout);
@@ -247,7 +258,7 @@ int conv3x3_launch(const ActView& in, int mode, const bf16* wpacked, int cout, i
              "conv3x3: pointers must be 16-byte aligned");
   MIMO_CHECK(in.H >= 2 && in.W >= 2, MIMO_ERR_ARG, "conv3x3: reflect padding needs H,W >= 2");
   if (fuse != nullptr) {
-    if (conv3x3_flat_ok(in, mode, cout) && !conv3x3_flat2_ok(in, mode, cout))
+    if (conv3x3_flat_ok(in, mode, cout) && !conv3x3_flat2_ok(in, mode, cout) && !prefer_c2(in, mode, cout))
       return conv3x3_flat_launch(in, mode, wpacked, cout, cin_pitch, out, out_cpitch, stat_sum, stat_sq, bias, relu, stream, fuse);
     if (conv3x3_c2_ok(in, mode, cout))
       return conv3x3_c2_launch(in, mode, wpacked, cout, cin_pitch, out, out_cpitch, stat_sum, stat_sq, bias, relu, stream, fuse);
@@ -256,7 +267,7 @@ int conv3x3_launch(const ActView& in, int mode, const bf16* wpacked, int cout, i
   }
   if (conv3x3_flat2_ok(in, mode, cout))
     return conv3x3_flat2_launch(in, mode, wpacked, cout, cin_pitch, out, out_cpitch, stat_sum, stat_sq, bias, relu, stream);
-  if (conv3x3_flat_ok(in, mode, cout))
+  if (conv3x3_flat_ok(in, mode, cout) && !prefer_c2(in, mode, cout))
     return conv3x3_flat_launch(in, mode, wpacked, cout, cin_pitch, out, out_cpitch, stat_sum, stat_sq, bias, relu, stream);
   if (conv3x3_c2_ok(in, mode, cout))
     return conv3x3_c2_launch(in, mode, wpacked, cout, cin_pitch, out, out_cpitch, stat_sum, stat_sq, bias, relu, stream);

@@ -2,6 +2,10 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <mutex>
+#include <string>
+#include <unordered_map>
+
 #include "common.cuh"
 
 namespace mimo {
@@ -54,10 +58,36 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// Encoded maps are a pure function of (base, rank, dims, strides, box, swizzle): eager launches (no CUDA graph: profiling, dropout
+// masks, the component-level entry points) re-use them instead of paying five driver calls per convolution launch.
+namespace {
+struct TmapCache {
+  std::mutex mu;
+  std::unordered_map<std::string, CUtensorMap> map;
+};
+TmapCache& tmap_cache() {
+  static TmapCache c;
+  return c;
+}
+}  // namespace
+
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                      const uint32_t* box, int swizzle128) {
   EncodeTiledFn fn = get_encode_fn();
   MIMO_CHECK(fn != nullptr, MIMO_ERR_CUDA, "cuTensorMapEncodeTiled driver entry point not available");
+  MIMO_CHECK(rank >= 1 && rank <= 5, MIMO_ERR_ARG, "encode_tmap: rank %d", rank);
+  struct Key { const void* base; int rank, swz; uint64_t dims[5], strides[4]; uint32_t box[5]; } key;
+  memset(&key, 0, sizeof(key));
+  key.base = base; key.rank = rank; key.swz = swizzle128;
+  for (int i = 0; i < rank; ++i) { key.dims[i] = dims[i]; key.box[i] = box[i]; if (i + 1 < rank) key.strides[i] = strides_bytes[i]; }
+  const std::string k(reinterpret_cast<const char*>(&key), sizeof(key));
+  {
+    TmapCache& c = tmap_cache();
+    std::lock_guard<std::mutex> lock(c.mu);
+    auto it = c.map.find(k);
+    if (it != c.map.end()) { *out = it->second; return MIMO_OK; }
+    if (c.map.size() > 8192) c.map.clear();   // bounded: a plan uses a few hundred maps
+  }
   cuuint64_t gdim[5];
   cuuint64_t gstr[4];
   cuuint32_t bdim[5], estr[5];
@@ -76,6 +106,11 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
               (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0), box[0],
               rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0, (unsigned long long)strides_bytes[0]);
     return MIMO_ERR_CUDA;
+  }
+  {
+    TmapCache& c = tmap_cache();
+    std::lock_guard<std::mutex> lock(c.mu);
+    c.map.emplace(k, *out);
   }
   return MIMO_OK;
 }
