@@ -66,7 +66,8 @@ struct C2Params {
 
 // DIAG: knock-out bits and cycle trace compiled in (diagnostic launches only: every ko test in the single-warp roles is a
 // constant-bank load + branch on the critical path). EPI: 0 plain store (dgrad), 1 store + BatchNorm statistics (training fprop),
-// 2 generic (bias / fused inference affine, ReLU, Dropout2d factor, halo destination, optional statistics).
+// 2 generic (bias / affine, ReLU, Dropout2d factor, halo destination, optional statistics), 3 fused inference epilogue (16-byte aligned
+// affine vectors, ReLU, Dropout2d factor, halo destination, no statistics).
 template <bool DIAG, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv3x3_c2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2,
@@ -280,8 +281,8 @@ conv3x3_c2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const bool stats = (EPI == 1 || (EPI == 2 && e.stat_sum != nullptr)) && !(ko & 8);
     // loop invariants in registers (the parameter struct lives in the constant bank)
     const int block_n = p.block_n, wb = p.wb, img_pix = p.img_pix, out_h = p.out_h, out_w = p.out_w, out_cpitch = e.out_cpitch;
-    const int out_cmax = EPI == 2 ? e.out_cmax : out_cpitch;
-    const int halo = EPI == 2 ? e.halo : 0;
+    const int out_cmax = EPI >= 2 ? e.out_cmax : out_cpitch;
+    const int halo = EPI >= 2 ? e.halo : 0;
     const long long total_pos = p.total_pos;
     bf16* const out = e.out;
     const int n_tiles_n = p.n_tiles_n, acc_stages = p.acc_stages;
@@ -315,7 +316,7 @@ conv3x3_c2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               const size_t pix = halo ? ((size_t)ni * (out_h + 2) + hp + 1) * (out_w + 2) + wp + 1 : ((size_t)ni * out_h + hp) * out_w + wp;
               dst[t] = out + pix * out_cpitch + co0;
               vmask[t] = 1.f;
-              if (EPI == 2 && e.drop != nullptr) drow[t] = e.drop + (size_t)ni * e.cout;
+              if (EPI >= 2 && e.drop != nullptr) drow[t] = e.drop + (size_t)ni * e.cout;
             }
           }
         }
@@ -328,21 +329,14 @@ conv3x3_c2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll 1
       for (int j = grp; j < nchunks; j += 2) {
         const int c0 = co0 + j * 16;
-        uint32_t raw[4][16];
-        if (!(ko & 32)) {
-#pragma unroll
-          for (int t = 0; t < 4; ++t)
-            if (t < T) tmem_ld16_nowait(t_addr0 + (uint32_t)t * (uint32_t)block_n + j * 16, raw[t]);
-          tmem_ld_wait();
-        }
         // per-channel vectors of this chunk (fused inference epilogue / bias): vec4 is set by the launcher when scale / shift hold
         // round_up(cout, 16) floats per n-tile column range (the executor's BatchNorm vectors are zero-padded up to the channel pitch)
         float sc[16], sh[16];
-        const bool affine = EPI == 2 && e.scale != nullptr;
+        const bool affine = EPI == 3 || (EPI == 2 && e.scale != nullptr);
         const bool biased = EPI == 2 && !affine && e.bias != nullptr;
-        const bool relu = EPI == 2 && (e.relu & 1);
+        const bool relu = EPI >= 2 && (e.relu & 1);
         if (affine) {
-          if (e.relu & 2) {
+          if (EPI == 3 || (e.relu & 2)) {
 #pragma unroll
             for (int i = 0; i < 16; i += 4) {
               const float4 a = __ldg(reinterpret_cast<const float4*>(e.scale + c0 + i));
@@ -364,12 +358,19 @@ conv3x3_c2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         float ssum[16], ssq[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) { ssum[i] = 0.f; ssq[i] = 0.f; }
+        // two tiles at a time: their TMEM loads are in flight together (four would cost 32 more registers: spills at the 168 cap)
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
+          uint32_t raw[2][16];
+          if ((t & 1) == 0 && t < T && !(ko & 32)) {
+            tmem_ld16_nowait(t_addr0 + (uint32_t)t * (uint32_t)block_n + j * 16, raw[0]);
+            if (t + 1 < T) tmem_ld16_nowait(t_addr0 + (uint32_t)(t + 1) * (uint32_t)block_n + j * 16, raw[1]);
+            tmem_ld_wait();
+          }
           if (t < T) {
             float v[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = (ko & 32) ? (float)(i + j) : __uint_as_float(raw[t][i]);
+            for (int i = 0; i < 16; ++i) v[i] = (ko & 32) ? (float)(i + j) : __uint_as_float(raw[t & 1][i]);
             if (affine) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], sc[i], sh[i]);
@@ -381,7 +382,7 @@ conv3x3_c2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll
               for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
             }
-            if (EPI == 2 && drow[t] != nullptr) {
+            if (EPI >= 2 && drow[t] != nullptr) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) v[i] *= (c0 + i < e.cout) ? __ldg(drow[t] + c0 + i) : 0.f;
             }
@@ -643,10 +644,11 @@ int conv3x3_c2_launch(const ActView& in, int mode, const bf16* wpacked, int cout
   }
   static const int trace_mode = env_int("MIMO_C2_TRACE", 0);
   const bool diag = p.ko != 0 || trace_mode == 2;
-  const int epi = (fuse != nullptr || bias != nullptr || relu != 0) ? 2 : (stat_sum != nullptr ? 1 : 0);
+  const int epi = (fuse != nullptr && stat_sum == nullptr) ? 3 : (fuse != nullptr || bias != nullptr || relu != 0) ? 2 : (stat_sum != nullptr ? 1 : 0);
   using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const C2Params);
-  static const KernelFn table[2][3] = {{conv3x3_c2_kernel<false, 0>, conv3x3_c2_kernel<false, 1>, conv3x3_c2_kernel<false, 2>},
-                                       {conv3x3_c2_kernel<true, 0>, conv3x3_c2_kernel<true, 1>, conv3x3_c2_kernel<true, 2>}};
+  static const KernelFn table[2][4] = {
+      {conv3x3_c2_kernel<false, 0>, conv3x3_c2_kernel<false, 1>, conv3x3_c2_kernel<false, 2>, conv3x3_c2_kernel<false, 3>},
+      {conv3x3_c2_kernel<true, 0>, conv3x3_c2_kernel<true, 1>, conv3x3_c2_kernel<true, 2>, conv3x3_c2_kernel<true, 3>}};
   const KernelFn kernel = table[diag ? 1 : 0][epi];
   MIMO_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   const int items = p.n_mitems * p.n_tiles_n;
