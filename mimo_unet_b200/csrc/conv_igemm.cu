@@ -244,7 +244,7 @@ static bool prefer_c2(const ActView& in, int mode, int cout) {
 
 bool conv3x3_fuse_ok(const ActView& in, int cout) {
   if (conv3x3_flat2_ok(in, 0, cout)) return false;   // (the opt-in experiment has no fused epilogue)
-  return conv3x3_flat_ok(in, 0, cout) || conv3x3_c2_ok(in, 0, cout);
+  return conv3x3_thin_ok(in, 0, cout) || conv3x3_flat_ok(in, 0, cout) || conv3x3_c2_ok(in, 0, cout);
 }
 
 int conv3x3_launch(const ActView& in, int mode, const bf16* wpacked, int cout, int cin_pitch, bf16* out, int out_cpitch,
@@ -257,6 +257,8 @@ int conv3x3_launch(const ActView& in, int mode, const bf16* wpacked, int cout, i
   MIMO_CHECK(((uintptr_t)in.base % 16) == 0 && ((uintptr_t)wpacked % 16) == 0 && ((uintptr_t)out % 16) == 0, MIMO_ERR_ALIGN,
              "conv3x3: pointers must be 16-byte aligned");
   MIMO_CHECK(in.H >= 2 && in.W >= 2, MIMO_ERR_ARG, "conv3x3: reflect padding needs H,W >= 2");
+  if (conv3x3_thin_ok(in, mode, cout))
+    return conv3x3_thin_launch(in, wpacked, cout, cin_pitch, out, out_cpitch, stat_sum, stat_sq, bias, relu, stream, fuse);
   if (fuse != nullptr) {
     if (conv3x3_flat_ok(in, mode, cout) && !conv3x3_flat2_ok(in, mode, cout) && !prefer_c2(in, mode, cout))
       return conv3x3_flat_launch(in, mode, wpacked, cout, cin_pitch, out, out_cpitch, stat_sum, stat_sq, bias, relu, stream, fuse);

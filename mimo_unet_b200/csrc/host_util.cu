@@ -26,8 +26,9 @@ void note_kernel(int id) { g_last_kernel = id; }
 int last_kernel() { return g_last_kernel; }
 const char* conv_kernel_name(int id) {
   static const char* names[] = {"", "conv3x3_flat_kernel", "conv3x3_flatk_kernel", "conv3x3_igemm_kernel", "conv3x3_wgrad_flat_kernel",
-                                "conv3x3_wgrad_flatk_kernel", "conv3x3_wgrad_kernel", "conv3x3_c2_kernel", "conv3x3_wgrad_c2_kernel", "conv3x3_flat2_kernel", "conv3x3_wgrad_flat2_kernel"};
-  return (id >= 0 && id < 11) ? names[id] : "";
+                                "conv3x3_wgrad_flatk_kernel", "conv3x3_wgrad_kernel", "conv3x3_c2_kernel", "conv3x3_wgrad_c2_kernel", "conv3x3_flat2_kernel", "conv3x3_wgrad_flat2_kernel",
+                                "conv3x3_thin_kernel"};
+  return (id >= 0 && id < 12) ? names[id] : "";
 }
 
 int num_sms() {

@@ -32,6 +32,10 @@ int conv3x3_c2_launch(const ActView& in, int mode, const bf16* wpacked, int cout
 // loop reads the 64-channel chunks of `in` and then those of `in2` through separate tensor maps; wpacked must use the chunk-aligned
 // channel order (WeightPackJob gap_at = in.C, gap = round_up(in.C, 64) - in.C), cin_pitch accordingly.
 // pre_zeroed: the caller has already cleared dw_packed on `stream` (the executor clears all layers with one memset)
+// CUDA-core kernel of the first layer (<= 4 input channels, <= 32 output channels): conv_thin.cu
+bool conv3x3_thin_ok(const ActView& in, int mode, int cout);
+int conv3x3_thin_launch(const ActView& in, const bf16* wpacked, int cout, int cin_pitch, bf16* out, int out_cpitch, float* stat_sum,
+                        float* stat_sq, const float* bias, int relu, cudaStream_t stream, const ConvFuse* fuse = nullptr);
 int conv3x3_wgrad_launch(const ActView& dy, const ActView& x, float* dw_packed, int cin_pitch, cudaStream_t stream, bool pre_zeroed = false);
 bool conv3x3_wgrad_flat_ok(const ActView& dy, const ActView& x);
 int conv3x3_wgrad_flat_launch(const ActView& dy, const ActView& x, float* dw_packed, int cin_pitch, cudaStream_t stream, bool pre_zeroed = false);

@@ -41,6 +41,10 @@ CONV_CASES = [
     (2, 672, 336, 8, 10),
     (4, 64, 64, 64, 64),
     (2, 30, 45, 2, 3),
+    # first-layer shapes (<= 4 input, <= 32 output channels): the CUDA-core kernels of conv_thin.cu (fprop, wgrad)
+    (3, 3, 21, 33, 47),
+    (1, 4, 32, 9, 11),
+    (2, 1, 8, 5, 7),
 ]
 
 
