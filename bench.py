@@ -344,6 +344,18 @@ def conv_flops_per_node(batch):
     return out
 
 
+def conv_is_core_per_node():
+    """Same indexing as conv_flops_per_node: True for the layers with more than 64 input or output channels (the U-Net core:
+    core.down2 .. core.up3), False for the small-channel encoder / decoder layers."""
+    rows = conv_shape_table()
+    out = []
+    for c1, c2 in zip(rows[0::2], rows[1::2]):
+        for _ in range(c1[1]):
+            for (_, _, ci, co, _, _) in (c1, c2):
+                out.append(ci > 64 or co > 64)
+    return out
+
+
 def run_gpu_arm(args):
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -471,6 +483,8 @@ def run_gpu_arm(args):
         msb, cnt = [0.0] * ncls, [0] * ncls
         node_fl = conv_flops_per_node(B)   # tag = 2 * node + conv  ->  algorithmic FLOPs of that layer (one of fprop/dgrad/wgrad)
         by_kernel = {}
+        node_core = conv_is_core_per_node()
+        by_class = {}
         for i in range(nl):
             msb[lcls[i]] += lms[i]
             cnt[lcls[i]] += 1
@@ -480,6 +494,12 @@ def run_gpu_arm(args):
                 e["launches"] += 1
                 e["ms"] += lms[i]
                 e["flops"] += node_fl[ltag[i]]
+                pas = names[lcls[i]].replace("conv_", "")   # fprop / dgrad / wgrad
+                ck = ("core (> 64 channels)" if node_core[ltag[i]] else "small-channel (<= 64 channels)") + (" wgrad" if pas == "wgrad" else " fprop+dgrad")
+                e2 = by_class.setdefault(ck, {"launches": 0, "ms": 0.0, "flops": 0.0})
+                e2["launches"] += 1
+                e2["ms"] += lms[i]
+                e2["flops"] += node_fl[ltag[i]]
         per_step = {n: (msb[i] / 3.0, cnt[i] // 3) for i, n in enumerate(names)}
         fprop_fl, dgrad_fl = conv_flops_per_step(B)
         wgrad_fl = fprop_fl   # every 3x3 conv has a weight gradient of the same FLOP count as its forward
@@ -507,8 +527,13 @@ def run_gpu_arm(args):
                                   "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1) if v["ms"] > 0 else None,
                                   "frac_of_peak": round(v["flops"] / (v["ms"] * 1e-3) / 1e12 / sustained, 4) if v["ms"] > 0 else None}
                               for k, v in sorted(by_kernel.items())},
+                "by_layer_class": {k: {"launches_per_step": v["launches"] // 3, "ms_per_step": round(v["ms"] / 3.0, 4),
+                                       "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1) if v["ms"] > 0 else None,
+                                       "frac_of_peak": round(v["flops"] / (v["ms"] * 1e-3) / 1e12 / sustained, 4) if v["ms"] > 0 else None}
+                                   for k, v in sorted(by_class.items())},
                 "note": "per-launch CUDA-event timing taken in 3 extra profiled steps (eager launches) right after the timed region; "
-                        "by_kernel: algorithmic FLOPs (true channel counts) of the launches each tensor-core kernel served / their time"}
+                        "by_kernel: algorithmic FLOPs (true channel counts) of the launches each conv kernel served / their time; "
+                        "by_layer_class: the same split by layer width (the U-Net core vs the small-channel encoder / decoder layers) and pass"}
 
     cpu = guard = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

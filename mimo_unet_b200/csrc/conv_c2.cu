@@ -584,13 +584,17 @@ int conv3x3_c2_launch(const ActView& in, int mode, const bf16* wpacked, int cout
             // cycles per item: TMA delivers ~20 B/cycle/SM (6.4 cycles per 128-byte row), a pair MMA costs max(N/2, 40) cycles, a
             // tcgen05.commit ~400 cycles of the issuing thread, the epilogue ~5 cycles per accumulator column and tile (exposed only
             // with a single accumulator set)
-            const double load = 6.4 * p.cin_chunks * (a_rows + (resident ? 0.0 : b_rows));
+            // ... plus ~300 cycles per TMA instruction / barrier round trip, and ~2000 cycles per item for the accumulator hand-over
+            // and the pipeline ramp (without them T = 1 ties with T = 4 on wide maps, where the per-(chunk, kh) segments have no halo
+            // to share: measured 352 us vs 234 us on C3's 90 -> 45 @ 256 x 256)
+            const double n_loads = p.cin_chunks * ((kh ? 3.0 : 1.0) * (q.seg_full + (q.seg_rem ? 1 : 0)) + (resident ? 0.0 : 3.0));
+            const double load = 6.4 * p.cin_chunks * (a_rows + (resident ? 0.0 : b_rows)) + 300.0 * n_loads;
             const double mma = (double)T * 9.0 * k_steps * (block_n / 2 > 40 ? block_n / 2 : 40);
             const double issue = 400.0 * (p.cin_chunks * ((kh ? 3.0 : 1.0) + (resident ? 0.0 : 3.0)) + 1.0) + (double)T * 9.0 * k_steps * 16.0;
             const double epi = stages == 1 ? 5.0 * T * block_n : 0.0;
             double item = load > mma ? load : mma;
             if (issue > item) item = issue;
-            const double cost = (double)waves * (item + epi) + (resident ? 6.4 * p.cin_chunks * b_rows : 0.0);
+            const double cost = (double)waves * (item + epi + 2000.0) + (resident ? 6.4 * p.cin_chunks * b_rows : 0.0);
             if (cost < best) { best = cost; bestc = Choice{T, kh, stages, split, resident}; }
           }
         }

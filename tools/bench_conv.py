@@ -24,6 +24,8 @@ SETS = {
     "c2all": [(64, 168, 84, 64, 80), (64, 84, 42, 64, 80), (64, 84, 168, 32, 40), (64, 168, 168, 32, 40), (64, 336, 168, 32, 40),
               (64, 168, 84, 32, 40), (64, 168, 336, 16, 20), (64, 336, 336, 16, 20), (64, 672, 336, 16, 20), (64, 336, 168, 16, 20),
               (64, 336, 336, 8, 10)],
+    # C3 (fbc 30, 256 x 256 maps): the wide-map decoder layers
+    "c3dec": [(32, 90, 45, 256, 256), (32, 45, 30, 256, 256), (32, 30, 30, 256, 256)],
     "probe": [(64, 21, 21, 128, 160), (64, 63, 31, 128, 160)],
     "small": [(2, 21, 21, 37, 45), (3, 63, 31, 16, 24), (2, 3, 21, 32, 32)],
 }
