@@ -5,6 +5,7 @@ The reference defines no multi-GPU behaviour (devices=1 everywhere); semantics f
 BatchNorm statistics, per-rank shuffles, gradients averaged over ranks."""
 from __future__ import annotations
 
+import os
 from typing import List, Optional
 
 import torch
@@ -74,20 +75,28 @@ class OverlappedGradientSynchronizer:
         self.events = [torch.cuda.Event() for _ in range(self.NUM_STAGES)]
         for e in self.events:
             e.record()  # torch creates the cudaEvent_t lazily on the first record
-        self.side = torch.cuda.Stream()
+        # MIMO_DP_PRIORITY=1: high-priority side stream (the collective's CTAs are placed before the next compute kernel's)
+        self.side = torch.cuda.Stream(priority=-1) if os.environ.get("MIMO_DP_PRIORITY", "0") == "1" else torch.cuda.Stream()
+        # MIMO_DP_BUCKETS = 4 (one bucket per backward stage, default) | 2 (decoders + core up, core down + encoders) | 1 (one
+        # all-reduce after backward: no overlap, but no collective kernel competing with the persistent compute kernels for SMs)
+        self.buckets = int(os.environ.get("MIMO_DP_BUCKETS", "4"))
+        # measurement only (results are wrong): MIMO_DP_DEBUG_SKIP = grad | loss | both drops the named exchange to attribute its cost
+        self._skip = os.environ.get("MIMO_DP_DEBUG_SKIP", "")
         self._work: List = []
         self._after_wait = None   # callable run by wait() once the buckets have been joined (gradient-aliasing check)
 
     def launch(self, flat: torch.Tensor, bounds):
         """bounds[k] = (start, end) element range of stage k inside `flat`."""
-        if world_size() == 1:
+        if world_size() == 1 or self._skip in ("grad", "both"):
             return
-        for k in range(self.NUM_STAGES):
-            a, b = bounds[k]
-            if b <= a:
+        groups = {4: [[0], [1], [2], [3]], 2: [[0, 1], [2, 3]], 1: [[0, 1, 2, 3]]}.get(self.buckets, [[0], [1], [2], [3]])
+        for g in groups:
+            live = [k for k in g if bounds[k][1] > bounds[k][0]]
+            if not live:
                 continue
+            a, b = min(bounds[k][0] for k in live), max(bounds[k][1] for k in live)   # stages are adjacent slices of the flat buffer
             with torch.cuda.stream(self.side):
-                self.side.wait_event(self.events[k])
+                self.side.wait_event(self.events[g[-1]])   # the last stage of the group is final last
                 self._work.append(dist.all_reduce(flat[a:b], op=dist.ReduceOp.AVG, group=self.group, async_op=True))
 
     def wait(self):
@@ -102,6 +111,9 @@ class OverlappedGradientSynchronizer:
         """Data-parallel loss-buffer update OFF the compute stream: the [S] per-subnetwork loss is averaged over ranks and
         added to the device loss buffer on the side stream; the next step's loss kernel waits for `loss_event` before it reads
         the buffer. (The result is not needed before the next step, so nothing on the compute stream blocks on NCCL.)"""
+        if self._skip in ("loss", "both"):
+            loss_buffer.add(loss.detach())
+            return
         cur = torch.cuda.current_stream()
         ready = torch.cuda.Event()
         ready.record(cur)
