@@ -391,6 +391,124 @@ __global__ void upsample_kernel(ActView in, ActView o, int off_h, int off_w) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Decoder concat in ONE pass (reference components.py:110-119: up(x1), F.pad, cat([x2_skip, x1_up])): whole pixel lines of the
+// haloed concat buffer `o` (c_off == 0) are written with 16-byte stores,
+//   channels [0, f)          <- `skip`, the DENSE copy of the encoder output (f = skip.C),
+//   channels [f, f + in.C)   <- bilinear x2 (align_corners) of `in`, zero outside the up-sampled area,
+//   the rest of the pitch    <- 0.
+// Why: with f = 21 the two producers used to write 42 and 84 bytes of every 128-byte line at different times of the forward
+// pass; the partial-sector writes made bn_relu_apply of in_convs.c2 103 us (37 us for its dense twin) and the up-sampling 133 us
+// (ncu: 104 MB read for a 63 MB input: sector fills). Thread = (pixel, 16-byte word k of the line); word k holds buffer channels
+// [8k, 8k + 8): its first n_skip channels come from skip word k, the others are up channels t + i with t = 8k - f, i.e. the
+// aligned source groups q = floor(t / 8) and q + 1 funnel-shifted by r = t - 8q (the same r for every word of the line).
+// ------------------------------------------------------------------------------------------------
+template <int WPP>
+__global__ void __launch_bounds__(256, 3)
+upsample_concat_kernel(ActView in, ActView skip, ActView o, int off_h, int off_w) {
+  const int uh = 2 * in.H, uw = 2 * in.W;
+  const float rh = uh > 1 ? (float)(in.H - 1) / (float)(uh - 1) : 0.f;
+  const float rw = uw > 1 ? (float)(in.W - 1) / (float)(uw - 1) : 0.f;
+  const int words = o.cpitch >> 3;
+  constexpr int lanes = 256 / WPP;
+  const int k = threadIdx.x % WPP, pl = threadIdx.x / WPP;
+  const int f = skip.C, cup = in.C, gup = (cup + 7) >> 3;
+  const int n_skip = min(max(f - 8 * k, 0), 8);
+  const int t = 8 * k - f;
+  const int q = t >= 0 ? (t >> 3) : -((-t + 7) >> 3);   // floor(t / 8)
+  const int r = t - 8 * q;                                // 0 .. 7
+  // every lane blends ONE aligned source group: `own` = q (r == 0) or q + 1 (r != 0: the word is the funnel of the left neighbour's
+  // group and this lane's; a lane whose own group does not exist contributes zeros)
+  const int g_own = r ? q + 1 : q;
+  const bool use_own = g_own >= 0 && g_own < gup;
+  const bool use_left = r != 0 && q >= 0 && q < gup;   // the left neighbour (word k - 1) owns group q
+  const uint4 mask_o = group_mask(use_own ? min(8, cup - 8 * g_own) : 0);
+  const uint4 mask_s = group_mask(n_skip);
+  const bool active = k < words;
+  const int rows = o.N * o.H;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int n = row / o.H, h = row - n * o.H;
+    const int y = h - off_h;
+    const bool yin = y >= 0 && y < uh;
+    const float sy = rh * y;
+    const int y0 = yin ? (int)sy : 0;
+    const int y1 = min(y0 + 1, in.H - 1);
+    const float ly = sy - y0;
+    const bf16* r0 = in.base + in.pix(n, y0, 0);
+    const bf16* r1 = in.base + in.pix(n, y1, 0);
+    const bf16* srow = skip.base + skip.pix(n, h, 0) + 8 * k;
+    // bilinear sample of this lane's source group at output column w (zeros outside the up-sampled area / for idle lanes)
+    auto sample = [&](int w) -> uint4 {
+      uint4 own = make_uint4(0, 0, 0, 0);
+      const int x = w - off_w;
+      if (active && w < o.W && use_own && yin && x >= 0 && x < uw) {
+        const float sx = rw * x;
+        const int x0 = (int)sx, x1 = min(x0 + 1, in.W - 1);
+        const float lx = sx - x0;
+        float a[8], b[8], cc[8], d[8], out[8];
+        unpack8(and4(*reinterpret_cast<const uint4*>(r0 + (size_t)x0 * in.cpitch + 8 * g_own), mask_o), a);
+        unpack8(and4(*reinterpret_cast<const uint4*>(r0 + (size_t)x1 * in.cpitch + 8 * g_own), mask_o), b);
+        unpack8(and4(*reinterpret_cast<const uint4*>(r1 + (size_t)x0 * in.cpitch + 8 * g_own), mask_o), cc);
+        unpack8(and4(*reinterpret_cast<const uint4*>(r1 + (size_t)x1 * in.cpitch + 8 * g_own), mask_o), d);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) out[i] = (1.f - ly) * ((1.f - lx) * a[i] + lx * b[i]) + ly * ((1.f - lx) * cc[i] + lx * d[i]);
+        own = pack8(out);
+      }
+      return own;
+    };
+    // funnel with the left neighbour's group, merge the skip channels, store the pixel and the halo cells that mirror it
+    auto emit = [&](int w, const uint4& own, const uint4& sw) {
+      uint4 word = own;
+      if (r != 0) {
+        uint4 left;
+        left.x = __shfl_up_sync(0xffffffffu, own.x, 1);
+        left.y = __shfl_up_sync(0xffffffffu, own.y, 1);
+        left.z = __shfl_up_sync(0xffffffffu, own.z, 1);
+        left.w = __shfl_up_sync(0xffffffffu, own.w, 1);
+        if (!use_left) left = make_uint4(0, 0, 0, 0);   // also covers word 0, whose left lane belongs to another pixel
+        word = funnel8(left, own, r);
+      }
+      if (!active || w >= o.W) return;
+      if (n_skip)
+        word = make_uint4((sw.x & mask_s.x) | (word.x & ~mask_s.x), (sw.y & mask_s.y) | (word.y & ~mask_s.y),
+                          (sw.z & mask_s.z) | (word.z & ~mask_s.z), (sw.w & mask_s.w) | (word.w & ~mask_s.w));
+      if (h > 1 && h < o.H - 2 && w > 1 && w < o.W - 2) {   // interior: one target (the common case)
+        *reinterpret_cast<uint4*>(o.base + o.pix(n, h, w) + 8 * k) = word;
+        return;
+      }
+      // border: the pixel itself + the halo cells that mirror it
+      const int hh = (h == 1) ? -1 : ((h == o.H - 2) ? o.H : -2);
+      const int ww = (w == 1) ? -1 : ((w == o.W - 2) ? o.W : -2);
+      const int hh2 = (o.H == 3 && h == 1) ? o.H : -2;
+      const int ww2 = (o.W == 3 && w == 1) ? o.W : -2;
+      const int hs[3] = {h, hh, hh2};
+      const int ws[3] = {w, ww, ww2};
+#pragma unroll 1
+      for (int ai = 0; ai < 3; ++ai) {
+        if (hs[ai] == -2) continue;
+#pragma unroll 1
+        for (int bi = 0; bi < 3; ++bi) {
+          if (ws[bi] == -2) continue;
+          *reinterpret_cast<uint4*>(o.base + o.pix(n, hs[ai], ws[bi]) + 8 * k) = word;
+        }
+      }
+    };
+    auto skip_word = [&](int w) -> uint4 {
+      return (active && n_skip && w < o.W) ? *reinterpret_cast<const uint4*>(srow + (size_t)w * skip.cpitch) : make_uint4(0, 0, 0, 0);
+    };
+    // two pixels per thread and trip: ten independent 16-byte loads in flight (the kernel is load-latency bound otherwise);
+    // uniform trip count: the shuffles need converged warps
+    for (int w0 = 0; w0 < o.W; w0 += 2 * lanes) {
+      const int wa = w0 + pl, wb = wa + lanes;
+      const uint4 sa = skip_word(wa), sb = skip_word(wb);
+      const uint4 oa = sample(wa);
+      const uint4 ob = sample(wb);
+      emit(wa, oa, sa);
+      emit(wb, ob, sb);
+    }
+  }
+}
+
 // Fast path of the up-sampling: block = (pixel lanes) x GPP lanes per pixel (GPP = power of two >= #channel groups, so
 // the groups of a pixel never straddle a warp), row-based 32-bit indexing, 16-byte loads of the four taps. Destination
 // slices whose channel offset is NOT a multiple of 8 (decoder concat: 21 + 42 channels) are still written with 16-byte
@@ -1365,6 +1483,38 @@ int upsample_launch(const ActView& in, const ActView& o, cudaStream_t st) {
   }
   const long long total = (long long)o.N * o.H * o.W * groups;
   upsample_kernel<<<grid_for(total), kBlock, 0, st>>>(in, o, dY / 2, dX / 2);
+  MIMO_LAUNCH_CHECK();
+  return MIMO_OK;
+}
+
+// skip: dense (pad 0) NHWC copy of the skip tensor; o: the WHOLE haloed concat buffer (c_off 0, C = skip.C + in.C)
+bool upsample_concat_ok(const ActView& in, const ActView& skip, const ActView& o) {
+  if (o.pad != 1 || o.c_off != 0 || o.C != skip.C + in.C || o.C > o.cpitch || (o.cpitch & 7) || (o.cpitch >> 3) > 32) return false;
+  if (skip.pad != 0 || skip.N != o.N || skip.H != o.H || skip.W != o.W || (skip.c_off & 7) || (skip.cpitch & 7)) return false;
+  if (skip.c_off + ((skip.C + 7) & ~7) > skip.cpitch) return false;
+  if (in.N != o.N || (in.c_off & 7) || (in.cpitch & 7) || in.c_off + ((in.C + 7) & ~7) > in.cpitch) return false;
+  if (((uintptr_t)o.base | (uintptr_t)skip.base | (uintptr_t)in.base) & 15) return false;
+  return o.H >= 2 * in.H && o.W >= 2 * in.W;
+}
+
+int upsample_concat_launch(const ActView& in, const ActView& skip, const ActView& o, cudaStream_t st) {
+  MIMO_CHECK(upsample_concat_ok(in, skip, o), MIMO_ERR_ARG, "upsample_concat: unsupported views");
+  const int dY = o.H - 2 * in.H, dX = o.W - 2 * in.W;
+  const int words = o.cpitch >> 3;
+  const int rows = o.N * o.H;
+  const int grid = rows < 8 * num_sms() ? rows : 8 * num_sms();
+  int wpp = 1;
+  while (wpp < words) wpp <<= 1;
+  const ActView inv = [&] { ActView v = in; v.base = in.base + in.c_off; v.c_off = 0; return v; }();
+  const ActView sv = [&] { ActView v = skip; v.base = skip.base + skip.c_off; v.c_off = 0; return v; }();
+  switch (wpp) {
+    case 1: upsample_concat_kernel<1><<<grid, kBlock, 0, st>>>(inv, sv, o, dY / 2, dX / 2); break;
+    case 2: upsample_concat_kernel<2><<<grid, kBlock, 0, st>>>(inv, sv, o, dY / 2, dX / 2); break;
+    case 4: upsample_concat_kernel<4><<<grid, kBlock, 0, st>>>(inv, sv, o, dY / 2, dX / 2); break;
+    case 8: upsample_concat_kernel<8><<<grid, kBlock, 0, st>>>(inv, sv, o, dY / 2, dX / 2); break;
+    case 16: upsample_concat_kernel<16><<<grid, kBlock, 0, st>>>(inv, sv, o, dY / 2, dX / 2); break;
+    default: upsample_concat_kernel<32><<<grid, kBlock, 0, st>>>(inv, sv, o, dY / 2, dX / 2); break;
+  }
   MIMO_LAUNCH_CHECK();
   return MIMO_OK;
 }

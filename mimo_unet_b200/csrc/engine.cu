@@ -76,6 +76,9 @@ struct mimo_unet_plan {
   int down2 = -1, down3 = -1, down4 = -1, up1 = -1, up2 = -1, up3 = -1;
   // extra buffers
   std::vector<int> xin, dcat, p1, gp1;   // per subnetwork
+  std::vector<int> x1d;                  // per subnetwork: DENSE copy of the encoder output x1_s (training / unfused path): the decoder's
+                                         // concat kernel merges it with the up-sampled core output into whole lines of dcat[s]
+  bool last_dense_skip = false;          // the last forward wrote x1_s into x1d (backward reads the pooling winners from there)
   int cat3 = -1, cat2 = -1, cat1 = -1, pxc = -1, px3 = -1, px4 = -1, x5 = -1, u1 = -1, u2 = -1, u3 = -1;
   int upd = -1;   // inference: the up-sampled core output shared by all decoders (virtual concat), -1 when not used
   int g_xc = -1, g_x3 = -1, g_x4 = -1, g_x5 = -1, g_u1 = -1, g_u2 = -1, g_u3 = -1;
@@ -326,11 +329,11 @@ int conv_bn_forward(mimo_unet_plan* P, ConvL& c, const ActView& in, const ActVie
 }
 
 int node_forward(mimo_unet_plan* P, int ni, bool training, const float* drop, cudaStream_t st, const ActView* in1 = nullptr,
-                 const ActView* in2 = nullptr) {
+                 const ActView* in2 = nullptr, const ActView* out_override = nullptr) {
   Node& n = P->nodes[ni];
   const ActView in = in1 ? *in1 : view_of(P, n.in);
   const ActView a1 = view_of(P, n.a1, 0, n.c1.cout);
-  const ActView out = view_of(P, n.out);
+  const ActView out = out_override ? *out_override : view_of(P, n.out);
   P->cur_tag = 2 * ni;
   int rc = conv_bn_forward(P, n.c1, in, a1, nullptr, nullptr, training, st, in2);
   if (rc) return rc;
@@ -437,6 +440,7 @@ int mimo_unet_plan_create(const mimo_unet_config_t* cfg, mimo_unet_plan_t** out)
     P->gp1.push_back(buf(1, 0, f));
     P->g_feat.push_back(buf(0, 0, f));
     P->g_x1.push_back(buf(0, 0, f));
+    P->x1d.push_back(buf(0, 0, f));
   }
   P->cat3 = buf(1, 1, 2 * c); P->pxc = buf(2, 1, c);
   P->cat2 = buf(2, 1, 4 * c); P->px3 = buf(3, 1, 2 * c);
@@ -630,6 +634,11 @@ int mimo_unet_forward(mimo_unet_plan_t* P, const float* x, const long long* gath
     if (gather) RUN(kPackIn, pack_input_launch(x, (long long)Cin * HW, HW, gather + (long long)s * B, xin, st));
     else RUN(kPackIn, pack_input_launch(x + (long long)s * Cin * HW, (long long)S * Cin * HW, HW, nullptr, xin, st));
   }
+  // Training / unfused path: the encoder output x1_s goes to a dense buffer and reaches the decoder's concat buffer through the
+  // concat kernel (whole-line writes). The fused inference path keeps writing x1_s straight into dcat[s] from the conv epilogue.
+  static const int dense_skip_on = getenv("MIMO_DENSE_SKIP") ? atoi(getenv("MIMO_DENSE_SKIP")) : 1;
+  const bool dense_skip = dense_skip_on && !(!tr && P->eval_fuse && P->fuse_next) &&
+                          upsample_concat_ok(view_of(P, P->u3, 0, c / 2), view_of(P, P->x1d[0], 0, f), view_of(P, P->dcat[0], 0, f + c / 2));
   const bool virt = !tr && P->eval_fuse && P->fuse_next && P->upd >= 0 &&
                     conv3x3_c2_ok(view_of(P, P->dcat[0], 0, f), 0, P->nodes[P->dec[0]].c1.cout);
   auto body = [&]() -> int {
@@ -647,7 +656,12 @@ int mimo_unet_forward(mimo_unet_plan_t* P, const float* x, const long long* gath
     }
     int rc;
     for (int s = 0; s < S; ++s) {
-      if ((rc = node_forward(P, P->enc_in[s], tr, mask(P->enc_in[s]), st))) return rc;
+      if (dense_skip) {
+        const ActView x1 = view_of(P, P->x1d[s], 0, f);
+        if ((rc = node_forward(P, P->enc_in[s], tr, mask(P->enc_in[s]), st, nullptr, nullptr, &x1))) return rc;
+      } else {
+        if ((rc = node_forward(P, P->enc_in[s], tr, mask(P->enc_in[s]), st))) return rc;
+      }
       if ((rc = node_forward(P, P->enc_down[s], tr, mask(P->enc_down[s]), st))) return rc;
     }
     if ((rc = node_forward(P, P->down2, tr, mask(P->down2), st))) return rc;
@@ -667,7 +681,10 @@ int mimo_unet_forward(mimo_unet_plan_t* P, const float* x, const long long* gath
         const ActView skip = view_of(P, P->dcat[s], 0, f), up = view_of(P, P->upd, 0, c / 2);
         if ((rc = node_forward(P, P->dec[s], tr, mask(P->dec[s]), st, &skip, &up))) return rc;
       } else {
-        RUN(kUpsample, upsample_launch(view_of(P, P->u3, 0, c / 2), view_of(P, P->dcat[s], f, c / 2), st));
+        if (dense_skip)   // skip + up-sampled core output -> whole 128-byte lines of the concat buffer
+          RUN(kUpsample, upsample_concat_launch(view_of(P, P->u3, 0, c / 2), view_of(P, P->x1d[s], 0, f), view_of(P, P->dcat[s], 0, f + c / 2), st));
+        else
+          RUN(kUpsample, upsample_launch(view_of(P, P->u3, 0, c / 2), view_of(P, P->dcat[s], f, c / 2), st));
         if ((rc = node_forward(P, P->dec[s], tr, mask(P->dec[s]), st))) return rc;
       }
       if (s < (int)P->final_keep.size() && P->final_keep[s])  // x_i = final_dropouts[i](x_i), model.py:294
@@ -689,6 +706,7 @@ int mimo_unet_forward(mimo_unet_plan_t* P, const float* x, const long long* gath
   }
   P->last_training = tr;
   P->last_fused = !tr && P->eval_fuse && P->fuse_next;
+  P->last_dense_skip = dense_skip;
   P->have_forward = true;
   return MIMO_OK;
 }
@@ -822,7 +840,7 @@ int mimo_unet_backward(mimo_unet_plan_t* P, const float* dout, const float* grad
       const ActView gp = view_of(P, P->gp1[s], 0, f);
       RUN(kGradGather, grad_gather_launch(&dpp, nullptr, nullptr, gp, 0, st));
       const ActView dskip = view_of(P, P->nodes[P->dec[s]].c1.dpad, 0, f);
-      const ActView act = view_of(P, P->dcat[s], 0, f);
+      const ActView act = P->last_dense_skip ? view_of(P, P->x1d[s], 0, f) : view_of(P, P->dcat[s], 0, f);
       RUN(kGradGather, grad_gather_launch(&dskip, &gp, &act, view_of(P, P->g_x1[s], 0, f), 0, st));
       if ((rc = node_backward(P, P->enc_in[s], tr, mask(P->enc_in[s]), accumulate, st))) return rc;
       if (dx) {
@@ -845,7 +863,7 @@ int mimo_unet_backward(mimo_unet_plan_t* P, const float* dout, const float* grad
   has_mask = has_mask || P->center_keep != nullptr;
   for (const bf16* m : P->final_keep) has_mask = has_mask || (m != nullptr);
   const bool allow = P->graph_mode != 0 && !P->graph_failed && !P->prof && !has_mask && dx == nullptr && P->bwd_calls > 2;
-  const unsigned long long key = (tr ? 1ull : 0ull) | (accumulate ? 2ull : 0ull);
+  const unsigned long long key = (tr ? 1ull : 0ull) | (accumulate ? 2ull : 0ull) | (P->last_dense_skip ? 4ull : 0ull);
   if ((rc = run_graphed(P, P->g_bwd[0], key, allow, st, stage0))) return rc;
   if (P->stage_ev[0]) MIMO_CUDA(cudaEventRecord(P->stage_ev[0], st));
   if ((rc = run_graphed(P, P->g_bwd[1], key, allow, st, stage1))) return rc;

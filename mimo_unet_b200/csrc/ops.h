@@ -65,6 +65,8 @@ int bn_relu_apply_launch(const bf16* y, int ycp, const float* scale, const float
                          const ActView* pool, cudaStream_t st);
 int maxpool_launch(const ActView& in, const ActView& o, long long* idx_nchw, cudaStream_t st);
 int upsample_launch(const ActView& in, const ActView& o, cudaStream_t st);
+bool upsample_concat_ok(const ActView& in, const ActView& skip, const ActView& o);
+int upsample_concat_launch(const ActView& in, const ActView& skip, const ActView& o, cudaStream_t st);
 int upsample_bwd_launch(const ActView& gdst, const ActView& gsrc, int accumulate, cudaStream_t st);
 int grad_gather_launch(const ActView* dpad, const ActView* gpool, const ActView* act, const ActView& gout, int accumulate,
                        cudaStream_t st);
