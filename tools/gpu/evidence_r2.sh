@@ -19,6 +19,7 @@ timeout 400 python bench.py --impl reference --steps 5 --warmup 2 > gpurun_out/$
 t "bench reference rc=$?"
 timeout 300 python tools/profile_layers.py --cfg C2 --out gpurun_out/${R}_layers_c2.txt > gpurun_out/layers.log 2>&1
 timeout 300 python tools/profile_layers.py --cfg C3 --out gpurun_out/${R}_layers_c3.txt >> gpurun_out/layers.log 2>&1
+timeout 300 python tools/bench_conv.py --set c2all,half,full --reps 20 > gpurun_out/${R}_bench_conv.txt 2>/dev/null
 t "layers rc=$?"
 timeout 300 python tools/bench_loss.py > gpurun_out/${R}_loss_bw.txt 2>&1
 t "bench_loss rc=$?"; tail -8 gpurun_out/${R}_loss_bw.txt
@@ -39,6 +40,7 @@ cap conv_c2        "conv3x3_c2_kernel"          6 4
 cap conv_flat      "conv3x3_flat_kernel"        0 3
 cap wgrad_flat     "conv3x3_wgrad_flat_kernel"  0 2
 cap wgrad_flatk    "conv3x3_wgrad_flatk_kernel" 0 3
-cap elem           "bn_bwd_bulk_kernel|bn_relu_apply_kernel|grad_gather_pool_kernel|upsample_fast_kernel" 0 6
+cap conv_thin      "conv3x3_thin_kernel"        0 1
+cap elem           "bn_bwd_bulk_kernel|bn_relu_apply_kernel|grad_gather_pool_kernel|upsample_fast_kernel|upsample_concat_kernel" 0 8
 cat gpurun_out/${R}_ncu_summary.txt
 ls -la gpurun_out/ncu/

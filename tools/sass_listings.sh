@@ -5,14 +5,15 @@ R=${1:-r02}
 OUT=profiles/${R}_sass
 mkdir -p $OUT
 cd "$(dirname "$0")/.."
-for f in conv_c2 conv_flat conv_flat2 conv_wgrad_flat conv_wgrad_flatk; do
+for f in conv_c2 conv_flat conv_flat2 conv_wgrad_flat conv_wgrad_flatk conv_thin; do
   cuobjdump -sass mimo_unet_b200/csrc/$f.o | sed 's#/\* 0x[0-9a-f]* \*/##' | sed 's/[[:space:]]*$//' | grep -v "^$" > $OUT/$f.sass
 done
 # the flat kernels are instantiated four times: keep the BN = 32 instance only (the one every 21-channel layer runs)
 python3 - "$OUT" <<'PY'
 import re, sys, os
 out = sys.argv[1]
-for name, keep in (("conv_flat", "flat_kernelILi32ELi2E"), ("conv_flat2", "flat2_kernelILi32ELi2E")):
+for name, keep in (("conv_flat", "flat_kernelILi32ELi2E"), ("conv_flat2", "flat2_kernelILi32ELi2E"), ("conv_c2", "c2_kernelILb0E"),
+                   ("conv_thin", "thin_kernelILi3ELi3E")):
     p = os.path.join(out, name + ".sass")
     txt = open(p).read()
     parts = re.split(r"(?=\n\s*Function : )", txt)
@@ -27,7 +28,7 @@ for fn in sorted(os.listdir(out)):
         m = re.search(r"\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
         if m:
             op = m.group(1)
-            for key in ("UTCHMMA", "UTCBAR", "UTMALDG", "UTMASTG", "UBLKCP", "LDTM", "STTM", "UTCCP", "SYNCS", "LDGSTS", "MEMBAR", "FENCE"):
+            for key in ("UTCHMMA", "UTCBAR", "UTMALDG", "UTMASTG", "UBLKCP", "LDTM", "STTM", "UTCCP", "SYNCS", "LDGSTS", "MEMBAR", "FENCE", "FFMA2"):
                 if op.startswith(key):
                     k = op if key in ("UTCHMMA", "UTCBAR", "UTMALDG") else key
                     c[k] = c.get(k, 0) + 1
