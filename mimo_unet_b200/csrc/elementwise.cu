@@ -62,9 +62,18 @@ __device__ __forceinline__ void store_group(bf16* p, int nvalid, const uint4& v,
     *reinterpret_cast<uint4*>(p) = v;
   } else {
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    if ((reinterpret_cast<uintptr_t>(p) & 3) == 0) {
+      // slices at an even channel offset (the 42-channel subnetwork slices of the stacked buffers): 32-bit stores of channel pairs
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      if (i < nvalid) reinterpret_cast<unsigned short*>(p)[i] = (unsigned short)(w[i >> 1] >> ((i & 1) * 16));
+      for (int i = 0; i < 4; ++i) {
+        if (2 * i + 1 < nvalid) reinterpret_cast<uint32_t*>(p)[i] = w[i];
+        else if (2 * i < nvalid) reinterpret_cast<unsigned short*>(p)[2 * i] = (unsigned short)w[i];
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i < nvalid) reinterpret_cast<unsigned short*>(p)[i] = (unsigned short)(w[i >> 1] >> ((i & 1) * 16));
+    }
   }
 }
 template <bool VEC>
@@ -787,7 +796,7 @@ __device__ __forceinline__ void fold_border(const ActView& dp, int n, int h, int
 // G = fold(dpad) (+ G when accumulating). Block = (pixel lanes) x (8-channel groups), one image row per block step.
 template <bool VEC_IN, bool VEC_OUT>
 __global__ void __launch_bounds__(256, 4)
-grad_fold_kernel(ActView dpad, ActView gout, int accumulate) {
+grad_fold_kernel(ActView dpad, ActView dpad2, int two, ActView gout, int accumulate) {
   const int groups = (gout.C + 7) >> 3;
   const int lanes = blockDim.x / groups;
   const int g = threadIdx.x % groups, pl = threadIdx.x / groups;
@@ -799,11 +808,19 @@ grad_fold_kernel(ActView dpad, ActView gout, int accumulate) {
   for (int row = blockIdx.x; row < rows; row += gridDim.x) {
     const int n = row / gout.H, h = row - n * gout.H;
     const bf16* src = dpad.base + dpad.pix(n, h + 1, 1) + c;
+    const bf16* src2 = dpad2.base + dpad2.pix(n, h + 1, 1) + c;
     bf16* dst = gout.base + gout.pix(n, h, 0) + c;
     for (int w = pl; w < gout.W; w += lanes) {
       float acc[8];
       unpack8(load_group<VEC_IN>(src + (size_t)w * dpad.cpitch, nv, mask), acc);
       fold_border<VEC_IN>(dpad, n, h, w, gout.H, gout.W, c, nv, mask, acc);
+      if (two) {   // sum of two sources (the same slice of two decoders' gradients) in one pass
+        float t2[8];
+        unpack8(load_group<VEC_IN>(src2 + (size_t)w * dpad2.cpitch, nv, mask), t2);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += t2[k];
+        fold_border<VEC_IN>(dpad2, n, h, w, gout.H, gout.W, c, nv, mask, acc);
+      }
       if (accumulate) {
         float old[8];
         unpack8(load_group<VEC_OUT>(dst + (size_t)w * gout.cpitch, nv, mask), old);
@@ -1536,20 +1553,22 @@ int upsample_bwd_launch(const ActView& gdst, const ActView& gsrc, int accumulate
 }
 
 int grad_gather_launch(const ActView* dpad, const ActView* gpool, const ActView* act, const ActView& gout, int accumulate,
-                       cudaStream_t st) {
+                       cudaStream_t st, const ActView* dpad2) {
   MIMO_CHECK(gout.pad == 0, MIMO_ERR_ARG, "grad_gather: output must be unpadded");
   if (dpad) MIMO_CHECK(dpad->pad == 0 && dpad->H == gout.H + 2 && dpad->W == gout.W + 2 && dpad->C == gout.C, MIMO_ERR_ARG, "grad_gather: dpad shape mismatch");
   if (gpool) MIMO_CHECK(act && gpool->pad == 0 && gpool->H == gout.H / 2 && gpool->W == gout.W / 2 && gpool->C == gout.C && act->C == gout.C && act->H == gout.H, MIMO_ERR_ARG, "grad_gather: pool shape mismatch");
   MIMO_CHECK((gout.C + 7) / 8 <= kBlock, MIMO_ERR_ARG, "grad_gather: too many channels (%d)", gout.C);
   const bool vo = view_vec_ok(gout);
+  if (dpad2) MIMO_CHECK(!gpool && dpad && dpad2->pad == 0 && dpad2->H == dpad->H && dpad2->W == dpad->W && dpad2->C == dpad->C && dpad2->N == dpad->N &&
+                        dpad2->cpitch == dpad->cpitch && dpad2->c_off == dpad->c_off, MIMO_ERR_ARG, "grad_gather: second source must match the first");
   if (!gpool) {
-    const bool vi = view_vec_ok(*dpad);
+    const bool vi = view_vec_ok(*dpad) && (!dpad2 || view_vec_ok(*dpad2));
     const int rows = gout.N * gout.H;
     const int grid = rows < 8 * num_sms() ? rows : 8 * num_sms();
-    if (vi && vo) grad_fold_kernel<true, true><<<grid, kBlock, 0, st>>>(*dpad, gout, accumulate);
-    else if (vi) grad_fold_kernel<true, false><<<grid, kBlock, 0, st>>>(*dpad, gout, accumulate);
-    else if (vo) grad_fold_kernel<false, true><<<grid, kBlock, 0, st>>>(*dpad, gout, accumulate);
-    else grad_fold_kernel<false, false><<<grid, kBlock, 0, st>>>(*dpad, gout, accumulate);
+    if (vi && vo) grad_fold_kernel<true, true><<<grid, kBlock, 0, st>>>(*dpad, dpad2 ? *dpad2 : *dpad, dpad2 ? 1 : 0, gout, accumulate);
+    else if (vi) grad_fold_kernel<true, false><<<grid, kBlock, 0, st>>>(*dpad, dpad2 ? *dpad2 : *dpad, dpad2 ? 1 : 0, gout, accumulate);
+    else if (vo) grad_fold_kernel<false, true><<<grid, kBlock, 0, st>>>(*dpad, dpad2 ? *dpad2 : *dpad, dpad2 ? 1 : 0, gout, accumulate);
+    else grad_fold_kernel<false, false><<<grid, kBlock, 0, st>>>(*dpad, dpad2 ? *dpad2 : *dpad, dpad2 ? 1 : 0, gout, accumulate);
   } else {
     const bool vec = vo && (!dpad || view_vec_ok(*dpad)) && view_vec_ok(*gpool) && view_vec_ok(*act);
     const int cell_rows = gout.N * ((gout.H + 1) / 2);

@@ -759,14 +759,19 @@ int mimo_unet_backward(mimo_unet_plan_t* P, const float* dout, const float* grad
     int rc;
     MIMO_CUDA(cudaMemsetAsync(P->ws + P->dwp_begin, 0, P->dwp_end - P->dwp_begin, st));
     P->unpack_jobs.clear();
-    for (int s = 0; s < S; ++s) {
-      Node& n = P->nodes[P->dec[s]];
+    for (int s = 0; s < S; ++s)
       if ((rc = node_backward(P, P->dec[s], tr, mask(P->dec[s]), accumulate, st))) return rc;
-      // gradient of the shared up-sampled core output: fold the [f, f + c/2) slice of every decoder into ONE buffer
-      // (the bilinear backward is linear, so it runs once on the sum instead of once per subnetwork)
-      const ActView dp = view_of(P, n.c1.dpad, f, c / 2);
+    // gradient of the shared up-sampled core output: fold the [f, f + c/2) slice of every decoder into ONE buffer (the bilinear
+    // backward is linear, so it runs once on the sum instead of once per subnetwork); two decoders per launch
+    for (int s = 0; s < S; s += 2) {
+      const ActView dp = view_of(P, P->nodes[P->dec[s]].c1.dpad, f, c / 2);
       const ActView t0 = view_of(P, P->tmp0, 0, c / 2);
-      RUN(kGradGather, grad_gather_launch(&dp, nullptr, nullptr, t0, s > 0 ? 1 : 0, st));
+      if (s + 1 < S) {
+        const ActView dp2 = view_of(P, P->nodes[P->dec[s + 1]].c1.dpad, f, c / 2);
+        RUN(kGradGather, grad_gather_launch(&dp, nullptr, nullptr, t0, s > 0 ? 1 : 0, st, &dp2));
+      } else {
+        RUN(kGradGather, grad_gather_launch(&dp, nullptr, nullptr, t0, s > 0 ? 1 : 0, st));
+      }
     }
     RUN(kUpsampleBwd, upsample_bwd_launch(view_of(P, P->tmp0, 0, c / 2), view_of(P, P->g_u3, 0, c / 2), 0, st));
     return flush_unpack();

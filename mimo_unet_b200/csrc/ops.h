@@ -69,7 +69,7 @@ bool upsample_concat_ok(const ActView& in, const ActView& skip, const ActView& o
 int upsample_concat_launch(const ActView& in, const ActView& skip, const ActView& o, cudaStream_t st);
 int upsample_bwd_launch(const ActView& gdst, const ActView& gsrc, int accumulate, cudaStream_t st);
 int grad_gather_launch(const ActView* dpad, const ActView* gpool, const ActView* act, const ActView& gout, int accumulate,
-                       cudaStream_t st);
+                       cudaStream_t st, const ActView* dpad2 = nullptr);
 int halo_fill_launch(const ActView& v, cudaStream_t st);
 int mask_mul_launch(const ActView& a, const bf16* keep, int mask_cp, float scale, cudaStream_t st);
 int maxunpool_launch(const ActView& in, const long long* idx_nchw, const ActView& o, cudaStream_t st);
