@@ -1430,6 +1430,8 @@ int weight_pack_batched_launch(const WeightPackJob* jobs, int n, cudaStream_t st
 int bn_finalize_launch(const float* psum, const float* psq, int tiles, int cpitch, int C, double count, const float* gamma,
                        const float* beta, const float* conv_bias, float* rm, float* rv, long long* nbt, float momentum, float eps,
                        float* scale, float* shift, float* save_mean, float* save_invstd, cudaStream_t st) {
+  static const int skip = getenv("MIMO_DEBUG_SKIP_FINALIZE") ? atoi(getenv("MIMO_DEBUG_SKIP_FINALIZE")) : 0;   // timing experiments only
+  if (skip) return MIMO_OK;
   bn_finalize_kernel<<<C, 128, 0, st>>>(psum, psq, tiles, cpitch, C, count, gamma, beta, conv_bias, rm, rv, nbt, momentum, eps, scale,
                                         shift, save_mean, save_invstd);
   MIMO_LAUNCH_CHECK();
@@ -1642,6 +1644,8 @@ int bn_bwd_launch(const ActView& G, const bf16* y, int ycp, const float* scale, 
       if (grid > bn_bwd_parts(C)) grid = bn_bwd_parts(C);
       bn_bwd_bulk_kernel<0><<<grid, kBlock, smem, st>>>(a);
       MIMO_LAUNCH_CHECK();
+      static const int skipf = getenv("MIMO_DEBUG_SKIP_FINALIZE") ? atoi(getenv("MIMO_DEBUG_SKIP_FINALIZE")) : 0;   // timing experiments only
+      if (!skipf)
       bn_bwd_finalize_kernel<<<ceil_div(C, 8), 256, 0, st>>>(part, grid, C, s1s2, dgamma, dbeta, dbias, scale, mean, invstd, training, grad_scale, accumulate);
       MIMO_LAUNCH_CHECK();
       a.rev = elementwise_reverse();
