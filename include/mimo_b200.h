@@ -100,6 +100,12 @@ int mimo_maxpool2x2(mimo_act_t in, mimo_act_t out, long long* idx_nchw, void* st
 /* nn.Upsample(x2, bilinear, align_corners=True) + F.pad to the skip size (components.py:78,112-115) into `out` */
 int mimo_upsample_bilinear2x(mimo_act_t in, mimo_act_t out, void* stream);
 int mimo_upsample_bilinear2x_bwd(mimo_act_t g_out, mimo_act_t g_in, int accumulate, void* stream);
+/* The whole `Up` front end of the decoders in one pass (components.py:110-119: up(x1), F.pad to the skip size, cat([x2, x1], 1)):
+ * `out` (pad 1, c_off 0, c = skip.c + in.c) receives whole pixel lines: channels [0, skip.c) copied from the DENSE (pad 0) skip tensor,
+ * [skip.c, skip.c + in.c) = bilinear x2 (align_corners) of `in`, zero outside the up-sampled area, pad channels of the pitch = 0, and
+ * the reflect halo. MIMO_ERR_ARG when the geometry is not supported (out.cpitch > 256, unaligned views): callers then use
+ * mimo_upsample_bilinear2x into the slice. */
+int mimo_upsample_concat(mimo_act_t in, mimo_act_t skip, mimo_act_t out, void* stream);
 /* nn.MaxUnpool2d(2) (components.py:87): `in` pooled map, idx_nchw int64 [n][c][h][w] (flat h*W+w of the output) */
 int mimo_maxunpool2x2(mimo_act_t in, const long long* idx_nchw, mimo_act_t out, void* stream);
 /* nn.ConvTranspose2d(cin, cout, kernel_size=2, stride=2) (components.py:96-98): w fp32 [cin][cout][2][2] */

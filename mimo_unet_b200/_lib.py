@@ -62,6 +62,7 @@ SIGNATURES = {
     "mimo_maxpool2x2": (i32, [Act, Act, vp, vp]),
     "mimo_upsample_bilinear2x": (i32, [Act, Act, vp]),
     "mimo_upsample_bilinear2x_bwd": (i32, [Act, Act, i32, vp]),
+    "mimo_upsample_concat": (i32, [Act, Act, Act, vp]),
     "mimo_maxunpool2x2": (i32, [Act, vp, Act, vp]),
     "mimo_convtranspose2x2": (i32, [Act, vp, vp, Act, vp]),
     "mimo_unpack_nchw": (i32, [Act, vp, vp]),

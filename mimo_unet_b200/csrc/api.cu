@@ -84,6 +84,11 @@ int mimo_upsample_bilinear2x(mimo_act_t in, mimo_act_t out, void* stream) {
   return upsample_launch(make_view(in), make_view(out), (cudaStream_t)stream);
 }
 
+int mimo_upsample_concat(mimo_act_t in, mimo_act_t skip, mimo_act_t out, void* stream) {
+  MIMO_CHECK(in.ptr && skip.ptr && out.ptr, MIMO_ERR_ARG, "upsample_concat: null pointer");
+  return upsample_concat_launch(make_view(in), make_view(skip), make_view(out), (cudaStream_t)stream);
+}
+
 int mimo_maxunpool2x2(mimo_act_t in, const long long* idx_nchw, mimo_act_t out, void* stream) {
   MIMO_CHECK(in.ptr && idx_nchw && out.ptr, MIMO_ERR_ARG, "maxunpool: null pointer");
   return maxunpool_launch(make_view(in), idx_nchw, make_view(out), (cudaStream_t)stream);

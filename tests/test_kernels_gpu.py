@@ -394,6 +394,34 @@ def test_upsample_into_concat_slice(lib, C_, c_off, cpitch):
         assert torch.all(rest == sentinel)
 
 
+@pytest.mark.parametrize("f,cup,cpitch", [(21, 42, 64), (30, 60, 96), (8, 16, 24), (16, 16, 32), (5, 3, 8), (21, 84, 112)])
+@pytest.mark.parametrize("H,W,extra", [(5, 7, 1), (3, 3, 0), (8, 6, 0)])
+def test_upsample_concat_whole_lines(lib, f, cup, cpitch, H, W, extra):
+    """Decoder concat in one pass (components.py:110-119): skip channels copied from a dense buffer, up-sampled channels funnel-shifted
+    behind them (f % 8 = 5, 6, 0 ... covers the shifted and the aligned word layouts), pad channels zero, reflect halo written."""
+    torch.manual_seed(13)
+    N = 2
+    x = bf16r(torch.randn(N, cup, H, W, device="cuda"))
+    xb = make_buffer(N, H, W, 1, p8(cup))
+    put_nchw(xb, x, 1)
+    OH, OW = 2 * H, 2 * W + extra
+    skip = bf16r(torch.randn(N, f, OH, OW, device="cuda"))
+    sb = make_buffer(N, OH, OW, 0, p8(f))          # pad channels keep the NaN fill: they must not leak into the output
+    put_nchw(sb, skip, 0)
+    ob = make_buffer(N, OH, OW, 1, cpitch)
+    _lib.check(lib.mimo_upsample_concat(act_of(xb, 1, 0, cup), act_of(sb, 0, 0, f), act_of(ob, 1, 0, f + cup), stream()))
+    ref = torch.cat([skip, bf16r(O.pad_to(O.upsample_bilinear2x_ac(x), OH, OW))], 1)
+    got = get_nchw(ob, 1, 0, f + cup, with_halo=True)
+    assert torch.equal(got[:, :f, 1:-1, 1:-1], skip)                       # copied bit for bit
+    assert rel_l2(got[:, f:, 1:-1, 1:-1], ref[:, f:]) <= TOL
+    assert torch.equal(got, F.pad(got[:, :, 1:-1, 1:-1], (1, 1, 1, 1), mode="reflect"))
+    assert torch.all(ob[..., f + cup:] == 0)                                # pad channels of the pitch
+    # the same values as the two-step path (up-sampling into the slice)
+    ob2 = make_buffer(N, OH, OW, 1, cpitch, fill=0.0)
+    _lib.check(lib.mimo_upsample_bilinear2x(act_of(xb, 1, 0, cup), act_of(ob2, 1, f, cup), stream()))
+    assert torch.equal(get_nchw(ob2, 1, f, cup), got[:, f:, 1:-1, 1:-1])
+
+
 @pytest.mark.parametrize("H,W", [(8, 10), (9, 11), (3, 3)])
 def test_grad_gather_fold_and_pool_bwd(lib, H, W):
     torch.manual_seed(7)
