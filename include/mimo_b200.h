@@ -271,6 +271,11 @@ int mimo_unet_backward_stage_first_state(const mimo_unet_plan_t* plan, int stage
 /* test hook: geometry of a named intermediate ("<node>.<buf>", e.g. "core.down2.c1.y") inside the workspace.
  * kind: 0 = bf16 activation view, 1 = fp32 vector of view->c floats. */
 int mimo_unet_debug_view(const mimo_unet_plan_t* plan, const char* name, mimo_act_t* view, int* kind);
+/* Channel layout of the subnetwork stack cat(x2_0, ..., x2_{S-1}) (model.py:113) at the head of the core's input and of core.up3's
+ * concat buffer: n_slices slices of slice_len channels, slice_stride apart (8-channel aligned; gap channels are zero). The views
+ * "core.down2.in", "core.up3.in" and their ".c1.dpad" gradients of mimo_unet_debug_view are in this physical order.
+ * n_slices == 0: no gaps. */
+int mimo_unet_stack_layout(const mimo_unet_plan_t* plan, int* slice_len, int* slice_stride, int* n_slices);
 /* number of kernels the last forward / backward enqueued (bench.py's gpu_launches) */
 int mimo_unet_last_launches(const mimo_unet_plan_t* plan);
 /* CUDA graphs of the executor's fixed launch sequences (built after two eager calls per plan; env MIMO_GRAPH=0 disables):

@@ -109,6 +109,7 @@ SIGNATURES = {
     "mimo_unet_forward": (i32, [vp, vp, vp, i32, C.POINTER(vp), vp, vp]),
     "mimo_unet_backward": (i32, [vp, vp, vp, vp, i32, vp]),
     "mimo_unet_debug_view": (i32, [vp, C.c_char_p, ActP, C.POINTER(i32)]),
+    "mimo_unet_stack_layout": (i32, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "mimo_unet_set_inference_fusion": (i32, [vp, i32]),
     "mimo_unet_set_backward_events": (i32, [vp, C.POINTER(C.c_void_p)]),
     "mimo_unet_backward_stage_first_state": (i32, [vp, i32]),

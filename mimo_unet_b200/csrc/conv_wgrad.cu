@@ -202,7 +202,7 @@ __global__ void wgrad_unpack_batched_kernel(const UnpackBatch b, float scale, in
     const int tap = i % 9;
     const int ci = (i / 9) % q.cin;
     const int co = i / (9 * q.cin);
-    const float v = q.packed[((size_t)tap * q.cout + co) * q.cin_pitch + ci] * scale;
+    const float v = q.packed[((size_t)tap * q.cout + co) * q.cin_pitch + q.sl.position(ci)] * scale;
     q.grad[i] = accumulate ? q.grad[i] + v : v;
   }
 }

@@ -152,17 +152,19 @@ __global__ void weight_pack_batched_kernel(const PackBatch b) {
   const WeightPackJob& q = b.job[j];
   const int nblk = b.first_block[j + 1] - b.first_block[j];
   const int cout = q.cout, cin = q.cin, cin_pitch = q.cin_pitch, cout_pitch = q.cout_pitch;
+  const int cin_phys = q.sl.phys_count(cin);
   const int total_f = 9 * cout * cin_pitch;
-  const int total_d = q.wd ? 9 * cin * cout_pitch : 0;
+  const int total_d = q.wd ? 9 * cin_phys * cout_pitch : 0;
   for (int i = ((int)blockIdx.x - b.first_block[j]) * blockDim.x + threadIdx.x; i < total_f + total_d; i += nblk * blockDim.x) {
     if (i < total_f) {
       const int cp = i % cin_pitch, co = (i / cin_pitch) % cout, tap = i / (cin_pitch * cout);
-      const int ci = cp < q.gap_at || q.gap == 0 ? cp : (cp >= q.gap_at + q.gap ? cp - q.gap : cin);   // cin = "zero" marker
-      q.wf[i] = __float2bfloat16_rn(ci < cin ? q.w[((size_t)co * cin + ci) * 9 + tap] : 0.f);
+      const int ci = q.sl.source(cp, cin);
+      q.wf[i] = __float2bfloat16_rn(ci >= 0 ? q.w[((size_t)co * cin + ci) * 9 + tap] : 0.f);
     } else {
       const int k = i - total_f;
-      const int co = k % cout_pitch, ci = (k / cout_pitch) % cin, tap = k / (cout_pitch * cin);
-      q.wd[k] = __float2bfloat16_rn(co < cout ? q.w[((size_t)co * cin + ci) * 9 + (8 - tap)] : 0.f);
+      const int co = k % cout_pitch, cp = (k / cout_pitch) % cin_phys, tap = k / (cout_pitch * cin_phys);
+      const int ci = q.sl.source(cp, cin);
+      q.wd[k] = __float2bfloat16_rn(co < cout && ci >= 0 ? q.w[((size_t)co * cin + ci) * 9 + (8 - tap)] : 0.f);
     }
   }
 }

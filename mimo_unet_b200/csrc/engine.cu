@@ -47,6 +47,8 @@ struct ConvL {
   size_t wf = 0, wd = 0, psum = 0, psq = 0, vec = 0 /* scale,shift,mean,invstd,s1,s2: 6*cout_p floats */, bnpart = 0, dwp = 0;
   int y = -1, dy = -1, dpad = -1;  // Buf ids: raw output, its gradient, padded-domain input gradient
   size_t wf_v = 0; int cin_pv = 0; // inference-only weight pack in the chunk-aligned channel order of a virtual concat (decoders)
+  int cin_x = 0;                   // PHYSICAL input channels (>= cin): the input buffer may keep its leading subnetwork slices 8-aligned
+  ChannelSlices sl{0, 0, 0};       // ... with this layout (sl_n == 0: cin_x == cin)
 };
 
 struct Node {  // one DoubleConv
@@ -80,6 +82,7 @@ struct mimo_unet_plan {
                                          // concat kernel merges it with the up-sampled core output into whole lines of dcat[s]
   bool last_dense_skip = false;          // the last forward wrote x1_s into x1d (backward reads the pooling winners from there)
   int cat3 = -1, cat2 = -1, cat1 = -1, pxc = -1, px3 = -1, px4 = -1, x5 = -1, u1 = -1, u2 = -1, u3 = -1;
+  int stack_c = 0;   // physical channels of the subnetwork stack at the head of cat3 / pxc (S * round_up(2f, 8), or c)
   int upd = -1;   // inference: the up-sampled core output shared by all decoders (virtual concat), -1 when not used
   int g_xc = -1, g_x3 = -1, g_x4 = -1, g_x5 = -1, g_u1 = -1, g_u2 = -1, g_u3 = -1;
   int gp_xc = -1, gp_x3 = -1, gp_x4 = -1;  // pooled-map gradients
@@ -152,28 +155,29 @@ ActView view_of(const mimo_unet_plan* P, int buf, int c_off, int C) {
 }
 ActView view_of(const mimo_unet_plan* P, const View& v) { return view_of(P, v.buf, v.c_off, v.C); }
 
-void setup_conv(mimo_unet_plan* P, Arena& A, ConvL& c, int cin, int cout, int N, int H, int W, int& state_cursor) {
-  c.cin = cin; c.cout = cout; c.cin_p = p8(cin); c.cout_p = p8(cout); c.N = N; c.H = H; c.W = W;
+void setup_conv(mimo_unet_plan* P, Arena& A, ConvL& c, int cin, int cout, int N, int H, int W, int& state_cursor,
+                ChannelSlices sl = ChannelSlices{0, 0, 0}) {
+  c.cin = cin; c.cout = cout; c.sl = sl; c.cin_x = sl.phys_count(cin); c.cin_p = p8(c.cin_x); c.cout_p = p8(cout); c.N = N; c.H = H; c.W = W;
   c.state0 = state_cursor;
   state_cursor += 7;
   c.m_tiles = conv3x3_stat_rows();
   c.wf = A.take((size_t)9 * cout * c.cin_p * sizeof(bf16));
-  c.wd = A.take((size_t)9 * cin * c.cout_p * sizeof(bf16));
+  c.wd = A.take((size_t)9 * c.cin_x * c.cout_p * sizeof(bf16));
   c.psum = A.take((size_t)c.m_tiles * c.cout_p * sizeof(float));
   c.psq = A.take((size_t)c.m_tiles * c.cout_p * sizeof(float));
   c.vec = A.take((size_t)6 * c.cout_p * sizeof(float));
   c.bnpart = A.take((size_t)bn_bwd_parts(cout) * 2 * cout * sizeof(float));
   c.y = add_buf(P, A, N, H, W, 0, cout);
   c.dy = add_buf(P, A, N, H, W, 2, cout);  // zero-tail layout: read by the flat dgrad / wgrad kernels
-  c.dpad = add_buf(P, A, N, H + 2, W + 2, 0, cin);
+  c.dpad = add_buf(P, A, N, H + 2, W + 2, 0, c.cin_x);
 }
 
 int add_node(mimo_unet_plan* P, Arena& A, const std::string& name, View in, int cin, int cmid, int cout, View out, View pool,
-             int level, int& state_cursor) {
+             int level, int& state_cursor, ChannelSlices in_slices = ChannelSlices{0, 0, 0}) {
   Node n;
   n.name = name;
   const int N = P->cfg.batch, H = P->Hs[level], W = P->Ws[level];
-  setup_conv(P, A, n.c1, cin, cmid, N, H, W, state_cursor);
+  setup_conv(P, A, n.c1, cin, cmid, N, H, W, state_cursor, in_slices);
   setup_conv(P, A, n.c2, cmid, cout, N, H, W, state_cursor);
   n.in = in;
   n.a1 = add_buf(P, A, N, H, W, 1, cmid);
@@ -360,11 +364,11 @@ int conv_bn_backward(mimo_unet_plan* P, ConvL& c, const ActView& G, const ActVie
   ++P->launches; ++P->launches;  // bn_bwd is three kernels
   if (P->grads[c.state0] != nullptr) {
     RUN(kConvWgrad, conv3x3_wgrad_launch(dyv, in, fptr(P, c.dwp), c.cin_p, st, true));
-    P->unpack_jobs.push_back({fptr(P, c.dwp), (float*)P->grads[c.state0], c.cout, c.cin, c.cin_p});  // flushed per stage
+    P->unpack_jobs.push_back({fptr(P, c.dwp), (float*)P->grads[c.state0], c.cout, c.cin, c.cin_p, c.sl});  // flushed per stage
   }
   if (need_in_grad) {
     bf16* dpad = bptr(P, P->bufs[c.dpad].off);
-    RUN(kConvDgrad, conv3x3_launch(dyv, 1, bptr(P, c.wd), c.cin, c.cout_p, dpad, c.cin_p, nullptr, nullptr, nullptr, 0, st));
+    RUN(kConvDgrad, conv3x3_launch(dyv, 1, bptr(P, c.wd), c.cin_x, c.cout_p, dpad, c.cin_p, nullptr, nullptr, nullptr, 0, st));
   }
   return MIMO_OK;
 }
@@ -442,13 +446,22 @@ int mimo_unet_plan_create(const mimo_unet_config_t* cfg, mimo_unet_plan_t** out)
     P->g_x1.push_back(buf(0, 0, f));
     P->x1d.push_back(buf(0, 0, f));
   }
-  P->cat3 = buf(1, 1, 2 * c); P->pxc = buf(2, 1, c);
+  // The subnetwork stack [x2_0 | x2_1 | ...] (2f channels each) leads cat3 and pxc. With 2f % 8 != 0 (f = 21: 42) every slice but the
+  // first would start at a channel offset that is not 16-byte aligned: scalar stores in bn_relu_apply, unaligned loads in the BatchNorm
+  // backward and no fused inference epilogue for those subnetworks. So the slices sit round_up(2f, 8) apart (gap channels stay
+  // zero), and the two convolutions that read the stack (core.down2.c1, core.up3.c1) get weights packed in that order (ChannelSlices).
+  static const int aligned_on = getenv("MIMO_ALIGNED_STACK") ? atoi(getenv("MIMO_ALIGNED_STACK")) : 1;
+  const int sp = (aligned_on && S > 1) ? round_up(2 * f, 8) : 2 * f;   // slice stride
+  const int cs = S * sp;                                                // physical width of the stack (c = S * 2f logical)
+  const ChannelSlices stack = sp != 2 * f ? ChannelSlices{2 * f, sp, S} : ChannelSlices{0, 0, 0};
+  P->stack_c = cs;
+  P->cat3 = buf(1, 1, cs + c); P->pxc = buf(2, 1, cs);
   P->cat2 = buf(2, 1, 4 * c); P->px3 = buf(3, 1, 2 * c);
   P->cat1 = buf(3, 1, 8 * c); P->px4 = buf(4, 1, 4 * c);
   P->x5 = buf(4, 1, 4 * c); P->u1 = buf(3, 1, 2 * c); P->u2 = buf(2, 1, c); P->u3 = buf(1, 1, c / 2);
-  P->g_xc = buf(1, 0, c); P->g_x3 = buf(2, 0, 2 * c); P->g_x4 = buf(3, 0, 4 * c); P->g_x5 = buf(4, 0, 4 * c);
+  P->g_xc = buf(1, 0, cs); P->g_x3 = buf(2, 0, 2 * c); P->g_x4 = buf(3, 0, 4 * c); P->g_x5 = buf(4, 0, 4 * c);
   P->g_u1 = buf(3, 0, 2 * c); P->g_u2 = buf(2, 0, c); P->g_u3 = buf(1, 0, c / 2);
-  P->gp_xc = buf(2, 0, c); P->gp_x3 = buf(3, 0, 2 * c); P->gp_x4 = buf(4, 0, 4 * c);
+  P->gp_xc = buf(2, 0, cs); P->gp_x3 = buf(3, 0, 2 * c); P->gp_x4 = buf(4, 0, 4 * c);
   P->tmp0 = buf(0, 0, c / 2); P->tmp1 = buf(1, 0, c); P->tmp2 = buf(2, 0, 2 * c); P->tmp3 = buf(3, 0, 4 * c);
 
   int cur = 0;
@@ -463,12 +476,12 @@ int mimo_unet_plan_create(const mimo_unet_config_t* cfg, mimo_unet_plan_t** out)
     P->enc_in.push_back(ni);
   }
   for (int s = 0; s < S; ++s) {
-    int ni = add_node(P, A, "encoder.down1s." + std::to_string(s), V(P->p1[s], 0, f), f, 2 * f, 2 * f, V(P->cat3, 2 * f * s, 2 * f),
-                      V(P->pxc, 2 * f * s, 2 * f), 1, cur);
-    P->nodes[ni].g2 = V(P->g_xc, 2 * f * s, 2 * f);
+    int ni = add_node(P, A, "encoder.down1s." + std::to_string(s), V(P->p1[s], 0, f), f, 2 * f, 2 * f, V(P->cat3, sp * s, 2 * f),
+                      V(P->pxc, sp * s, 2 * f), 1, cur);
+    P->nodes[ni].g2 = V(P->g_xc, sp * s, 2 * f);
     P->enc_down.push_back(ni);
   }
-  P->down2 = add_node(P, A, "core.down2", V(P->pxc, 0, c), c, 2 * c, 2 * c, V(P->cat2, 0, 2 * c), V(P->px3, 0, 2 * c), 2, cur);
+  P->down2 = add_node(P, A, "core.down2", V(P->pxc, 0, cs), c, 2 * c, 2 * c, V(P->cat2, 0, 2 * c), V(P->px3, 0, 2 * c), 2, cur, stack);
   P->nodes[P->down2].g2 = V(P->g_x3, 0, 2 * c);
   P->down3 = add_node(P, A, "core.down3", V(P->px3, 0, 2 * c), 2 * c, 4 * c, 4 * c, V(P->cat1, 0, 4 * c), V(P->px4, 0, 4 * c), 3, cur);
   P->nodes[P->down3].g2 = V(P->g_x4, 0, 4 * c);
@@ -478,7 +491,7 @@ int mimo_unet_plan_create(const mimo_unet_config_t* cfg, mimo_unet_plan_t** out)
   P->nodes[P->up1].g2 = V(P->g_u1, 0, 2 * c);
   P->up2 = add_node(P, A, "core.up2", V(P->cat2, 0, 4 * c), 4 * c, 2 * c, c, V(P->u2, 0, c), none, 2, cur);
   P->nodes[P->up2].g2 = V(P->g_u2, 0, c);
-  P->up3 = add_node(P, A, "core.up3", V(P->cat3, 0, 2 * c), 2 * c, c, c / 2, V(P->u3, 0, c / 2), none, 1, cur);
+  P->up3 = add_node(P, A, "core.up3", V(P->cat3, 0, cs + c), 2 * c, c, c / 2, V(P->u3, 0, c / 2), none, 1, cur, stack);
   P->nodes[P->up3].g2 = V(P->g_u3, 0, c / 2);
   const int d = c / 2 + f;
   for (int s = 0; s < S; ++s) {
@@ -646,11 +659,12 @@ int mimo_unet_forward(mimo_unet_plan_t* P, const float* x, const long long* gath
       std::vector<WeightPackJob> jobs;
       for (auto& n : P->nodes)
         for (ConvL* cl : {&n.c1, &n.c2})
-          jobs.push_back({(const float*)P->state[cl->state0], bptr(P, cl->wf), bptr(P, cl->wd), cl->cout, cl->cin, cl->cin_p, cl->cout_p, 0, 0});
+          jobs.push_back({(const float*)P->state[cl->state0], bptr(P, cl->wf), bptr(P, cl->wd), cl->cout, cl->cin, cl->cin_p, cl->cout_p, cl->sl});
       if (virt)   // chunk-aligned packs of the decoders' first conv: [x1_s (f, padded to 64) | up (c/2)]
         for (int s2 = 0; s2 < S; ++s2) {
           ConvL& cl = P->nodes[P->dec[s2]].c1;
-          jobs.push_back({(const float*)P->state[cl.state0], bptr(P, cl.wf_v), nullptr, cl.cout, cl.cin, cl.cin_pv, cl.cout_p, f, round_up(f, 64) - f});
+          jobs.push_back({(const float*)P->state[cl.state0], bptr(P, cl.wf_v), nullptr, cl.cout, cl.cin, cl.cin_pv, cl.cout_p,
+                          ChannelSlices{f, round_up(f, 64), 1}});
         }
       RUN(kPackW, weight_pack_batched_launch(jobs.data(), (int)jobs.size(), st));
     }
@@ -673,7 +687,7 @@ int mimo_unet_forward(mimo_unet_plan_t* P, const float* x, const long long* gath
     if ((rc = node_forward(P, P->up1, tr, mask(P->up1), st))) return rc;
     RUN(kUpsample, upsample_launch(view_of(P, P->u1, 0, 2 * c), view_of(P, P->cat2, 2 * c, 2 * c), st));
     if ((rc = node_forward(P, P->up2, tr, mask(P->up2), st))) return rc;
-    RUN(kUpsample, upsample_launch(view_of(P, P->u2, 0, c), view_of(P, P->cat3, c, c), st));
+    RUN(kUpsample, upsample_launch(view_of(P, P->u2, 0, c), view_of(P, P->cat3, P->stack_c, c), st));
     if ((rc = node_forward(P, P->up3, tr, mask(P->up3), st))) return rc;
     if (virt) RUN(kUpsample, upsample_launch(view_of(P, P->u3, 0, c / 2), view_of(P, P->upd, 0, c / 2), st));
     for (int s = 0; s < S; ++s) {
@@ -781,7 +795,7 @@ int mimo_unet_backward(mimo_unet_plan_t* P, const float* dout, const float* grad
     P->unpack_jobs.clear();
     if ((rc = node_backward(P, P->up3, tr, mask(P->up3), accumulate, st))) return rc;
     {
-      const ActView dp = view_of(P, P->nodes[P->up3].c1.dpad, c, c);
+      const ActView dp = view_of(P, P->nodes[P->up3].c1.dpad, P->stack_c, c);   // the up-sampled part follows the (aligned) stack
       const ActView t = view_of(P, P->tmp1, 0, c);
       RUN(kGradGather, grad_gather_launch(&dp, nullptr, nullptr, t, 0, st));
       RUN(kUpsampleBwd, upsample_bwd_launch(t, view_of(P, P->g_u2, 0, c), 0, st));
@@ -827,12 +841,14 @@ int mimo_unet_backward(mimo_unet_plan_t* P, const float* dout, const float* grad
     }
     if ((rc = node_backward(P, P->down2, tr, mask(P->down2), accumulate, st))) return rc;
     {
-      const ActView dpp = view_of(P, P->nodes[P->down2].c1.dpad, 0, c);
-      const ActView gp = view_of(P, P->gp_xc, 0, c);
+      // the whole physical stack (gap channels carry zeros on every operand: zero weight rows, zero-initialised buffers)
+      const int cs = P->stack_c;
+      const ActView dpp = view_of(P, P->nodes[P->down2].c1.dpad, 0, cs);
+      const ActView gp = view_of(P, P->gp_xc, 0, cs);
       RUN(kGradGather, grad_gather_launch(&dpp, nullptr, nullptr, gp, 0, st));
-      const ActView dskip = view_of(P, P->nodes[P->up3].c1.dpad, 0, c);
-      const ActView act = view_of(P, P->cat3, 0, c);
-      RUN(kGradGather, grad_gather_launch(&dskip, &gp, &act, view_of(P, P->g_xc, 0, c), 0, st));
+      const ActView dskip = view_of(P, P->nodes[P->up3].c1.dpad, 0, cs);
+      const ActView act = view_of(P, P->cat3, 0, cs);
+      RUN(kGradGather, grad_gather_launch(&dskip, &gp, &act, view_of(P, P->g_xc, 0, cs), 0, st));
     }
     return flush_unpack();
   };
@@ -913,6 +929,13 @@ int mimo_unet_backward_stage_first_state(const mimo_unet_plan_t* P, int stage) {
   return P->nodes[P->dec[0]].c1.state0;
 }
 
+int mimo_unet_stack_layout(const mimo_unet_plan_t* P, int* slice_len, int* slice_stride, int* n_slices) {
+  MIMO_CHECK(P && slice_len && slice_stride && n_slices, MIMO_ERR_ARG, "stack_layout: null argument");
+  const ChannelSlices& sl = P->nodes[P->down2].c1.sl;
+  *slice_len = sl.sl_len; *slice_stride = sl.sl_stride; *n_slices = sl.sl_n;
+  return MIMO_OK;
+}
+
 int mimo_unet_debug_view(const mimo_unet_plan_t* P, const char* name, mimo_act_t* view, int* kind) {
   MIMO_CHECK(P && name && view && kind, MIMO_ERR_ARG, "debug_view: null argument");
   MIMO_CHECK(P->bound, MIMO_ERR_STATE, "debug_view: plan is not bound");
@@ -938,7 +961,7 @@ int mimo_unet_debug_view(const mimo_unet_plan_t* P, const char* name, mimo_act_t
   if (cl) {
     if (what == "y") fill(view_of(P, cl->y, 0, cl->cout));
     else if (what == "dy") fill(view_of(P, cl->dy, 0, cl->cout));
-    else if (what == "dpad") fill(view_of(P, cl->dpad, 0, cl->cin));
+    else if (what == "dpad") fill(view_of(P, cl->dpad, 0, cl->cin_x));
     else {
       const int k = what == "scale" ? 0 : what == "shift" ? 1 : what == "mean" ? 2 : 3;
       *kind = 1;

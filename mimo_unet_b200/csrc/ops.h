@@ -43,10 +43,32 @@ bool conv3x3_wgrad_flatk_ok(const ActView& dy, const ActView& x);
 int conv3x3_wgrad_flatk_launch(const ActView& dy, const ActView& x, float* dw_packed, int cin_pitch, cudaStream_t stream, bool pre_zeroed = false);
 // batched variants: one launch for many layers (the per-layer kernels are a few microseconds each; their launch gaps
 // cost more than their work)
-// gap_at/gap (fprop pack only): packed input channel c' holds source channel c' (c' < gap_at) or c' - gap (c' >= gap_at + gap), zeros in
-// between: the chunk-aligned channel order of a virtual concat (conv3x3_c2_launch with a second input view)
-struct WeightPackJob { const float* w; bf16* wf; bf16* wd; int cout, cin, cin_pitch, cout_pitch; int gap_at, gap; };
-struct WgradUnpackJob { const float* packed; float* grad; int cout, cin, cin_pitch; };
+// Input-channel layout of a packed weight (ChannelSlices): the first sl_n * sl_len source channels are sl_n slices of sl_len channels
+// that sit sl_stride apart in the packed / physical order (zeros in the gaps), the remaining channels follow at sl_n * sl_stride.
+// sl_n == 0: identity. Two users: the chunk-aligned order of a virtual concat (one slice of in.C channels padded to a multiple of 64,
+// conv3x3_c2_launch with a second input view) and the 8-channel-aligned subnetwork slices of the stacked buffers (S slices of 2f
+// channels, stride round_up(2f, 8)).
+struct ChannelSlices {
+  int sl_len, sl_stride, sl_n;
+  __host__ __device__ int phys_count(int cin) const { return sl_n == 0 ? cin : sl_n * sl_stride + (cin - sl_n * sl_len); }
+  // physical position -> source channel, or -1 for a gap
+  __host__ __device__ int source(int cp, int cin) const {
+    if (sl_n == 0) return cp < cin ? cp : -1;
+    if (cp < sl_n * sl_stride) { const int s = cp / sl_stride, r = cp - s * sl_stride; return r < sl_len ? s * sl_len + r : -1; }
+    const int ci = sl_n * sl_len + (cp - sl_n * sl_stride);
+    return ci < cin ? ci : -1;
+  }
+  // source channel -> physical position
+  __host__ __device__ int position(int ci) const {
+    if (sl_n == 0 || ci >= sl_n * sl_len) return sl_n == 0 ? ci : sl_n * sl_stride + (ci - sl_n * sl_len);
+    const int s = ci / sl_len;
+    return s * sl_stride + (ci - s * sl_len);
+  }
+};
+// wf: [9][cout][cin_pitch] over PHYSICAL input positions; wd (may be null): [9][phys_count(cin)][cout_pitch], rows at physical positions
+struct WeightPackJob { const float* w; bf16* wf; bf16* wd; int cout, cin, cin_pitch, cout_pitch; ChannelSlices sl; };
+// packed: fp32 [9][cout][cin_pitch] over physical input positions -> grad OIHW [cout][cin][3][3]
+struct WgradUnpackJob { const float* packed; float* grad; int cout, cin, cin_pitch; ChannelSlices sl; };
 int weight_pack_batched_launch(const WeightPackJob* jobs, int n, cudaStream_t st);
 int wgrad_unpack_batched_launch(const WgradUnpackJob* jobs, int n, float scale, int accumulate, cudaStream_t st);
 int conv3x3_wgrad_flatk_schedule(int cout, int cin, long long total_pos, int sms, int cta, int* out, int max_segs);

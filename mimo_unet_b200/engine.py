@@ -125,6 +125,20 @@ class UNetPlan:
         return int(self.lib.mimo_unet_last_launches(self.handle))
 
     # -- test hook -----------------------------------------------------------------------------
+    _STACKED = ("core.down2.in", "core.up3.in", "core.down2.c1.dpad", "core.up3.c1.dpad")
+
+    def _logical_channels(self, name: str, t: torch.Tensor) -> torch.Tensor:
+        """The buffers that start with the subnetwork stack keep its slices 8-channel aligned (mimo_unet_stack_layout): drop the gap
+        channels so that callers see the reference's channel order."""
+        if name not in self._STACKED:
+            return t
+        ln, st, n = C.c_int(), C.c_int(), C.c_int()
+        check(self.lib.mimo_unet_stack_layout(self.handle, C.byref(ln), C.byref(st), C.byref(n)), "mimo_unet_stack_layout")
+        if n.value == 0:
+            return t
+        idx = [s * st.value + r for s in range(n.value) for r in range(ln.value)] + list(range(n.value * st.value, t.shape[1]))
+        return t[:, torch.tensor(idx, device=t.device)].contiguous()
+
     def debug_tensor(self, name: str) -> torch.Tensor:
         """Returns an fp32 NCHW copy of a named intermediate (interior only) or an fp32 vector."""
         a = Act()
@@ -140,7 +154,7 @@ class UNetPlan:
         nbytes = a.n * Hp * Wp * a.cpitch * 2
         t = self.workspace[off: off + nbytes].view(torch.bfloat16).view(a.n, Hp, Wp, a.cpitch)
         t = t[:, o: o + a.h, o: o + a.w, a.c_off: a.c_off + a.c]
-        return t.permute(0, 3, 1, 2).float().contiguous()
+        return self._logical_channels(name, t.permute(0, 3, 1, 2).float().contiguous())
 
     def debug_tensor_padded(self, name: str) -> torch.Tensor:
         """fp32 NCHW copy including the halo."""
@@ -151,4 +165,4 @@ class UNetPlan:
         e = 2 if a.pad else 0
         Hp, Wp = a.h + e, a.w + e
         t = self.workspace[off: off + a.n * Hp * Wp * a.cpitch * 2].view(torch.bfloat16).view(a.n, Hp, Wp, a.cpitch)
-        return t[..., a.c_off: a.c_off + a.c].permute(0, 3, 1, 2).float().contiguous()
+        return self._logical_channels(name, t[..., a.c_off: a.c_off + a.c].permute(0, 3, 1, 2).float().contiguous())
