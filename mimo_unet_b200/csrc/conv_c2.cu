@@ -17,14 +17,22 @@
 //   A ring      per 64-channel chunk ONE contiguous segment of T*128 + 2*(W+2) + 2 rows per CTA: all nine taps of all T tiles
 //               are row-shifted UMMA windows into it (SWIZZLE_128B is absolute-address based), so every input row is staged
 //               (T*128 + 2*(W+2) + 2) / (T*128) times per chunk instead of three times (one segment per kernel row).
-//   B ring      per (chunk, kh) the three kw taps x (block_n / 2) weight rows per CTA, shared by the T tiles.
+//   B ring      per (chunk, kh) the three kw taps x (block_n / 2) weight rows per CTA, shared by the T tiles -- or, for layers with
+//               at most two K chunks, the whole weight slab of the pair's n-tile RESIDENT in shared memory for the kernel's lifetime
+//               (b_resident: one load, no per-block barrier / commit; the launcher keeps the number of pairs a multiple of the n-tiles).
 //   pipeline    both CTAs' TMA loads signal the LEADER's full barriers (cp.async.bulk.tensor ... .cta_group::2); the leader's
 //               elected thread issues tcgen05.mma.cta_group::2 and frees ring slots in both CTAs with multicast commits;
 //               accumulators are double buffered in TMEM (2 x T x block_n columns), the epilogue warps of both CTAs hand
 //               them back with a (remote) arrive on the leader's barrier.
-//   epilogue    per CTA its own 128 rows per tile: tcgen05.ld -> bf16 -> 16-byte global stores straight from registers;
-//               BatchNorm sum / sum-of-squares of the stored values via the transposed warp butterfly into per-warp
+//   epilogue    8 warps per CTA (two per TMEM lane quarter: even / odd 16-column chunks), chunk-outer / tile-inner: tcgen05.ld of two
+//               tiles in flight -> bf16 -> 16-byte global stores straight from registers; BatchNorm sum / sum-of-squares of the
+//               stored values accumulated over the T tiles in registers, ONE transposed warp butterfly per chunk into per-quarter
 //               shared-memory accumulators (fixed order -> deterministic), one partial row per CTA at the end.
+//   variants    template <DIAG, EPI>: the knock-outs / cycle trace (MIMO_C2_KO, MIMO_C2_TRACE=2) exist only in the DIAG instantiations
+//               (in a one-warp role every parameter test is a constant-bank load + branch on the critical path); EPI = 0 plain store
+//               (dgrad), 1 + statistics (training fprop), 2 generic, 3 fused inference epilogue.
+//   plan        n-tiling, streamed / resident weights, T and the segment mode are chosen per launch by a cost model in cycles
+//               (conv3x3_c2_launch).
 // mode 0 (fprop): in = pad==1 view, output dense [N][H][W]; mode 1 (dgrad): in = pad==2 (zero tail) view of dY, output =
 // padded-domain gradient [N][H+2][W+2].
 #include "common.cuh"

@@ -30,7 +30,7 @@ int conv3x3_c2_launch(const ActView& in, int mode, const bf16* wpacked, int cout
                       const ActView* in2 = nullptr);
 // in2 != nullptr: VIRTUAL CONCAT -- the conv input is cat([in, in2], channels) without the concatenated tensor existing: the K
 // loop reads the 64-channel chunks of `in` and then those of `in2` through separate tensor maps; wpacked must use the chunk-aligned
-// channel order (WeightPackJob gap_at = in.C, gap = round_up(in.C, 64) - in.C), cin_pitch accordingly.
+// channel order (WeightPackJob::sl = ChannelSlices{in.C, round_up(in.C, 64), 1}), cin_pitch accordingly.
 // pre_zeroed: the caller has already cleared dw_packed on `stream` (the executor clears all layers with one memset)
 // CUDA-core kernel of the first layer (<= 4 input channels, <= 32 output channels): conv_thin.cu
 bool conv3x3_thin_ok(const ActView& in, int mode, int cout);
