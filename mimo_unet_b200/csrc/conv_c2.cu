@@ -1,5 +1,6 @@
 // CTA-pair ("c2") tcgen05 implicit-GEMM 3x3 convolution: forward and input-gradient of every layer with more than 64
-// input or output channels (the shared core of the reference U-Net, model.py:190-243, ~72 % of its FLOPs).
+// input or output channels (the shared core of the reference U-Net, model.py:190-243, ~72 % of its FLOPs), and of the
+// small-channel layers where it beats conv3x3_flat_kernel (maps up to 126 columns wide, or > 32 channels: prefer_c2 in conv_igemm.cu).
 //
 // Replaces: nn.Conv2d(k=3, padding=1, padding_mode="reflect") forward (reference components.py:23,26) and its cuDNN dgrad.
 //
