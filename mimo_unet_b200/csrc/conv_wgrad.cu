@@ -192,18 +192,23 @@ __global__ void wgrad_unpack_kernel(const float* __restrict__ packed, float* __r
 constexpr int kMaxBatchJobs = 48;
 struct UnpackBatch { WgradUnpackJob job[kMaxBatchJobs]; int first_block[kMaxBatchJobs + 1]; int n; };
 
+// one index decode per (co, ci) pair, nine taps per thread: 36 contiguous bytes of the OIHW gradient
 __global__ void wgrad_unpack_batched_kernel(const UnpackBatch b, float scale, int accumulate) {
   int j = 0;
   while (j + 1 < b.n && (int)blockIdx.x >= b.first_block[j + 1]) ++j;
   const WgradUnpackJob& q = b.job[j];
   const int nblk = b.first_block[j + 1] - b.first_block[j];
-  const int total = q.cout * q.cin * 9;
-  for (int i = ((int)blockIdx.x - b.first_block[j]) * blockDim.x + threadIdx.x; i < total; i += nblk * blockDim.x) {
-    const int tap = i % 9;
-    const int ci = (i / 9) % q.cin;
-    const int co = i / (9 * q.cin);
-    const float v = q.packed[((size_t)tap * q.cout + co) * q.cin_pitch + q.sl.position(ci)] * scale;
-    q.grad[i] = accumulate ? q.grad[i] + v : v;
+  const int pairs = q.cout * q.cin;
+  const size_t tap_stride = (size_t)q.cout * q.cin_pitch;
+  for (int i = ((int)blockIdx.x - b.first_block[j]) * blockDim.x + threadIdx.x; i < pairs; i += nblk * blockDim.x) {
+    const int co = i / q.cin, ci = i - co * q.cin;
+    const float* src = q.packed + (size_t)co * q.cin_pitch + q.sl.position(ci);
+    float* dst = q.grad + (size_t)i * 9;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const float v = src[tap * tap_stride] * scale;
+      dst[tap] = accumulate ? dst[tap] + v : v;
+    }
   }
 }
 
@@ -284,7 +289,7 @@ int wgrad_unpack_batched_launch(const WgradUnpackJob* jobs, int n, float scale, 
     for (int j = 0; j < b.n; ++j) {
       b.job[j] = jobs[base + j];
       b.first_block[j] = blocks;
-      int nb = ceil_div(jobs[base + j].cout * jobs[base + j].cin * 9, 256 * 4);
+      int nb = ceil_div(jobs[base + j].cout * jobs[base + j].cin, 256);
       if (nb > num_sms()) nb = num_sms();
       blocks += nb < 1 ? 1 : nb;
     }
