@@ -220,6 +220,17 @@ int mimo_ensemble_aggregate(const float* p1, long long p1_bs, long long p1_ss, c
                             long long p2_ss, int batch, int members, long long inner, float* mean, float* aleatoric_var,
                             float* epistemic_var, void* stream);
 
+/* MimoUnetModel.validation_step math (mimo/models/mimo_unet.py:146-183 with LaplaceNLL, losses.py:132-192) in ONE pass over
+ * (p1, p2, label): element (b, s, j) of p1 / p2 at p[b*bs + s*ss + j], j < inner = C*H*W; label / mask (mask may be NULL): the
+ * UN-repeated [batch][inner] tensors (repeat_subnetworks shows every subnetwork the same label). Writes the four [batch][inner] maps
+ * (ensemble mean, aleatoric std, epistemic std, mean - label) and `scalars`: val_loss[members], val_loss_combined, mae, mse, rmse, r2
+ * of (mean, label) (mimo/metrics.py:22-34), mean clip(aleatoric_std, 0, 5), mean clip(epistemic_std, 0, 5)
+ * (members + 7 floats). scratch: mimo_validation_scratch_floats(members) floats. members <= 16. */
+int mimo_validation_scratch_floats(int members);
+int mimo_validation_laplace(const float* p1, const float* p2, long long bs, long long ss, const float* label, const float* mask,
+                            int batch, int members, long long inner, float eps_min, float eps_max, float* mean, float* aleatoric_std,
+                            float* epistemic_std, float* err, float* scratch, float* scalars, void* stream);
+
 /* ------------------------------------------------------------------ whole-network executor ---------------- */
 /* MimoUNet.forward / autograd backward (mimo/models/mimo_components/model.py:94-117), bilinear path. */
 typedef struct {

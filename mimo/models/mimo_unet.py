@@ -105,6 +105,19 @@ class MimoUnetModel(LightningModule):
         label = repeat_subnetworks(label, num_subnetworks=S)
         mask_t = repeat_subnetworks(mask, num_subnetworks=S) if mask is not None else None
         p1, p2 = self(image)
+        if isinstance(self.loss_fn, LaplaceNLL) and p1.is_cuda and S <= 16 and not torch.is_grad_enabled():
+            # one pass over (p1, p2, label): per-subnetwork NLL means, ensemble aggregation, combined-scale NLL, regression
+            # metrics and the clipped std means (reference mimo_unet.py:157-183); the label is NOT repeated for the kernel
+            from mimo_unet_b200 import functional as Fn
+            v = Fn.validation_laplace(p1, p2, batch["label"], mask, self.loss_fn.eps_min, self.loss_fn.eps_max)
+            y_mean = batch["label"].float()
+            self._log_val_loss(v["val_loss"], v["val_loss_combined"])
+            self._log_metrics(y_pred=v["preds"], y_true=y_mean, stage="val", precomputed=v["metrics"])
+            bs = self._batch_size()
+            self.log("metric_val/aleatoric_std_mean", v["aleatoric_std_mean"], batch_size=bs)
+            self.log("metric_val/epistemic_std_mean", v["epistemic_std_mean"], batch_size=bs)
+            return {"loss": v["val_loss"].mean(), "label": y_mean, "preds": v["preds"], "aleatoric_std_map": v["aleatoric_std"],
+                    "epistemic_std_map": v["epistemic_std"], "err_map": v["err"], "mask": mask}
         val_loss = self.loss_fn.forward(p1, p2, label, mask=mask_t, reduce_mean=False).mean(dim=(0, 2, 3, 4))
         y_pred_mean, aleatoric_var, epistemic_var = compute_uncertainties(self.loss_fn, p1, p2)
         y_mean = label.mean(dim=1)

@@ -99,6 +99,8 @@ SIGNATURES = {
     "mimo_evidential_loss_bwd": (i32, [vp, vp, vp, i64, i64, vp, i32, f32, vp, vp]),
     "mimo_scale_by_scalar": (i32, [vp, i64, vp, vp]),
     "mimo_ensemble_aggregate": (i32, [vp, i64, i64, vp, i64, i64, i32, i32, i64, vp, vp, vp, vp]),
+    "mimo_validation_scratch_floats": (i32, [i32]),
+    "mimo_validation_laplace": (i32, [vp, vp, i64, i64, vp, vp, i32, i32, i64, f32, f32, vp, vp, vp, vp, vp, vp, vp]),
     "mimo_unet_plan_create": (i32, [C.POINTER(UnetConfig), C.POINTER(vp)]),
     "mimo_unet_plan_destroy": (None, [vp]),
     "mimo_unet_workspace_bytes": (sz, [vp]),

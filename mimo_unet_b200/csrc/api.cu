@@ -288,4 +288,15 @@ int mimo_ensemble_aggregate(const float* p1, long long p1_bs, long long p1_ss, c
                           (cudaStream_t)stream);
 }
 
+int mimo_validation_scratch_floats(int members) { return validation_scratch_floats(members); }
+
+int mimo_validation_laplace(const float* p1, const float* p2, long long bs, long long ss, const float* label, const float* mask,
+                            int batch, int members, long long inner, float eps_min, float eps_max, float* mean, float* aleatoric_std,
+                            float* epistemic_std, float* err, float* scratch, float* scalars, void* stream) {
+  MIMO_CHECK(p1 && p2 && label && mean && aleatoric_std && epistemic_std && err && scratch && scalars, MIMO_ERR_ARG,
+             "validation_laplace: null pointer");
+  return validation_laplace_launch(p1, p2, bs, ss, label, mask, batch, members, inner, eps_min, eps_max, mean, aleatoric_std,
+                                   epistemic_std, err, scratch, scalars, (cudaStream_t)stream);
+}
+
 }  // extern "C"

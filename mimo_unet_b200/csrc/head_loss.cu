@@ -641,6 +641,110 @@ __global__ void laplace_train_finalize_kernel(const float* __restrict__ part, in
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Validation-step math in ONE pass over (p1, p2, label) (reference mimo_unet.py:146-183 with LaplaceNLL, losses.py:132-192;
+// SURVEY 8 f2): per pixel of [B][inner] (inner = C * H * W) and all S subnetworks
+//   nll_s      = log(clamp(exp(ls_s))) + |mu_s - y| / clamp(exp(ls_s))               (-> val_loss[s] = mean over b, inner)
+//   mean       = sum_s mu_s / S,  alea = sum_s 2 exp(2 ls_s) / S,  epi = sum_s (mu_s - mean)^2 / (S - 1)   (utils.py:76-101)
+//   param      = clamp(sqrt(alea + epi) / sqrt(2)),  nll_c = log(param) + |mean - y| / param                (-> val_loss_combined)
+//   maps       mean, sqrt(alea), sqrt(epi), mean - y;   sums of |e|, e^2, y, y^2 (metrics.py:22-34) and of clip(std, 0, 5)
+// The label is the un-repeated [B][inner] tensor (repeat_subnetworks is a stride-0 view of it: every subnetwork sees the same label).
+// Partials: one row of S + 8 floats per block, combined in a fixed order by validation_finalize_kernel (deterministic).
+// ------------------------------------------------------------------------------------------------
+constexpr int kValExtra = 8;   // combined nll, sum|e|, sum e^2, sum y, sum y^2, sum clip(alea_std), sum clip(epi_std), (spare)
+
+__global__ void __launch_bounds__(256)
+validation_laplace_kernel(const float* __restrict__ p1, const float* __restrict__ p2, long long p_bs, long long p_ss,
+                          const float* __restrict__ y, const float* __restrict__ mask, int B, int S, long long inner, float eps_min,
+                          float eps_max, float* __restrict__ mean_o, float* __restrict__ alea_std_o, float* __restrict__ epi_std_o,
+                          float* __restrict__ err_o, float* __restrict__ part) {
+  extern __shared__ float red[];   // [warps][S + kValExtra]
+  const int nacc = S + kValExtra;
+  float comb = 0.f, sae = 0.f, sse = 0.f, sy = 0.f, syy = 0.f, sal = 0.f, sep = 0.f;
+  float nll_acc[16];
+#pragma unroll
+  for (int s = 0; s < 16; ++s) nll_acc[s] = 0.f;
+  const long long total = (long long)B * inner;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / inner, r = i - b * inner;
+    const float yv = y[i];
+    const float m = mask ? mask[i] : 1.f;
+    const float* q1 = p1 + b * p_bs + r;
+    const float* q2 = p2 + b * p_bs + r;
+    float mu[16], sum = 0.f, al = 0.f;
+#pragma unroll
+    for (int s = 0; s < 16; ++s) {
+      if (s < S) {
+        mu[s] = q1[s * p_ss];
+        const float ls = q2[s * p_ss];
+        const float sc = fminf(fmaxf(expf(ls), eps_min), eps_max);
+        nll_acc[s] += (logf(sc) + fabsf(mu[s] - yv) / sc) * m;
+        sum += mu[s];
+        const float e2 = expf(ls) * 1.41421356237309515f;   // std = exp(log_scale) * sqrt(2), no clamp (losses.py:166-167)
+        al += e2 * e2;
+      }
+    }
+    const float mean = sum / (float)S;
+    al /= (float)S;
+    float ep = 0.f;
+    if (S > 1) {
+#pragma unroll
+      for (int s = 0; s < 16; ++s)
+        if (s < S) { const float d = mu[s] - mean; ep = fmaf(d, d, ep); }
+      ep /= (float)(S - 1);
+    }
+    const float cstd = sqrtf(al + ep);
+    const float param = fminf(fmaxf(cstd / 1.41421356237309515f, eps_min), eps_max);
+    const float e = mean - yv;
+    comb += (logf(param) + fabsf(e) / param) * m;
+    const float as = sqrtf(al), es = sqrtf(ep);
+    mean_o[i] = mean; alea_std_o[i] = as; epi_std_o[i] = es; err_o[i] = e;
+    sae += fabsf(e); sse = fmaf(e, e, sse); sy += yv; syy = fmaf(yv, yv, syy);
+    sal += fminf(fmaxf(as, 0.f), 5.f); sep += fminf(fmaxf(es, 0.f), 5.f);
+  }
+  // block reduction: lanes by shuffle, warps through shared memory in a fixed order
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  auto put = [&](int k, float v) {
+    v = warp_sum(v);
+    if (lane == 0) red[warp * nacc + k] = v;
+  };
+#pragma unroll
+  for (int s = 0; s < 16; ++s)
+    if (s < S) put(s, nll_acc[s]);
+  put(S + 0, comb); put(S + 1, sae); put(S + 2, sse); put(S + 3, sy); put(S + 4, syy); put(S + 5, sal); put(S + 6, sep); put(S + 7, 0.f);
+  __syncthreads();
+  for (int k = threadIdx.x; k < nacc; k += blockDim.x) {
+    float a = 0.f;
+    for (int w = 0; w < nw; ++w) a += red[w * nacc + k];
+    part[(size_t)blockIdx.x * nacc + k] = a;
+  }
+}
+
+// scalars: [S] val_loss, then val_loss_combined, mae, mse, rmse, r2, mean clip(aleatoric_std, 0, 5), mean clip(epistemic_std, 0, 5)
+__global__ void validation_finalize_kernel(const float* __restrict__ part, int nblk, int S, double count, float* __restrict__ scalars) {
+  const int nacc = S + kValExtra;
+  __shared__ double acc[16 + kValExtra];
+  for (int k = threadIdx.x; k < nacc; k += blockDim.x) {
+    double a = 0.0;
+    for (int b = 0; b < nblk; ++b) a += (double)part[(size_t)b * nacc + k];
+    acc[k] = a;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) scalars[s] = (float)(acc[s] / count);
+    const double comb = acc[S], sae = acc[S + 1], sse = acc[S + 2], sy = acc[S + 3], syy = acc[S + 4];
+    scalars[S + 0] = (float)(comb / count);
+    scalars[S + 1] = (float)(sae / count);
+    const double mse = sse / count;
+    scalars[S + 2] = (float)mse;
+    scalars[S + 3] = (float)sqrt(mse);
+    const double ss_tot = syy - sy * sy / count;           // torchmetrics r2_score: 1 - SS_res / SS_tot
+    scalars[S + 4] = (float)(1.0 - sse / ss_tot);
+    scalars[S + 5] = (float)(acc[S + 5] / count);
+    scalars[S + 6] = (float)(acc[S + 6] / count);
+  }
+}
+
 __global__ void lossbuffer_weights_kernel(const LossBufferState* lb, float* w) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     float t[64];
@@ -971,6 +1075,25 @@ int laplace_train_launch(const float* out, const float* y, long long y_bs, long 
   MIMO_LAUNCH_CHECK();
   laplace_train_finalize_kernel<<<1, kBlock, 0, st>>>(part, nblk, B, S, (double)B * (double)n, (LossBufferState*)lb_state, fixed_w,
                                                       update_buffer, loss, weights, weighted, mpart, metrics);
+  MIMO_LAUNCH_CHECK();
+  return MIMO_OK;
+}
+
+int validation_scratch_floats(int S) { return 2 * num_sms() * (S + kValExtra); }
+
+int validation_laplace_launch(const float* p1, const float* p2, long long p_bs, long long p_ss, const float* y, const float* mask, int B,
+                              int S, long long inner, float eps_min, float eps_max, float* mean, float* alea_std, float* epi_std,
+                              float* err, float* scratch, float* scalars, cudaStream_t st) {
+  MIMO_CHECK(S >= 1 && S <= 16, MIMO_ERR_ARG, "validation: 1..16 subnetworks supported (got %d)", S);
+  MIMO_CHECK(B >= 1 && inner >= 1, MIMO_ERR_ARG, "validation: empty input");
+  const long long total = (long long)B * inner;
+  int grid = 2 * num_sms();
+  if ((long long)grid * kBlock > total) grid = (int)((total + kBlock - 1) / kBlock);
+  const size_t smem = (size_t)(kBlock / 32) * (S + kValExtra) * sizeof(float);
+  validation_laplace_kernel<<<grid, kBlock, smem, st>>>(p1, p2, p_bs, p_ss, y, mask, B, S, inner, eps_min, eps_max, mean, alea_std,
+                                                        epi_std, err, scratch);
+  MIMO_LAUNCH_CHECK();
+  validation_finalize_kernel<<<1, 64, 0, st>>>(scratch, grid, S, (double)total, scalars);
   MIMO_LAUNCH_CHECK();
   return MIMO_OK;
 }

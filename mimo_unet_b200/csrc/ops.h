@@ -131,6 +131,10 @@ int laplace_train_launch(const float* out, const float* y, long long y_bs, long 
                          long long m_ss, const long long* gather, int B, int S, int C, long long HW, float eps_min, float eps_max,
                          void* lb_state, const float* fixed_w, int update_buffer, float* dout, float* part, float* loss,
                          float* weights, float* weighted, cudaStream_t st, float* mpart = nullptr, float* metrics = nullptr, int kind = 0);
+int validation_scratch_floats(int S);
+int validation_laplace_launch(const float* p1, const float* p2, long long p_bs, long long p_ss, const float* y, const float* mask, int B,
+                              int S, long long inner, float eps_min, float eps_max, float* mean, float* alea_std, float* epi_std,
+                              float* err, float* scratch, float* scalars, cudaStream_t st);
 int scale_by_scalar_launch(float* x, long long n, const float* s, cudaStream_t st);
 int aggregate_launch(const float* p1, long long p1_bs, long long p1_ss, const float* p2, long long p2_bs, long long p2_ss, int B,
                      int S, long long inner, float* mean, float* alea, float* epi, cudaStream_t st);

@@ -330,3 +330,43 @@ def ensemble_aggregate(p1: torch.Tensor, p2: torch.Tensor):
     check(_lib.lib().mimo_ensemble_aggregate(a.data_ptr(), a_bs, a_ss, b.data_ptr(), b_bs, b_ss, B, S, inner, mean.data_ptr(),
                                              alea.data_ptr(), epi.data_ptr(), stream_ptr()), "mimo_ensemble_aggregate")
     return mean, alea, epi
+
+
+def validation_laplace(p1: torch.Tensor, p2: torch.Tensor, label: torch.Tensor, mask: torch.Tensor = None, eps_min: float = 1e-5,
+                       eps_max: float = 1e3):
+    """The math of MimoUnetModel.validation_step (reference mimo/models/mimo_unet.py:146-183 with LaplaceNLL) in one pass over
+    (p1, p2, label): p1 / p2 [B, S, C, H, W] (location, log-scale), label / mask the UN-repeated [B, C, H, W] tensors.
+    Returns a dict: val_loss [S], val_loss_combined, the maps preds / aleatoric_std / epistemic_std / err ([B, C, H, W]),
+    metrics {mae, mse, rmse, r2} of (preds, label), aleatoric_std_mean / epistemic_std_mean (means of the stds clipped to [0, 5])."""
+    _need_cuda(p1, p2, label)
+    B, S = p1.shape[0], p1.shape[1]
+    inner_shape = tuple(p1.shape[2:])
+    inner = 1
+    for d in inner_shape:
+        inner *= d
+
+    def prep(t):
+        t = t.detach().float()
+        if not t[0, 0].is_contiguous():
+            t = t.contiguous()
+        return t
+
+    a, b = prep(p1), prep(p2)
+    if (a.stride(0), a.stride(1)) != (b.stride(0), b.stride(1)):
+        a, b = a.contiguous(), b.contiguous()
+    y = label.detach().float().contiguous()
+    m = mask.detach().float().contiguous() if mask is not None else None
+    if tuple(y.shape) != (B,) + inner_shape:
+        raise _lib.MimoError(f"validation_laplace: label shape {tuple(y.shape)} != {(B,) + inner_shape}")
+    lib = _lib.lib()
+    maps = [torch.empty((B,) + inner_shape, dtype=torch.float32, device=p1.device) for _ in range(4)]
+    scratch = torch.empty(lib.mimo_validation_scratch_floats(S), dtype=torch.float32, device=p1.device)
+    scalars = torch.empty(S + 7, dtype=torch.float32, device=p1.device)
+    check(lib.mimo_validation_laplace(a.data_ptr(), b.data_ptr(), a.stride(0), a.stride(1), y.data_ptr(),
+                                      m.data_ptr() if m is not None else None, B, S, inner, eps_min, eps_max, maps[0].data_ptr(),
+                                      maps[1].data_ptr(), maps[2].data_ptr(), maps[3].data_ptr(), scratch.data_ptr(), scalars.data_ptr(),
+                                      stream_ptr()), "mimo_validation_laplace")
+    return {"val_loss": scalars[:S], "val_loss_combined": scalars[S], "preds": maps[0], "aleatoric_std": maps[1],
+            "epistemic_std": maps[2], "err": maps[3],
+            "metrics": {"mae": scalars[S + 1], "mse": scalars[S + 2], "rmse": scalars[S + 3], "r2": scalars[S + 4]},
+            "aleatoric_std_mean": scalars[S + 5], "epistemic_std_mean": scalars[S + 6]}

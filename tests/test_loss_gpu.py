@@ -213,3 +213,35 @@ def test_evidential_head_and_loss_vs_oracle():
         assert rel_l2(raw.grad, r64.grad) <= 2e-4    # digamma series + fp32 lgamma against fp64
     assert torch.equal(crit.mode(par), par[:, 0])
     assert rel_l2(crit.aleatoric_var(par), par[:, 3] / (par[:, 2] - 1)) == 0.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("S,C,with_mask", [(2, 1, True), (1, 1, False), (4, 2, True), (16, 1, False)])
+def test_fused_validation_pass_matches_oracle(S, C, with_mask):
+    """MimoUnetModel.validation_step math (reference mimo_unet.py:146-183) in one kernel pass vs the oracle's restatement:
+    per-subnetwork NLL means, ensemble aggregation, combined-scale NLL, the four maps, regression metrics, clipped std means.
+    p1 / p2 are strided views of one [B, S, 2C, H, W] tensor like the module's output; log-scales reach both clamp bounds."""
+    torch.manual_seed(21)
+    B, H, W = 3, 19, 23
+    out = torch.randn(B, S, 2 * C, H, W, device="cuda")
+    out[:, :, C:] = out[:, :, C:] * 4.0              # exp() spans ~1e-7 .. 1e7: both clamps (1e-5, 1e3) are active somewhere
+    label = torch.rand(B, C, H, W, device="cuda")
+    mask = (torch.rand(B, C, H, W, device="cuda") > 0.2).float() if with_mask else None
+    p1, p2 = out[:, :, :C], out[:, :, C:]
+    v = Fn.validation_laplace(p1, p2, label, mask)
+    lab5 = label[:, None].expand(-1, S, -1, -1, -1)
+    vl, comb, mean, alea, epi = O.validation_math(out.cpu().double(), lab5.cpu().double(), None if mask is None else mask.cpu().double())
+    assert rel_l2(v["val_loss"].cpu(), vl.float()) <= 1e-5
+    assert abs(float(v["val_loss_combined"]) - float(comb)) <= 1e-5 * abs(float(comb))
+    assert rel_l2(v["preds"].cpu(), mean.float()) <= 1e-6
+    assert rel_l2(v["aleatoric_std"].cpu(), alea.sqrt().float()) <= 1e-5
+    assert rel_l2(v["epistemic_std"].cpu(), epi.sqrt().float()) <= 1e-5
+    assert rel_l2(v["err"].cpu(), (mean - label.cpu().double()).float()) <= 1e-5
+    e = (mean - label.cpu().double()).flatten()
+    y = label.cpu().double().flatten()
+    ref = {"mae": e.abs().mean(), "mse": (e * e).mean(), "rmse": (e * e).mean().sqrt(),
+           "r2": 1.0 - (e * e).sum() / ((y - y.mean()) ** 2).sum()}
+    for k, r in ref.items():
+        assert abs(float(v["metrics"][k]) - float(r)) <= 1e-4 * max(1.0, abs(float(r))), k
+    assert abs(float(v["aleatoric_std_mean"]) - float(alea.sqrt().clip(0, 5).mean())) <= 1e-4
+    assert abs(float(v["epistemic_std_mean"]) - float(epi.sqrt().clip(0, 5).mean())) <= 1e-4
