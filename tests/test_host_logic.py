@@ -254,3 +254,23 @@ print("ok")
     env = dict(os.environ, PYTHONPATH=root + os.pathsep + REFERENCE_ROOT)
     r = subprocess.run([sys.executable, "-c", code, root, REFERENCE_ROOT], capture_output=True, text=True, env=env, cwd="/tmp")
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_subnetwork_stack_layout_is_8_channel_aligned():
+    """The S subnetwork slices (2f channels each) at the head of the core's input / core.up3's concat buffer start at multiples of
+    round_up(2f, 8) channels (host-only plan creation): no gaps when 2f is already a multiple of 8 or when there is one subnetwork."""
+    import ctypes as C
+    from mimo_unet_b200 import _lib
+    from mimo_unet_b200.engine import UnetConfig
+    lib = _lib.lib()
+    for S, f, expect in ((2, 21, (42, 48, 2)), (4, 21, (42, 48, 4)), (2, 30, (60, 64, 2)), (2, 8, (0, 0, 0)), (1, 21, (0, 0, 0)),
+                         (3, 13, (26, 32, 3))):
+        h = C.c_void_p()
+        c = UnetConfig(3, 2, S, f, 2, 32, 32)
+        _lib.check(lib.mimo_unet_plan_create(C.byref(c), C.byref(h)), "plan_create")
+        try:
+            ln, st, n = C.c_int(), C.c_int(), C.c_int()
+            _lib.check(lib.mimo_unet_stack_layout(h, C.byref(ln), C.byref(st), C.byref(n)), "stack_layout")
+            assert (ln.value, st.value, n.value) == expect, (S, f)
+        finally:
+            lib.mimo_unet_plan_destroy(h)
